@@ -1,0 +1,171 @@
+/* ttg_b200.h — C ABI of libttg_b200.so: the hand-written sm_100a kernels behind
+ * tartangan's GAN training step (SA-GAN / SA-GAN-IQN generator + discriminator,
+ * forward, backward and the double-backward the R1 penalty needs).
+ *
+ * tartangan has no FFI of its own: every arithmetic op on its hot path is an ATen
+ * library call made from Python.  Each entry point below therefore
+ * cites the reference call site (file:line under /root/reference/tartangan) whose
+ * ATen op(s) it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller
+ *     (PyTorch allocates inputs, outputs and workspaces; kernels never allocate,
+ *     never retain pointers past return);
+ *   - activations are NHWC ("channels last"), element type given by a dtype code:
+ *     TTG_F32 = 0, TTG_BF16 = 1; parameters, statistics and losses are fp32;
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes to it, nothing
+ *     synchronises, so all entry points are CUDA-graph capturable and re-entrant;
+ *   - return 0 on success, non-zero on error; ttg_last_error() gives the
+ *     thread-local message.  Unsupported shapes are errors, never fallbacks.
+ */
+#ifndef TTG_B200_H
+#define TTG_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ttg_last_error(void);
+int ttg_version(void);
+int ttg_device_arch(void);
+
+/* ---- convolution: nn.Conv2d k in {1,3}, stride 1, pad k/2
+ * (models/blocks/generator.py:41,44,52,124; discriminator.py:17,63,66,78; attention.py:14-17)
+ * ttg_pack_weight_direct: OIHW fp32 -> [tap][Cin][Cout] (mode 0, fprop) or the flipped,
+ * transposed filter [tap][Cout][Cin] (mode 1, dgrad = fprop with swapped channel roles).
+ * ttg_conv2d_direct: exact fp32-accumulate CUDA-core path (fp32 parity mode, RGB layers).
+ * `up`=1 folds F.interpolate(scale_factor=2, mode='nearest') (generator.py:58) into the
+ * input addressing: x is [N, H/2, W/2, Cin]. */
+int ttg_pack_weight_direct(const float* w, float* wp, int Cout, int Cin, int ksize, int mode, void* stream);
+int ttg_conv2d_direct(const void* x, const float* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                      int Cout, int ksize, int up, int dtype_in, int dtype_out, void* stream);
+int ttg_conv2d_wgrad_direct(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                            int ksize, int up, int dtype_x, int dtype_gy, void* stream);
+
+/* ---- tensor-core convolution (bf16 operands, fp32 accumulate in TMEM, tcgen05.mma)
+ * same reference call sites as above; Cin, Cout multiples of 16.
+ * ttg_pack_weight_tc: OIHW fp32 -> bf16 UMMA B-operand image, mode 0 fprop / 1 dgrad.
+ * ttg_conv2d_tc: y = conv(x) (+bias); optional fused input transform
+ *   a = lrelu((x - mean[c]) * invstd[c] * gamma[c] + beta[c]) (pre_mean != NULL), i.e. the
+ *   BatchNorm2d+LeakyReLU that precedes the conv in every residual block, and optional
+ *   nearest x2 upsample folded into the addressing (up=1).
+ * ttg_conv2d_wgrad_tc: gw (fp32 OIHW) = sum_pixels gy x shifted(x). */
+size_t ttg_pack_weight_tc_bytes(int Cout, int Cin, int ksize);
+int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, int ksize, int mode, void* stream);
+int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                  int ksize, int up, int dtype_out, void* stream);
+int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
+                        int up, void* workspace, void* stream);
+size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);
+
+/* ---- train-mode BatchNorm2d fused with LeakyReLU
+ * (nn.BatchNorm2d + nn.LeakyReLU(0.2) pairs: generator.py:38-43,120-122;
+ *  discriminator.py:60-65,132-135,153-156; eps 1e-5, momentum 0.1, unbiased running var)
+ * workspace: ttg_bn_workspace_bytes(C) bytes. */
+size_t ttg_bn_workspace_bytes(int C);
+int ttg_bn_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* invstd,
+                 float* running_mean, float* running_var, long long* num_batches, void* workspace, int dtype,
+                 void* stream);
+int ttg_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
+                      float* invstd, void* stream);
+int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const float* mean, const float* invstd,
+                   const float* gamma, const float* beta, float slope, int dtype, void* stream);
+int ttg_bn_act_bwd(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
+                   float* gbeta, void* workspace, int dtype, void* stream);
+/* backward of ttg_bn_act_bwd w.r.t. (ga, x, gamma) given u = cotangent of gx: the
+ * NativeBatchNormBackwardBackward0 nodes created by models/losses.py:23-26. */
+int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
+                    const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                    float* ggamma, void* workspace, int dtype, void* stream);
+int ttg_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, void* stream);
+int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n, float slope, int dtype, void* stream);
+/* conv bias gradient: out[c] = sum over rows of x[M,C] */
+int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream);
+
+/* ---- resampling / glue
+ * pool2_sum: nn.AvgPool2d(2) with scale 0.25 (discriminator.py:67); adjoint of upsample2.
+ * upsample2: F.interpolate nearest x2 (generator.py:58); adjoint of pool2_sum.
+ * bilinear_down_*: F.interpolate(scale_factor=0.5, mode='bilinear', align_corners=True)
+ *   (discriminator.py:55-57,92) and its transpose.
+ * axpby: residual add x + h (generator.py:62, discriminator.py:95) and gradient accumulation.
+ * spatial_sum/bcast: torch.sum(feats, [2,3]) (discriminator.py:143,166) and its adjoint. */
+int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream);
+int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream);
+int ttg_bilinear_down_fwd(const void* x, void* y, int N, int Hi, int Wi, int C, int dtype, void* stream);
+int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream);
+int ttg_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int dtype, void* stream);
+int ttg_scale_f32(const float* x, float* out, long long n, float host_scale, const float* dev_scale, void* stream);
+int ttg_spatial_sum(const void* x, float* out, int N, int HW, int C, int dtype, void* stream);
+int ttg_spatial_bcast(const float* g, void* gx, int N, int HW, int C, int dtype, void* stream);
+/* module boundary: reference tensors are fp32 NCHW (trainers/trainer.py:57-61,69-74) */
+int ttg_nchw_to_nhwc(const float* x, void* y, int N, int C, int HW, int dtype, void* stream);
+int ttg_nhwc_to_nchw(const void* x, float* y, int N, int C, int HW, int dtype, void* stream);
+int ttg_cast(const void* x, int src_dtype, void* y, int dst_dtype, long long n, void* stream);
+/* nn.Tanh at the generator output (generator.py:126) */
+int ttg_tanh_fwd(const float* x, float* y, long long n, void* stream);
+int ttg_tanh_bwd(const float* y, const float* g, float* gx, long long n, void* stream);
+
+/* ---- IQN head + losses
+ * ttg_iqn_head_fwd: IQN.forward + CosineQuantileEmbedding.forward + Linear(C->1) + mean over
+ *   quantiles (models/iqn.py:41-46,91-103; blocks/discriminator.py:164-175).  rows r = q*B + b.
+ * ttg_iqn_head_bwd: gradient of p_tau w.r.t. feats, We, be, wo, bo given g[r].
+ * ttg_quantile_huber_*: iqn_loss (models/iqn.py:111-130).
+ * ttg_bce_logits_*: nn.BCEWithLogitsLoss (trainers/cnn.py:88,131,147).
+ * ttg_sqsum_f32: grad_dout.pow(2).view(B,-1).sum(1).mean() (models/losses.py:27-29), scale=1/B. */
+int ttg_iqn_head_fwd(const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                     const float* bo, float* p_tau, float* p_mean, int B, int nq, int C, int E, void* stream);
+int ttg_iqn_head_bwd(const float* g, const float* feats, const float* taus, const float* We, const float* be,
+                     const float* wo, float* gf, float* gWe, float* gbe, float* gwo, float* gbo, int B, int nq,
+                     int C, int E, void* stream);
+int ttg_quantile_huber_fwd(const float* p_tau, const float* target, const float* taus, float* loss, int B, int nq,
+                           float k, void* stream);
+int ttg_quantile_huber_bwd(const float* p_tau, const float* target, const float* taus, const float* gloss,
+                           float* gp, int B, int nq, float k, void* stream);
+int ttg_bce_logits_fwd(const float* x, const float* y, float* loss, int n, void* stream);
+int ttg_bce_logits_bwd(const float* x, const float* y, const float* gloss, float* gx, int n, void* stream);
+int ttg_sqsum_f32(const float* x, long long n, float scale, float* out, void* workspace, void* stream);
+/* nn.Linear (generator.py:71 input MLP, discriminator.py:137 SA-GAN head) and its gradients */
+int ttg_matmul_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA,
+                   int transB, void* stream);
+int ttg_colsum_f32(const float* x, float* out, int M, int N, float scale, void* stream);
+int ttg_rowbcast_f32(const float* g, float* out, int M, int N, float scale, void* stream);
+
+/* ---- optimiser
+ * torch.optim.Adam(betas=(0,0.999)) (trainers/cnn.py:84-85, iqn.py:84-85) over a flat fp32
+ * buffer, with update_target_generator's EMA (cnn.py:158-165) fused in when ema != NULL. */
+int ttg_adam_flat(float* p, const float* g, float* m, float* v, float* ema, long long n, float lr, float beta1,
+                  float beta2, float eps, float ema_lr, float* step, void* stream);
+int ttg_ema_flat(float* target, const float* src, long long n, float lr, void* stream);
+
+/* ---- 2-D self-attention (models/blocks/attention.py:21-35)
+ * maxpool2: F.max_pool2d(.,[2,2]) with argmax bookkeeping; attn_*: softmax(theta^T phi) g. */
+int ttg_maxpool2_fwd(const void* x, void* y, unsigned char* idx, int N, int Ho, int Wo, int C, int dtype, void* stream);
+int ttg_maxpool2_scatter(const void* gy, const unsigned char* idx, void* gx, int N, int Ho, int Wo, int C, int dtype,
+                         void* stream);
+int ttg_maxpool2_gather(const void* x, const unsigned char* idx, void* y, int N, int Ho, int Wo, int C, int dtype,
+                        void* stream);
+int ttg_bmm(const void* A, const void* B, void* C, int batch, int M, int N, int K, int transA, int transB, int dtype,
+            void* stream);
+int ttg_softmax_fwd(const void* x, void* y, long long rows, int cols, int dtype, void* stream);
+int ttg_softmax_bwd(const void* y, const void* gy, void* gx, long long rows, int cols, int dtype, void* stream);
+/* backward of ttg_softmax_bwd given w = cotangent of gx: cot_gy, cot_y (D-side attention under R1) */
+int ttg_softmax_bwd2(const void* y, const void* gy, const void* w, void* cot_gy, void* cot_y, long long rows, int cols,
+                     int dtype, void* stream);
+/* gamma * o (attention.py:35): out = x * (*dev_scale); and the dot product giving d/dgamma */
+int ttg_scale_dev(const void* x, void* out, long long n, const float* dev_scale, int dtype, void* stream);
+int ttg_dot_f32out(const void* a, const void* b, float* out, long long n, void* workspace, int dtype, void* stream);
+
+/* ---- spectral norm power iteration (torch.nn.utils.spectral_norm semantics; the seam is the
+ * conv_factory kwarg of the blocks: generator.py:34, discriminator.py:28,52) */
+int ttg_spectral_norm(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
+                      int n_iter, float eps, void* workspace, void* stream);
+/* g_w = (g - dot(g, w_out) * u v^T) / sigma */
+int ttg_spectral_norm_bwd(const float* g, const float* w_out, const float* u, const float* v, const float* sigma,
+                          float* gw, int rows, int cols, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

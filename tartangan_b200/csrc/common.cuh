@@ -1,0 +1,94 @@
+// Shared helpers for the tartangan_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#define TTG_OK 0
+#define TTG_ERR_ARG 1
+#define TTG_ERR_CUDA 2
+#define TTG_ERR_UNSUPPORTED 3
+
+#define TTG_F32 0
+#define TTG_BF16 1
+
+typedef __nv_bfloat16 bf16;
+
+extern "C" const char* ttg_last_error(void);
+int ttg_set_error(int code, const char* fmt, ...);
+
+#define TTG_CHECK_LAUNCH(name)                                                      \
+  do {                                                                              \
+    cudaError_t e__ = cudaPeekAtLastError();                                        \
+    if (e__ != cudaSuccess) {                                                       \
+      (void)cudaGetLastError();                                                     \
+      return ttg_set_error(TTG_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__));  \
+    }                                                                               \
+  } while (0)
+
+#define TTG_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return ttg_set_error(TTG_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+// Dispatch on the activation dtype code.
+#define TTG_DISPATCH(dtype, ...)                                                       \
+  do {                                                                                 \
+    if ((dtype) == TTG_F32) { typedef float T; __VA_ARGS__; }                          \
+    else if ((dtype) == TTG_BF16) { typedef bf16 T; __VA_ARGS__; }                     \
+    else return ttg_set_error(TTG_ERR_ARG, "bad dtype code %d", (int)(dtype));         \
+  } while (0)
+
+static inline int ttg_num_sms() { return 148; }   // B200
+static inline int ttg_grid_for(long long work_items, int per_block, int max_waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)ttg_num_sms() * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------- device side
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vectors: 4 floats or 8 bf16.
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+  __device__ __forceinline__ void pack(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float lrelu_mask(float v, float slope) { return v > 0.f ? 1.f : slope; }

@@ -1,0 +1,286 @@
+// Heads and losses (all fp32, tiny tensors, latency-bound):
+//   * IQN head: cosine tau embedding -> Linear(E->C) -> tanh -> multiply with pooled
+//     features -> Linear(C->1), per-quantile prediction + mean over quantiles, in ONE
+//     kernel (reference models/iqn.py:41-46,91-103 + blocks/discriminator.py:164-178);
+//     its backward in one kernel.  The embedding (rows x C) is never written to HBM.
+//   * quantile-Huber loss (models/iqn.py:111-130) forward / backward.
+//   * BCE-with-logits mean (trainers/cnn.py:88,131,147) forward / backward.
+//   * sum of squares (R1 penalty reduction, models/losses.py:27-29).
+//   * small fp32 matmul with transposes (nn.Linear in blocks/generator.py:71 and
+//     blocks/discriminator.py:137; closed under differentiation).
+#include "common.cuh"
+
+#define IQN_MAX_E 32
+
+// ---------------------------------------------------------------- IQN head forward
+// rows r = q*B + b (quantile-major, Appendix B.9).  One warp per row.
+__global__ void __launch_bounds__(256) iqn_head_fwd_kernel(
+    const float* __restrict__ feats, const float* __restrict__ taus, const float* __restrict__ We,
+    const float* __restrict__ be, const float* __restrict__ wo, const float* __restrict__ bo,
+    float* __restrict__ p_tau, int B, int R, int C, int E) {
+  extern __shared__ float s_we[];   // [C][E] + be[C] + wo[C]
+  float* s_be = s_we + C * E; float* s_wo = s_be + C;
+  for (int i = threadIdx.x; i < C * E; i += blockDim.x) s_we[i] = We[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_be[i] = be[i]; s_wo[i] = wo[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = blockIdx.x * nwarp + warp; r < R; r += gridDim.x * nwarp) {
+    const int b = r % B;
+    const float tau = taus[r];
+    float cs[IQN_MAX_E];
+#pragma unroll
+    for (int k = 0; k < IQN_MAX_E; ++k) cs[k] = k < E ? cosf(tau * 3.14159265358979323846f * (float)(k + 1)) : 0.f;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float pre = s_be[c];
+#pragma unroll
+      for (int k = 0; k < IQN_MAX_E; ++k) if (k < E) pre += cs[k] * s_we[c * E + k];
+      acc += feats[(long long)b * C + c] * tanhf(pre) * s_wo[c];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) p_tau[r] = acc + (bo ? bo[0] : 0.f);
+  }
+}
+__global__ void quantile_mean_kernel(const float* __restrict__ p_tau, float* __restrict__ p_mean, int B, int nq) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { float s = 0.f; for (int q = 0; q < nq; ++q) s += p_tau[q * B + b]; p_mean[b] = s / (float)nq; }
+}
+// bo may be null (used by the double-backward, where the bias does not enter).
+extern "C" int ttg_iqn_head_fwd(const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                                const float* bo, float* p_tau, float* p_mean, int B, int nq, int C, int E, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(E <= IQN_MAX_E, "iqn_head: embedding dims %d > %d", E, IQN_MAX_E);
+  int R = B * nq;
+  size_t smem = sizeof(float) * ((size_t)C * E + 2 * C);
+  TTG_REQUIRE(smem <= 200 * 1024, "iqn_head: C*E too large for shared memory");
+  cudaFuncSetAttribute(iqn_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  iqn_head_fwd_kernel<<<ttg_grid_for(R, 8, 1), 256, smem, st>>>(feats, taus, We, be, wo, bo, p_tau, B, R, C, E);
+  TTG_CHECK_LAUNCH("iqn_head_fwd");
+  if (p_mean) {
+    quantile_mean_kernel<<<(B + 127) / 128, 128, 0, st>>>(p_tau, p_mean, B, nq);
+    TTG_CHECK_LAUNCH("quantile_mean");
+  }
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- IQN head backward
+// g[r] = cotangent of p_tau[r] (the mean-over-quantiles cotangent is folded in by the caller).
+// Lane = channel; each warp walks a slice of the batch; per-channel partials reduced through
+// shared memory then fp32 atomics (outputs zeroed here).
+__global__ void __launch_bounds__(256) iqn_head_bwd_kernel(
+    const float* __restrict__ g, const float* __restrict__ feats, const float* __restrict__ taus,
+    const float* __restrict__ We, const float* __restrict__ be, const float* __restrict__ wo,
+    float* __restrict__ gf, float* __restrict__ gWe, float* __restrict__ gbe, float* __restrict__ gwo,
+    float* __restrict__ gbo, int B, int nq, int C, int E) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const bool live = c < C;
+  float we[IQN_MAX_E], gwe[IQN_MAX_E];
+#pragma unroll
+  for (int k = 0; k < IQN_MAX_E; ++k) { we[k] = (live && k < E) ? We[c * E + k] : 0.f; gwe[k] = 0.f; }
+  const float bec = live ? be[c] : 0.f, woc = live ? wo[c] : 0.f;
+  float a_gwo = 0.f, a_gbe = 0.f, a_gbo = 0.f;
+  for (int b = blockIdx.y * nwarp + warp; b < B; b += gridDim.y * nwarp) {
+    const float f = live ? feats[(long long)b * C + c] : 0.f;
+    float a_gf = 0.f;
+    for (int q = 0; q < nq; ++q) {
+      const int r = q * B + b;
+      const float gr = g[r], tau = taus[r];
+      float pre = bec, cs[IQN_MAX_E];
+#pragma unroll
+      for (int k = 0; k < IQN_MAX_E; ++k) {
+        cs[k] = k < E ? cosf(tau * 3.14159265358979323846f * (float)(k + 1)) : 0.f;
+        pre += cs[k] * we[k];
+      }
+      const float e = tanhf(pre);
+      a_gf += gr * e * woc;
+      a_gwo += gr * f * e;
+      const float gpre = gr * f * woc * (1.f - e * e);
+      a_gbe += gpre;
+#pragma unroll
+      for (int k = 0; k < IQN_MAX_E; ++k) gwe[k] += gpre * cs[k];
+      if (blockIdx.x == 0 && lane == 0) a_gbo += gr;
+    }
+    if (live && gf) gf[(long long)b * C + c] = a_gf;
+  }
+  if (live) {
+    if (gwo) atomicAdd(&gwo[c], a_gwo);
+    if (gbe) atomicAdd(&gbe[c], a_gbe);
+    if (gWe) {
+#pragma unroll
+      for (int k = 0; k < IQN_MAX_E; ++k) if (k < E) atomicAdd(&gWe[c * E + k], gwe[k]);
+    }
+  }
+  if (gbo && blockIdx.x == 0 && lane == 0) atomicAdd(gbo, a_gbo);
+}
+extern "C" int ttg_iqn_head_bwd(const float* g, const float* feats, const float* taus, const float* We, const float* be,
+                                const float* wo, float* gf, float* gWe, float* gbe, float* gwo, float* gbo, int B, int nq,
+                                int C, int E, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(E <= IQN_MAX_E, "iqn_head: embedding dims %d > %d", E, IQN_MAX_E);
+  if (gWe) cudaMemsetAsync(gWe, 0, sizeof(float) * (size_t)C * E, st);
+  if (gbe) cudaMemsetAsync(gbe, 0, sizeof(float) * C, st);
+  if (gwo) cudaMemsetAsync(gwo, 0, sizeof(float) * C, st);
+  if (gbo) cudaMemsetAsync(gbo, 0, sizeof(float), st);
+  int gy = (B + 7) / 8; if (gy > 64) gy = 64;
+  dim3 grid((C + 31) / 32, gy);
+  iqn_head_bwd_kernel<<<grid, 256, 0, st>>>(g, feats, taus, We, be, wo, gf, gWe, gbe, gwo, gbo, B, nq, C, E);
+  TTG_CHECK_LAUNCH("iqn_head_bwd");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- quantile Huber loss
+__device__ __forceinline__ float block_sum_256(float v) {
+  __shared__ float s[8];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < 8 ? s[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) t = warp_sum(t);
+  __syncthreads();
+  return t;   // valid in thread 0 (and warp 0)
+}
+// loss = (1/B) * sum_{q,b} |tau - 1[err<0]| * huber_k(err),  err = target[b] - p[q,b]
+__global__ void __launch_bounds__(256) quantile_huber_fwd_kernel(const float* __restrict__ p, const float* __restrict__ target,
+                                                                   const float* __restrict__ taus, float* __restrict__ loss,
+                                                                   int B, int R, float k) {
+  float acc = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    float err = target[r % B] - p[r];
+    float mag = fabsf(err);
+    float h = mag <= k ? 0.5f * err * err : k * (mag - 0.5f * k);
+    acc += fabsf(taus[r] - (err < 0.f ? 1.f : 0.f)) * h;
+  }
+  acc = block_sum_256(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, acc / (float)B);
+}
+__global__ void quantile_huber_bwd_kernel(const float* __restrict__ p, const float* __restrict__ target,
+                                          const float* __restrict__ taus, const float* __restrict__ gloss,
+                                          float* __restrict__ gp, int B, int R, float k) {
+  const float gl = gloss[0] / (float)B;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    float err = target[r % B] - p[r];
+    float w = fabsf(taus[r] - (err < 0.f ? 1.f : 0.f));
+    float dh = fabsf(err) <= k ? err : (err > 0.f ? k : -k);
+    gp[r] = -gl * w * dh;
+  }
+}
+extern "C" int ttg_quantile_huber_fwd(const float* p_tau, const float* target, const float* taus, float* loss, int B, int nq,
+                                      float k, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(loss, 0, sizeof(float), st);
+  quantile_huber_fwd_kernel<<<ttg_grid_for(B * nq, 256, 1), 256, 0, st>>>(p_tau, target, taus, loss, B, B * nq, k);
+  TTG_CHECK_LAUNCH("quantile_huber_fwd");
+  return TTG_OK;
+}
+extern "C" int ttg_quantile_huber_bwd(const float* p_tau, const float* target, const float* taus, const float* gloss,
+                                      float* gp, int B, int nq, float k, void* stream) {
+  quantile_huber_bwd_kernel<<<ttg_grid_for(B * nq, 256, 1), 256, 0, (cudaStream_t)stream>>>(p_tau, target, taus, gloss, gp, B, B * nq, k);
+  TTG_CHECK_LAUNCH("quantile_huber_bwd");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- BCE with logits (mean)
+__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                      float* __restrict__ loss, int n) {
+  float acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v = x[i];
+    acc += fmaxf(v, 0.f) - v * y[i] + log1pf(expf(-fabsf(v)));
+  }
+  acc = block_sum_256(acc);
+  if (threadIdx.x == 0) atomicAdd(loss, acc / (float)n);
+}
+__global__ void bce_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gloss,
+                               float* __restrict__ gx, int n) {
+  const float gl = gloss[0] / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    gx[i] = gl * (1.f / (1.f + expf(-x[i])) - y[i]);
+}
+extern "C" int ttg_bce_logits_fwd(const float* x, const float* y, float* loss, int n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(loss, 0, sizeof(float), st);
+  bce_fwd_kernel<<<ttg_grid_for(n, 256, 1), 256, 0, st>>>(x, y, loss, n);
+  TTG_CHECK_LAUNCH("bce_logits_fwd");
+  return TTG_OK;
+}
+extern "C" int ttg_bce_logits_bwd(const float* x, const float* y, const float* gloss, float* gx, int n, void* stream) {
+  bce_bwd_kernel<<<ttg_grid_for(n, 256, 1), 256, 0, (cudaStream_t)stream>>>(x, y, gloss, gx, n);
+  TTG_CHECK_LAUNCH("bce_logits_bwd");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- sum of squares: out = scale * sum x^2
+__global__ void __launch_bounds__(256) sqsum_kernel(const float* __restrict__ x, double* __restrict__ ws, long long n) {
+  float acc = 0.f;
+  const long long n4 = n / 4;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += x[i] * x[i];
+  acc = block_sum_256(acc);
+  if (threadIdx.x == 0) atomicAdd(ws, (double)acc);
+}
+__global__ void sqsum_finalize_kernel(const double* ws, float scale, float* out) { out[0] = (float)(ws[0] * (double)scale); }
+extern "C" int ttg_sqsum_f32(const float* x, long long n, float scale, float* out, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sqsum: input must be 16-byte aligned");
+  double* ws = (double*)workspace;
+  cudaMemsetAsync(ws, 0, sizeof(double), st);
+  sqsum_kernel<<<ttg_grid_for(n / 4 + 1, 1024, 4), 256, 0, st>>>(x, ws, n);
+  TTG_CHECK_LAUNCH("sqsum");
+  sqsum_finalize_kernel<<<1, 1, 0, st>>>(ws, scale, out);
+  TTG_CHECK_LAUNCH("sqsum_finalize");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- small fp32 matmul
+// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]);  row-major, 16x16 tiles.
+__global__ void __launch_bounds__(256) matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                         const float* __restrict__ bias, float* __restrict__ Cm, int M,
+                                                         int N, int K, int ta, int tb) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    int ak = k0 + tx, bk = k0 + ty;
+    sa[ty][tx] = (row < M && ak < K) ? (ta ? A[(long long)ak * M + row] : A[(long long)row * K + ak]) : 0.f;
+    sb[ty][tx] = (bk < K && col < N) ? (tb ? Bm[(long long)col * K + bk] : Bm[(long long)bk * N + col]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
+    __syncthreads();
+  }
+  if (row < M && col < N) Cm[(long long)row * N + col] = acc + (bias ? bias[col] : 0.f);
+}
+extern "C" int ttg_matmul_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA,
+                              int transB, void* stream) {
+  TTG_REQUIRE(M > 0 && N > 0 && K > 0, "matmul: empty operand");
+  dim3 grid((N + 15) / 16, (M + 15) / 16);
+  matmul_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, bias, C, M, N, K, transA, transB);
+  TTG_CHECK_LAUNCH("matmul_f32");
+  return TTG_OK;
+}
+// out[n] = scale * sum_m x[m,n]
+__global__ void colsum_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int N, float scale) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) { float s = 0.f; for (int m = 0; m < M; ++m) s += x[(long long)m * N + n]; out[n] = s * scale; }
+}
+extern "C" int ttg_colsum_f32(const float* x, float* out, int M, int N, float scale, void* stream) {
+  colsum_f32_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, out, M, N, scale);
+  TTG_CHECK_LAUNCH("colsum_f32");
+  return TTG_OK;
+}
+// out[m,n] = scale * g[n]
+__global__ void rowbcast_f32_kernel(const float* __restrict__ g, float* __restrict__ out, int M, int N, float scale) {
+  long long total = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) out[i] = scale * g[i % N];
+}
+extern "C" int ttg_rowbcast_f32(const float* g, float* out, int M, int N, float scale, void* stream) {
+  rowbcast_f32_kernel<<<ttg_grid_for((long long)M * N, 1024), 256, 0, (cudaStream_t)stream>>>(g, out, M, N, scale);
+  TTG_CHECK_LAUNCH("rowbcast_f32");
+  return TTG_OK;
+}

@@ -1,0 +1,259 @@
+// Train-mode BatchNorm2d (+ fused LeakyReLU) over NHWC activations:
+// statistics, forward, backward and backward-of-backward (needed by the R1
+// gradient penalty, reference models/losses.py:17-30).  Replaces the ATen ops
+// native_batch_norm / native_batch_norm_backward / NativeBatchNormBackwardBackward
+// + leaky_relu(_backward) issued by every nn.BatchNorm2d + nn.LeakyReLU pair in
+// reference models/blocks/{generator,discriminator}.py.
+// All kernels are HBM streams: 16-byte vector loads, per-channel partial sums in
+// registers -> shared -> one fp64 atomic per (block, channel).
+#include "chanops.cuh"
+
+// ---------------------------------------------------------------- statistics
+template <typename T> struct StatsOp {
+  static constexpr int NIN = 1, NACC = 2;
+  const T* in[1];
+  __device__ __forceinline__ void acc(const float* v, int, float* a) const { a[0] += v[0]; a[1] += v[0] * v[0]; }
+};
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double m = sums[c] / (double)M;
+    double var = sums[C + c] / (double)M - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+  if (c == 0 && num_batches) *num_batches += 1;
+}
+
+extern "C" size_t ttg_bn_workspace_bytes(int C) { return sizeof(double) * 5 * (size_t)C; }
+
+extern "C" int ttg_bn_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* invstd,
+                            float* running_mean, float* running_var, long long* num_batches, void* workspace,
+                            int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(M > 0 && C > 0, "bn_stats: empty input");
+  double* ws = (double*)workspace;
+  TTG_DISPATCH(dtype, {
+    StatsOp<T> op; op.in[0] = (const T*)x;
+    int rc = launch_chan_reduce<T>("bn_stats", op, M, C, ws, st);
+    if (rc) return rc;
+  });
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, M, C, eps, momentum, mean, invstd, running_mean,
+                                                       running_var, num_batches);
+  TTG_CHECK_LAUNCH("bn_finalize");
+  return TTG_OK;
+}
+
+// eval-mode helper: mean/invstd from running statistics.
+__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, int C, float* mean, float* invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = rm[c]; invstd[c] = rsqrtf(rv[c] + eps); }
+}
+extern "C" int ttg_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
+                                 float* invstd, void* stream) {
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, eps, C, mean, invstd);
+  TTG_CHECK_LAUNCH("bn_eval_stats");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- forward
+template <typename T> struct BnActFwdOp {
+  static constexpr int NIN = 1, NOUT = 1;
+  const T* in[1]; T* out[1];
+  const float *mean, *invstd, *gamma, *beta; float slope;
+  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
+    float y = (v[0] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+    o[0] = lrelu(y, slope);
+  }
+};
+
+extern "C" int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const float* mean, const float* invstd,
+                              const float* gamma, const float* beta, float slope, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, {
+    BnActFwdOp<T> op; op.in[0] = (const T*)x; op.out[0] = (T*)y;
+    op.mean = mean; op.invstd = invstd; op.gamma = gamma; op.beta = beta; op.slope = slope;
+    return launch_chan_map<T>("bn_act_fwd", op, M * C, C, (cudaStream_t)stream);
+  });
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- backward
+// d = ga * lrelu'(y);  gx = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
+template <typename T> struct BnActBwdRedOp {
+  static constexpr int NIN = 2, NACC = 2;
+  const T* in[2];   // x, ga
+  const float *mean, *invstd, *gamma, *beta; float slope;
+  __device__ __forceinline__ void acc(const float* v, int c, float* a) const {
+    float xh = (v[0] - mean[c]) * invstd[c];
+    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
+    a[0] += d; a[1] += d * xh;
+  }
+};
+template <typename T> struct BnActBwdMapOp {
+  static constexpr int NIN = 2, NOUT = 1;
+  const T* in[2]; T* out[1];
+  const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
+  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
+    float xh = (v[0] - mean[c]) * invstd[c];
+    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
+    float db = (float)sums[c] * invM, cc = (float)sums[C + c] * invM;
+    o[0] = gamma[c] * invstd[c] * (d - db - xh * cc);
+  }
+};
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* ggamma, float* gbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { if (gbeta) gbeta[c] = (float)sums[c]; if (ggamma) ggamma[c] = (float)sums[C + c]; }
+}
+
+extern "C" int ttg_bn_act_bwd(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
+                              float* gbeta, void* workspace, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws = (double*)workspace;
+  TTG_DISPATCH(dtype, {
+    BnActBwdRedOp<T> r; r.in[0] = (const T*)x; r.in[1] = (const T*)ga;
+    r.mean = mean; r.invstd = invstd; r.gamma = gamma; r.beta = beta; r.slope = slope;
+    int rc = launch_chan_reduce<T>("bn_act_bwd_reduce", r, M, C, ws, st);
+    if (rc) return rc;
+    if (gx) {
+      BnActBwdMapOp<T> m; m.in[0] = (const T*)x; m.in[1] = (const T*)ga; m.out[0] = (T*)gx;
+      m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
+      m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
+      rc = launch_chan_map<T>("bn_act_bwd_apply", m, M * C, C, st);
+      if (rc) return rc;
+    }
+  });
+  if (ggamma || gbeta) {
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta);
+    TTG_CHECK_LAUNCH("bn_param_grads");
+  }
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- backward of backward
+// Given u = cotangent of gx (see DESIGN.md "BN double backward"):
+//   g_ga = m * gamma*r * P(u)
+//   g_x  = gamma*r^2 * [ xhat*(c*e - cov) - e*P(d) - c*P(u) ]
+//   g_gamma = r * M * (cov - c*e)
+// with P(v) = v - mean(v) - xhat*mean(v*xhat), c = mean(d*xhat), e = mean(u*xhat),
+// cov = mean(u*d) - mean(u)*mean(d).
+template <typename T> struct BnActBwd2RedOp {
+  static constexpr int NIN = 3, NACC = 5;
+  const T* in[3];   // x, ga, u
+  const float *mean, *invstd, *gamma, *beta; float slope;
+  __device__ __forceinline__ void acc(const float* v, int c, float* a) const {
+    float xh = (v[0] - mean[c]) * invstd[c];
+    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
+    float u = v[2];
+    a[0] += d; a[1] += d * xh; a[2] += u; a[3] += u * xh; a[4] += u * d;
+  }
+};
+template <typename T> struct BnActBwd2MapOp {
+  static constexpr int NIN = 3, NOUT = 2;
+  const T* in[3]; T* out[2];   // out: g_ga, g_x
+  const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
+  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
+    float r = invstd[c], g = gamma[c];
+    float xh = (v[0] - mean[c]) * r;
+    float m = lrelu_mask(xh * g + beta[c], slope);
+    float d = v[1] * m, u = v[2];
+    float db = (float)sums[c] * invM, cc = (float)sums[C + c] * invM;
+    float ub = (float)sums[2 * C + c] * invM, e = (float)sums[3 * C + c] * invM;
+    float cov = (float)sums[4 * C + c] * invM - ub * db;
+    float Pd = d - db - xh * cc, Pu = u - ub - xh * e;
+    o[0] = m * g * r * Pu;
+    o[1] = g * r * r * (xh * (cc * e - cov) - e * Pd - cc * Pu);
+  }
+};
+__global__ void bn_bwd2_gamma_kernel(const double* sums, const float* invstd, long long M, int C, float* ggamma) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    double invM = 1.0 / (double)M;
+    double db = sums[c] * invM, cc = sums[C + c] * invM, ub = sums[2 * C + c] * invM, e = sums[3 * C + c] * invM;
+    double cov = sums[4 * C + c] * invM - ub * db;
+    ggamma[c] = (float)((double)invstd[c] * (double)M * (cov - cc * e));
+  }
+}
+
+extern "C" int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
+                               const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               float slope, float* ggamma, void* workspace, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws = (double*)workspace;
+  TTG_DISPATCH(dtype, {
+    BnActBwd2RedOp<T> r; r.in[0] = (const T*)x; r.in[1] = (const T*)ga; r.in[2] = (const T*)u;
+    r.mean = mean; r.invstd = invstd; r.gamma = gamma; r.beta = beta; r.slope = slope;
+    int rc = launch_chan_reduce<T>("bn_act_bwd2_reduce", r, M, C, ws, st);
+    if (rc) return rc;
+    BnActBwd2MapOp<T> m; m.in[0] = (const T*)x; m.in[1] = (const T*)ga; m.in[2] = (const T*)u;
+    m.out[0] = (T*)g_ga; m.out[1] = (T*)g_x;
+    m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
+    m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
+    rc = launch_chan_map<T>("bn_act_bwd2_apply", m, M * C, C, st);
+    if (rc) return rc;
+  });
+  if (ggamma) {
+    bn_bwd2_gamma_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, invstd, M, C, ggamma);
+    TTG_CHECK_LAUNCH("bn_bwd2_gamma");
+  }
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- plain LeakyReLU (--norm id)
+template <typename T> struct LreluOp {     // y = lrelu(x)
+  static constexpr int NIN = 1, NOUT = 1;
+  const T* in[1]; T* out[1]; float slope;
+  __device__ __forceinline__ void apply(const float* v, int, float* o) const { o[0] = lrelu(v[0], slope); }
+};
+template <typename T> struct LreluMaskMulOp {   // out = g * lrelu'(x)
+  static constexpr int NIN = 2, NOUT = 1;
+  const T* in[2]; T* out[1]; float slope;
+  __device__ __forceinline__ void apply(const float* v, int, float* o) const { o[0] = v[1] * lrelu_mask(v[0], slope); }
+};
+extern "C" int ttg_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, {
+    LreluOp<T> op; op.in[0] = (const T*)x; op.out[0] = (T*)y; op.slope = slope;
+    return launch_chan_map<T>("lrelu_fwd", op, n, (n % 8 == 0) ? 8 : 1, (cudaStream_t)stream);
+  });
+  return TTG_OK;
+}
+extern "C" int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n, float slope, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, {
+    LreluMaskMulOp<T> op; op.in[0] = (const T*)x; op.in[1] = (const T*)g; op.out[0] = (T*)gx; op.slope = slope;
+    return launch_chan_map<T>("lrelu_bwd", op, n, (n % 8 == 0) ? 8 : 1, (cudaStream_t)stream);
+  });
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- per-channel sum (conv bias gradient)
+template <typename T> struct SumOp {
+  static constexpr int NIN = 1, NACC = 1;
+  const T* in[1];
+  __device__ __forceinline__ void acc(const float* v, int, float* a) const { a[0] += v[0]; }
+};
+__global__ void d2f_kernel(const double* s, int n, float* o) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = (float)s[i];
+}
+extern "C" int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  double* ws = (double*)workspace;
+  TTG_DISPATCH(dtype, {
+    SumOp<T> op; op.in[0] = (const T*)x;
+    int rc = launch_chan_reduce<T>("channel_sum", op, M, C, ws, st);
+    if (rc) return rc;
+  });
+  d2f_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, out);
+  TTG_CHECK_LAUNCH("channel_sum_finalize");
+  return TTG_OK;
+}

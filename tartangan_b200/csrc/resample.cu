@@ -1,0 +1,297 @@
+// Spatial resampling and glue kernels over NHWC activations (all HBM streams):
+//   2x2 sum-pool (nn.AvgPool2d(2), reference blocks/discriminator.py:67, and the
+//   adjoint of nearest upsample), nearest x2 upsample (F.interpolate, reference
+//   blocks/generator.py:58, and the adjoint of avg-pool), bilinear 1/2 with
+//   align_corners=True and its transpose (blocks/discriminator.py:55-57,92),
+//   residual add (generator.py:62, discriminator.py:95), sum over H,W
+//   (discriminator.py:143,166), NCHW fp32 <-> NHWC conversions at the module
+//   boundary, tanh (generator.py:126).
+#include "common.cuh"
+
+template <typename T, int V> struct Ld {
+  static __device__ __forceinline__ void ld(const T* p, float* f) {
+    if constexpr (V == 1) f[0] = to_f(*p); else { Vec<T> q; q.load(p); q.unpack(f); }
+  }
+  static __device__ __forceinline__ void st(T* p, const float* f) {
+    if constexpr (V == 1) *p = from_f<T>(f[0]); else { Vec<T> q; q.pack(f); q.store(p); }
+  }
+};
+
+template <typename T> static inline bool vec2_ok(int C, const void* a, const void* b) {
+  return C % Vec<T>::N == 0 && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15);
+}
+
+// y[n,oy,ox,c] = scale * sum_{2x2} x[n,2oy+dy,2ox+dx,c]
+template <typename T, int V>
+__global__ void pool2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Ho, int Wo, int C, float scale) {
+  const int cv = C / V;
+  const long long total = (long long)N * Ho * Wo * cv;
+  const int Wi = Wo * 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
+    const T* src = x + (((long long)n * Ho * 2 + oy * 2) * Wi + ox * 2) * C + c;
+    float a[V], b[V], s[V];
+    Ld<T, V>::ld(src, a); Ld<T, V>::ld(src + C, b);
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = a[j] + b[j];
+    Ld<T, V>::ld(src + (long long)Wi * C, a); Ld<T, V>::ld(src + (long long)Wi * C + C, b);
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = (s[j] + a[j] + b[j]) * scale;
+    Ld<T, V>::st(y + (((long long)n * Ho + oy) * Wo + ox) * C + c, s);
+  }
+}
+extern "C" int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, x, y)) { pool2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
+    else { pool2_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
+  });
+  TTG_CHECK_LAUNCH("pool2_sum");
+  return TTG_OK;
+}
+
+// y[n,oy,ox,c] = scale * x[n,oy/2,ox/2,c]
+template <typename T, int V>
+__global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, int Wi, int C, float scale) {
+  const int cv = C / V; const int Ho = Hi * 2, Wo = Wi * 2;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
+    float a[V];
+    Ld<T, V>::ld(x + (((long long)n * Hi + (oy >> 1)) * Wi + (ox >> 1)) * C + c, a);
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] *= scale;
+    Ld<T, V>::st(y + (((long long)n * Ho + oy) * Wo + ox) * C + c, a);
+  }
+}
+extern "C" int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, x, y)) { upsample2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Hi * Wi * 4 * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
+    else { upsample2_kernel<T, 1><<<ttg_grid_for((long long)N * Hi * Wi * 4 * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
+  });
+  TTG_CHECK_LAUNCH("upsample2");
+  return TTG_OK;
+}
+
+// Bilinear, output size = input/2, align_corners=True: src = dst * (in-1)/(out-1).
+__device__ __forceinline__ void bil_src(int o, int in, int out, int& i0, int& i1, float& w1) {
+  float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  float s = scale * (float)o;
+  i0 = (int)s; if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  w1 = s - (float)i0;
+}
+template <typename T, int V>
+__global__ void bilinear_down_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int Hi, int Wi, int C) {
+  const int cv = C / V; const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
+    int y0, y1, x0, x1; float wy, wx;
+    bil_src(oy, Hi, Ho, y0, y1, wy); bil_src(ox, Wi, Wo, x0, x1, wx);
+    const T* b = x + (long long)n * Hi * Wi * C + c;
+    float a00[V], a01[V], a10[V], a11[V], o[V];
+    Ld<T, V>::ld(b + ((long long)y0 * Wi + x0) * C, a00); Ld<T, V>::ld(b + ((long long)y0 * Wi + x1) * C, a01);
+    Ld<T, V>::ld(b + ((long long)y1 * Wi + x0) * C, a10); Ld<T, V>::ld(b + ((long long)y1 * Wi + x1) * C, a11);
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      o[j] = (1.f - wy) * ((1.f - wx) * a00[j] + wx * a01[j]) + wy * ((1.f - wx) * a10[j] + wx * a11[j]);
+    Ld<T, V>::st(y + (((long long)n * Ho + oy) * Wo + ox) * C + c, o);
+  }
+}
+extern "C" int ttg_bilinear_down_fwd(const void* x, void* y, int N, int Hi, int Wi, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0, "bilinear_down: odd input size %dx%d", Hi, Wi);
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, x, y)) { bilinear_down_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * (Hi / 2) * (Wi / 2) * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
+    else { bilinear_down_kernel<T, 1><<<ttg_grid_for((long long)N * (Hi / 2) * (Wi / 2) * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
+  });
+  TTG_CHECK_LAUNCH("bilinear_down_fwd");
+  return TTG_OK;
+}
+
+// Transpose of the above as a gather: gx[iy,ix] = sum over outputs whose footprint covers (iy,ix).
+__device__ __forceinline__ int bil_candidates(int i, int in, int out, int* oidx, float* w) {
+  // outputs o with i0(o)==i or i1(o)==i lie within +-1 of i*(out-1)/(in-1)
+  int cnt = 0;
+  int guess = in > 1 ? (int)((float)i * (float)(out - 1) / (float)(in - 1)) : 0;
+  for (int o = guess - 1; o <= guess + 2; ++o) {
+    if (o < 0 || o >= out) continue;
+    int i0, i1; float w1; bil_src(o, in, out, i0, i1, w1);
+    float ww = 0.f;
+    if (i0 == i) ww += 1.f - w1;
+    if (i1 == i) ww += w1;
+    if (i0 == i || i1 == i) { oidx[cnt] = o; w[cnt] = ww; ++cnt; }
+  }
+  return cnt;
+}
+template <typename T, int V>
+__global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N, int Hi, int Wi, int C) {
+  const int cv = C / V; const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long total = (long long)N * Hi * Wi * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ix = (int)(p % Wi); p /= Wi; int iy = (int)(p % Hi); int n = (int)(p / Hi);
+    int oys[4], oxs[4]; float wys[4], wxs[4];
+    int ny = bil_candidates(iy, Hi, Ho, oys, wys), nx = bil_candidates(ix, Wi, Wo, oxs, wxs);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int a = 0; a < ny; ++a)
+      for (int b = 0; b < nx; ++b) {
+        float w = wys[a] * wxs[b];
+        if (w == 0.f) continue;
+        float g[V];
+        Ld<T, V>::ld(gy + (((long long)n * Ho + oys[a]) * Wo + oxs[b]) * C + c, g);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += w * g[j];
+      }
+    Ld<T, V>::st(gx + (((long long)n * Hi + iy) * Wi + ix) * C + c, acc);
+  }
+}
+extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Hi * Wi * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_for((long long)N * Hi * Wi * C, 256), 256, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+  });
+  TTG_CHECK_LAUNCH("bilinear_down_bwd");
+  return TTG_OK;
+}
+
+// out = alpha*a + beta*b
+template <typename T, int V>
+__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long nvec, float alpha, float beta) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[V], y[V];
+    Ld<T, V>::ld(a + i * V, x); Ld<T, V>::ld(b + i * V, y);
+#pragma unroll
+    for (int j = 0; j < V; ++j) x[j] = alpha * x[j] + beta * y[j];
+    Ld<T, V>::st(o + i * V, x);
+  }
+}
+extern "C" int ttg_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return TTG_OK;
+  TTG_DISPATCH(dtype, {
+    bool vec = n % Vec<T>::N == 0 && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15);
+    if (vec) axpby_kernel<T, Vec<T>::N><<<ttg_grid_for(n / Vec<T>::N, 512), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n / Vec<T>::N, alpha, beta);
+    else axpby_kernel<T, 1><<<ttg_grid_for(n, 1024), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, alpha, beta);
+  });
+  TTG_CHECK_LAUNCH("axpby");
+  return TTG_OK;
+}
+
+// out = x * (host_scale * *dev_scale)   (dev_scale may be null); fp32 only (loss plumbing)
+__global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict__ o, long long n, float hs, const float* ds) {
+  float s = hs * (ds ? *ds : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = x[i] * s;
+}
+extern "C" int ttg_scale_f32(const float* x, float* out, long long n, float host_scale, const float* dev_scale, void* stream) {
+  if (n == 0) return TTG_OK;
+  scale_f32_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, out, n, host_scale, dev_scale);
+  TTG_CHECK_LAUNCH("scale_f32");
+  return TTG_OK;
+}
+
+// feats[n,c] = sum_{hw} x[n,hw,c]   (fp32 out);  one block per (n, channel group)
+template <typename T>
+__global__ void spatial_sum_kernel(const T* __restrict__ x, float* __restrict__ out, int HW, int C) {
+  int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    const T* p = x + (long long)n * HW * C + c;
+    for (int i = 0; i < HW; ++i) s += to_f(p[(long long)i * C]);
+    out[(long long)n * C + c] = s;
+  }
+}
+extern "C" int ttg_spatial_sum(const void* x, float* out, int N, int HW, int C, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, { spatial_sum_kernel<T><<<N, 128, 0, (cudaStream_t)stream>>>((const T*)x, out, HW, C); });
+  TTG_CHECK_LAUNCH("spatial_sum");
+  return TTG_OK;
+}
+template <typename T>
+__global__ void spatial_bcast_kernel(const float* __restrict__ g, T* __restrict__ gx, long long total, int HW, int C) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long long n = i / ((long long)HW * C);
+    gx[i] = from_f<T>(g[n * C + c]);
+  }
+}
+extern "C" int ttg_spatial_bcast(const float* g, void* gx, int N, int HW, int C, int dtype, void* stream) {
+  long long total = (long long)N * HW * C;
+  TTG_DISPATCH(dtype, { spatial_bcast_kernel<T><<<ttg_grid_for(total, 1024), 256, 0, (cudaStream_t)stream>>>(g, (T*)gx, total, HW, C); });
+  TTG_CHECK_LAUNCH("spatial_bcast");
+  return TTG_OK;
+}
+
+// NCHW fp32 (contiguous) -> NHWC T, and back.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int N, int C, int HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / HW; int p = (int)(i % HW);
+    const float* s = x + n * C * HW + p; T* d = y + i * C;
+    for (int c = 0; c < C; ++c) d[c] = from_f<T>(s[(long long)c * HW]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int N, int C, int HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long n = i / HW; int p = (int)(i % HW);
+    const T* s = x + i * C; float* d = y + n * C * HW + p;
+    for (int c = 0; c < C; ++c) d[(long long)c * HW] = to_f(s[c]);
+  }
+}
+extern "C" int ttg_nchw_to_nhwc(const float* x, void* y, int N, int C, int HW, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, { nchw_to_nhwc_kernel<T><<<ttg_grid_for((long long)N * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, N, C, HW); });
+  TTG_CHECK_LAUNCH("nchw_to_nhwc");
+  return TTG_OK;
+}
+extern "C" int ttg_nhwc_to_nchw(const void* x, float* y, int N, int C, int HW, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, { nhwc_to_nchw_kernel<T><<<ttg_grid_for((long long)N * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, N, C, HW); });
+  TTG_CHECK_LAUNCH("nhwc_to_nchw");
+  return TTG_OK;
+}
+
+// dtype casts (flat)
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ x, D* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = from_f<D>(to_f(x[i]));
+}
+extern "C" int ttg_cast(const void* x, int src_dtype, void* y, int dst_dtype, long long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) return TTG_OK;
+  int grid = ttg_grid_for(n, 1024);
+  if (src_dtype == TTG_F32 && dst_dtype == TTG_BF16) cast_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (bf16*)y, n);
+  else if (src_dtype == TTG_BF16 && dst_dtype == TTG_F32) cast_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (float*)y, n);
+  else if (src_dtype == TTG_F32 && dst_dtype == TTG_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (float*)y, n);
+  else if (src_dtype == TTG_BF16 && dst_dtype == TTG_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
+  else return ttg_set_error(TTG_ERR_ARG, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  TTG_CHECK_LAUNCH("cast");
+  return TTG_OK;
+}
+
+// tanh forward / backward (fp32 image at the generator boundary)
+__global__ void tanh_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = tanhf(x[i]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ gx, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) gx[i] = g[i] * (1.f - y[i] * y[i]);
+}
+extern "C" int ttg_tanh_fwd(const float* x, float* y, long long n, void* stream) {
+  if (n == 0) return TTG_OK;
+  tanh_fwd_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  TTG_CHECK_LAUNCH("tanh_fwd");
+  return TTG_OK;
+}
+extern "C" int ttg_tanh_bwd(const float* y, const float* g, float* gx, long long n, void* stream) {
+  if (n == 0) return TTG_OK;
+  tanh_bwd_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(y, g, gx, n);
+  TTG_CHECK_LAUNCH("tanh_bwd");
+  return TTG_OK;
+}

@@ -1,0 +1,123 @@
+"""Generator blocks — interface of tartangan/models/blocks/generator.py.
+
+Same constructors, defaults and state-dict keys; the forward passes run the
+hand-written kernels.  Fusions relative to the reference module graph: the nearest
+x2 upsample (generator.py:58) is folded into the addressing of the first 3x3 conv
+and of the 1x1 skip projection (never materialised), and each BatchNorm+LeakyReLU
+pair is one kernel.
+"""
+import functools
+
+from torch import nn
+
+from ... import ops
+from ..layers import (BatchNorm2d, Conv2d, Interpolate, LeakyReLU, Linear, Tanh, native, run_layers)
+
+
+class GeneratorBlock(nn.Module):
+    """Non-residual block (generator.py:9-29): BlockModel's default, unused by the cnn/iqn
+    trainers.  Like the reference, its first norm is sized with out_dims (Appendix B.14)."""
+
+    def __init__(self, in_dims, out_dims, upsample=True, first_block=False, norm_factory=BatchNorm2d,
+                 activation_factory=functools.partial(LeakyReLU, 0.2)):
+        super().__init__()
+        norm_factory, activation_factory = native(norm_factory), native(activation_factory)
+        layers = [norm_factory(out_dims), activation_factory(), Conv2d(in_dims, out_dims, 3, padding=1, bias=True),
+                  norm_factory(out_dims), activation_factory(), Conv2d(out_dims, out_dims, 3, padding=1, bias=True)]
+        if first_block:
+            layers = layers[2:]
+        if upsample:
+            layers.insert(0, Interpolate(scale_factor=2, mode='nearest'))
+        self.convs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return run_layers(self.convs, x)
+
+
+class ResidualGeneratorBlock(nn.Module):
+    """generator.py:32-62: up x2 -> [BN, act,] conv3 -> BN -> act -> conv3, plus (projected) skip."""
+
+    def __init__(self, in_dims, out_dims, upsample=True, first_block=False, norm_factory=BatchNorm2d,
+                 conv_factory=Conv2d, activation_factory=functools.partial(LeakyReLU, 0.2)):
+        super().__init__()
+        norm_factory, conv_factory = native(norm_factory), native(conv_factory)
+        activation_factory = native(activation_factory)
+        layers = [norm_factory(in_dims), activation_factory(), conv_factory(in_dims, out_dims, 3, padding=1),
+                  norm_factory(out_dims), activation_factory(), conv_factory(out_dims, out_dims, 3, padding=1)]
+        if first_block:
+            layers = layers[2:]
+        self.upsample = upsample
+        self.project_input = None
+        if in_dims != out_dims:
+            self.project_input = nn.Sequential(conv_factory(in_dims, out_dims, 1))
+        self.convs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = ops.ensure_internal(x)
+        if self.upsample:
+            x = ops.upsample2(x)
+        xs, xh = ops.fork(x)
+        h = run_layers(self.convs, xh)
+        if self.project_input is not None:
+            xs = run_layers(self.project_input, xs)
+        return ops.add(xs, h)
+
+
+class GeneratorInputMLP(nn.Module):
+    """generator.py:65-80: Linear(latent -> size^2*C) -> act -> view(B, C, size, size)."""
+
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None,
+                 activation_factory=functools.partial(LeakyReLU, 0.2)):
+        super().__init__()
+        self.base_img = nn.Sequential(Linear(latent_dims, size ** 2 * output_dims), native(activation_factory)())
+        self.latent_dims, self.output_dims, self.size = latent_dims, output_dims, size
+
+    def forward(self, z):
+        img = run_layers(self.base_img, z.float())
+        return ops.to_internal(img.view(-1, self.output_dims, self.size, self.size))
+
+
+class GeneratorInputMLP1d(nn.Module):
+    """generator.py:83-98 (text trainer only): constructor kept for surface parity."""
+
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None,
+                 activation_factory=functools.partial(LeakyReLU, 0.2)):
+        super().__init__()
+        self.base = nn.Sequential(Linear(latent_dims, size * output_dims), native(activation_factory)())
+        self.latent_dims, self.output_dims, self.size = latent_dims, output_dims, size
+
+    def forward(self, z):
+        return run_layers(self.base, z.float()).view(-1, self.output_dims, self.size)
+
+
+class TiledZGeneratorInput(nn.Module):
+    """generator.py:101-112: z tiled over a size x size grid (requires latent_dims == output_dims)."""
+
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None, **_):
+        super().__init__()
+        self.size = size
+        assert latent_dims == output_dims
+
+    def forward(self, z):
+        b, c = z.shape
+        return ops.SpatialBcastFn.apply(z.float(), (b, c, self.size, self.size), ops.state.act_dtype)
+
+
+class GeneratorOutput(nn.Module):
+    """generator.py:115-129: BN -> act -> conv1x1(C -> data_dims) -> tanh; returns fp32 NCHW."""
+
+    def __init__(self, in_dims, out_dims, norm_factory=BatchNorm2d, conv_factory=Conv2d,
+                 activation_factory=functools.partial(LeakyReLU, 0.2), output_activation_factory=Tanh):
+        super().__init__()
+        self.convs = nn.Sequential(
+            native(norm_factory)(in_dims), native(activation_factory)(),
+            native(conv_factory)(in_dims, out_dims, 1, padding=0, bias=True),
+            native(output_activation_factory)())
+
+    def forward(self, x):
+        layers = list(self.convs)
+        x = run_layers(layers[:2], ops.ensure_internal(x))
+        conv = layers[2]
+        x = conv(x, out_dtype=ops.torch.float32) if isinstance(conv, Conv2d) else conv(x)
+        x = run_layers(layers[3:], x)
+        return ops.from_internal(x)

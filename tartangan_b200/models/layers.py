@@ -1,0 +1,121 @@
+"""Leaf modules: parameter containers identical to torch.nn's (same init, same
+state-dict keys) whose forward runs the sm_100a kernels.  Mirrors the leaf modules
+the reference uses (nn.Conv2d / nn.BatchNorm2d / nn.LeakyReLU / nn.Linear /
+nn.AvgPool2d / nn.Tanh) plus tartangan/models/layers.py (Interpolate, PixelNorm).
+"""
+import functools
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d restricted to what the reference path uses: k in {1,3}, stride 1, padding k//2."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, **kw):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=bias, **kw)
+        k = self.kernel_size[0]
+        if (self.kernel_size not in ((1, 1), (3, 3)) or self.stride != (1, 1) or self.padding != (k // 2, k // 2)
+                or self.dilation != (1, 1) or self.groups != 1):
+            raise NotImplementedError('tartangan_b200.Conv2d supports kernel 1 or 3, stride 1, padding k//2 '
+                                      f'(got k={self.kernel_size}, stride={self.stride}, padding={self.padding})')
+
+    def forward(self, x, up=0, out_dtype=None):
+        return ops.conv2d(ops.ensure_internal(x), self.weight, self.bias, up, out_dtype)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d; blocks fuse it with the following LeakyReLU (ops.bn_act)."""
+
+    def forward(self, x, slope=1.0):
+        return ops.bn_act(ops.ensure_internal(x), self, slope)
+
+
+class LeakyReLU(nn.LeakyReLU):
+    def forward(self, x):
+        return ops.leaky_relu(x, self.negative_slope)
+
+
+class AvgPool2d(nn.AvgPool2d):
+    def __init__(self, kernel_size=2, **kw):
+        super().__init__(kernel_size, **kw)
+        if self.kernel_size not in (2, (2, 2)):
+            raise NotImplementedError('tartangan_b200.AvgPool2d supports kernel_size=2 only')
+
+    def forward(self, x):
+        return ops.avg_pool2(x)
+
+
+class Linear(nn.Linear):
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
+class Tanh(nn.Tanh):
+    def forward(self, x):
+        return ops.tanh(x)
+
+
+class Interpolate(nn.Module):
+    """tartangan/models/layers.py:6-13; only the two modes the blocks use are implemented."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.args, self.kwargs = args, kwargs
+
+    def forward(self, x):
+        return interpolate(x, *self.args, **self.kwargs)
+
+
+def interpolate(x, size=None, scale_factor=None, mode='nearest', align_corners=None):
+    x = ops.ensure_internal(x)
+    if size is None and scale_factor == 2 and mode == 'nearest':
+        return ops.upsample2(x)
+    if size is None and scale_factor == 0.5 and mode == 'bilinear' and align_corners:
+        return ops.bilinear_down(x)
+    raise NotImplementedError(f'tartangan_b200.interpolate: scale_factor={scale_factor}, mode={mode}, '
+                              f'align_corners={align_corners} is not on the reference path')
+
+
+class PixelNorm(nn.Module):
+    """tartangan/models/layers.py:16-22 (imported by trainers/iqn.py, never instantiated there)."""
+
+    def __init__(self, eps=1e-8):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, x):
+        raise NotImplementedError('PixelNorm is not used by the cnn/iqn trainers; no kernel is provided')
+
+
+def native(factory):
+    """Map a torch.nn factory handed to a block constructor onto the kernel-backed twin."""
+    table = {nn.Conv2d: Conv2d, nn.BatchNorm2d: BatchNorm2d, nn.LeakyReLU: LeakyReLU,
+             nn.AvgPool2d: AvgPool2d, nn.Linear: Linear, nn.Tanh: Tanh}
+    if isinstance(factory, functools.partial):
+        return functools.partial(native(factory.func), *factory.args, **factory.keywords)
+    if factory in table:
+        return table[factory]
+    if factory in (nn.SELU, nn.ELU):
+        raise NotImplementedError('tartangan_b200: --activation selu/elu has no kernel yet; use relu (LeakyReLU 0.2)')
+    return factory
+
+
+def run_layers(layers, x):
+    """Run an nn.Sequential-style list, fusing (BatchNorm2d | Identity) + LeakyReLU pairs into one op."""
+    layers = list(layers)
+    i = 0
+    while i < len(layers):
+        m = layers[i]
+        nxt = layers[i + 1] if i + 1 < len(layers) else None
+        if isinstance(m, BatchNorm2d) and isinstance(nxt, LeakyReLU):
+            x = ops.bn_act(ops.ensure_internal(x), m, nxt.negative_slope)
+            i += 2
+        elif isinstance(m, nn.Identity):
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    return x

@@ -1,0 +1,1035 @@
+"""Differentiable operators over the C ABI (include/ttg_b200.h).
+
+Every operator is a ``torch.autograd.Function`` whose forward launches the
+hand-written kernels through ``_lib.call`` and whose backward is itself written in
+terms of these operators, never ``once_differentiable`` where the R1 penalty
+(reference models/losses.py:17-30, ``create_graph=True``) needs a second backward:
+conv fprop/dgrad/wgrad, BatchNorm+LeakyReLU, pooling, bilinear, sum-pool, Linear,
+the IQN head, max-pool, bmm and softmax are all closed under differentiation here.
+
+Activation tensors keep the reference's logical NCHW shape but live in NHWC memory
+(``torch.channels_last`` strides); their dtype (fp32 or bf16) is the precision mode.
+PyTorch is used for allocation, streams and autograd bookkeeping only.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import call, ptr, dtype_code
+
+SLOPE = 0.2
+
+
+class _State:
+    act_dtype = torch.bfloat16     # precision mode for activations ('bf16' default)
+    inputs_only = False            # set by gradient_penalty: skip parameter gradients
+    use_tc = False                 # tensor-core conv kernels when shapes allow (off until conv_tc lands)
+    launches = 0                   # kernels launched through the C ABI (bench counter)
+
+
+state = _State()
+
+
+def set_precision(mode):
+    """'bf16' (bf16 activations / tensor-core convs) or 'fp32' (exact CUDA-core path)."""
+    state.act_dtype = {'bf16': torch.bfloat16, 'fp32': torch.float32}[mode]
+
+
+def get_precision():
+    return 'bf16' if state.act_dtype == torch.bfloat16 else 'fp32'
+
+
+class inputs_only_grads:
+    """Context: backward passes inside compute gradients w.r.t. activations only
+    (the R1 penalty differentiates w.r.t. the real images, models/losses.py:23-26)."""
+
+    def __enter__(self):
+        self.prev, state.inputs_only = state.inputs_only, True
+
+    def __exit__(self, *a):
+        state.inputs_only = self.prev
+
+
+# --------------------------------------------------------------------------- helpers
+def _is_nhwc(x):
+    return x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def nhwc(x):
+    """Return x in NHWC memory (logical NCHW).  Gradients produced by these ops already are."""
+    if _is_nhwc(x):
+        return x
+    return x.contiguous(memory_format=torch.channels_last) if x.dim() == 4 else x.contiguous()
+
+
+def empty_nhwc(n, c, h, w, dtype, device):
+    return torch.empty((n, h, w, c), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def _empty_like(x):
+    if x.dim() == 4:
+        n, c, h, w = x.shape
+        return empty_nhwc(n, c, h, w, x.dtype, x.device)
+    return torch.empty(x.shape, dtype=x.dtype, device=x.device)
+
+
+def _ws(nbytes, device):
+    return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+
+def _flat(x):
+    return x if x.is_contiguous() else x.contiguous()
+
+
+# --------------------------------------------------------------------------- layout boundary
+class ToInternal(Function):
+    """fp32 NCHW (reference layout, trainers/trainer.py:57-61) -> NHWC activation dtype."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        n, c, h, w = x.shape
+        x = x.float() if x.dtype != torch.float32 else x
+        y = empty_nhwc(n, c, h, w, dtype, x.device)
+        if _is_nhwc(x) and not x.is_contiguous():
+            call('ttg_cast', ptr(x), _lib.F32, ptr(y), dtype_code(dtype), x.numel())
+        else:
+            call('ttg_nchw_to_nhwc', ptr(x.contiguous()), ptr(y), n, c, h * w, dtype_code(dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return FromInternal.apply(g), None
+
+
+class FromInternal(Function):
+    """NHWC activation -> fp32 NCHW contiguous."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dtype = x.dtype
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call('ttg_nhwc_to_nchw', ptr(x), ptr(y), n, c, h * w, dtype_code(x.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToInternal.apply(g, ctx.dtype)
+
+
+def to_internal(x, dtype=None):
+    return ToInternal.apply(x, dtype or state.act_dtype)
+
+
+def from_internal(x):
+    return FromInternal.apply(x)
+
+
+# --------------------------------------------------------------------------- convolution
+_pack_cache = {}
+
+
+def _packed(w, mode, kind):
+    """Packed copy of a conv weight, cached on (storage, version)."""
+    key = (w.data_ptr(), kind, mode)
+    # _version catches in-place torch updates; _ttg_epoch is bumped by FusedAdam, whose kernel
+    # writes the flat parameter buffer behind autograd's back.
+    ver = (w._version, getattr(w, '_ttg_epoch', 0))
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1].device == w.device and hit[2] == tuple(w.shape):
+        return hit[1]
+    cout, cin, k, _ = w.shape
+    wd = w.detach()
+    wd = wd if wd.is_contiguous() else wd.contiguous()
+    if kind == 'direct':
+        wp = torch.empty(k * k * cin * cout, dtype=torch.float32, device=w.device)
+        call('ttg_pack_weight_direct', ptr(wd), ptr(wp), cout, cin, k, mode)
+    else:
+        nbytes = _lib.lib.ttg_pack_weight_tc_bytes(cout, cin, k)
+        wp = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        call('ttg_pack_weight_tc', ptr(wd), ptr(wp), cout, cin, k, mode)
+    if len(_pack_cache) > 4096:
+        _pack_cache.clear()
+    _pack_cache[key] = (ver, wp, tuple(w.shape))
+    return wp
+
+
+def _tc_ok(dtype, cin, cout):
+    return state.use_tc and dtype == torch.bfloat16 and cin % 16 == 0 and cout % 16 == 0 and cin <= 256 and cout <= 256
+
+
+def _conv_raw(x, w, bias, mode, up, out_dtype=None):
+    """y = conv(x) with w packed in `mode` (0 fprop: w is OIHW; 1 dgrad: roles swapped)."""
+    x = nhwc(x)
+    n, cx, hi, wi = x.shape
+    cout, cin, k, _ = w.shape
+    c_in_eff, c_out_eff = (cin, cout) if mode == 0 else (cout, cin)
+    assert cx == c_in_eff, f'conv: input has {cx} channels, weight expects {c_in_eff}'
+    h, wd_ = hi << up, wi << up
+    out_dtype = out_dtype or x.dtype
+    y = empty_nhwc(n, c_out_eff, h, wd_, out_dtype, x.device)
+    if _tc_ok(x.dtype, cin, cout) and out_dtype in (torch.bfloat16, torch.float32):
+        wp = _packed(w, mode, 'tc')
+        call('ttg_conv2d_tc', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, up,
+             dtype_code(out_dtype))
+    else:
+        wp = _packed(w, mode, 'direct')
+        call('ttg_conv2d_direct', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, up,
+             dtype_code(x.dtype), dtype_code(out_dtype))
+    return y
+
+
+class Conv2dFn(Function):
+    """nn.Conv2d(k in {1,3}, padding=k//2) with optional nearest x2 upsample of the input folded in."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, up, out_dtype):
+        ctx.save_for_backward(x, w)
+        ctx.up, ctx.has_bias, ctx.in_dtype = up, bias is not None, x.dtype
+        return _conv_raw(x, w, bias, 0, up, out_dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = gb = None
+        if gy.dtype != ctx.in_dtype:
+            gy = CastFn.apply(gy, ctx.in_dtype)
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgradFn.apply(gy, w, ctx.up)
+        if not state.inputs_only:
+            if ctx.needs_input_grad[1]:
+                gw = ConvWgradFn.apply(x, gy, w.shape[2], ctx.up)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ChannelSumFn.apply(gy)
+        return gx, gw, gb, None, None
+
+
+class ConvDgradFn(Function):
+    """gx = conv(gy, flipped/transposed w); with up=1 followed by the adjoint of nearest upsample."""
+
+    @staticmethod
+    def forward(ctx, gy, w, up):
+        ctx.save_for_backward(gy, w)
+        ctx.up = up
+        gx = _conv_raw(gy, w, None, 1, 0)
+        if up:
+            gx = _pool2(gx, 1.0)
+        return gx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, w = ctx.saved_tensors
+        g_gy = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_gy = Conv2dFn.apply(ggx, w, None, ctx.up, None)
+        if ctx.needs_input_grad[1] and not state.inputs_only:
+            g_w = ConvWgradFn.apply(ggx, gy, w.shape[2], ctx.up)
+        return g_gy, g_w, None
+
+
+class ConvWgradFn(Function):
+    """gw[co,ci,ky,kx] = sum_pixels gy[p,co] * x[p+tap,ci]  (fp32, OIHW)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, k, up):
+        ctx.save_for_backward(x, gy)
+        ctx.k, ctx.up = k, up
+        x, gy = nhwc(x), nhwc(gy)
+        n, cout, h, w = gy.shape
+        cin = x.shape[1]
+        gw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
+        if _tc_ok(x.dtype, cin, cout) and gy.dtype == torch.bfloat16:
+            ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
+            call('ttg_conv2d_wgrad_tc', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up, ptr(ws))
+        else:
+            call('ttg_conv2d_wgrad_direct', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up,
+                 dtype_code(x.dtype), dtype_code(gy.dtype))
+        return gw
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        g_x = g_gy = None
+        if ctx.needs_input_grad[0]:
+            g_x = ConvDgradFn.apply(gy, ggw, ctx.up)
+        if ctx.needs_input_grad[1]:
+            g_gy = Conv2dFn.apply(x, ggw, None, ctx.up, None)
+        return g_x, g_gy, None, None
+
+
+def conv2d(x, w, bias=None, up=0, out_dtype=None):
+    return Conv2dFn.apply(x, w, bias, up, out_dtype)
+
+
+class ChannelSumFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        n, c, h, w = x.shape
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
+        call('ttg_channel_sum', ptr(x), n * h * w, c, ptr(out), ptr(_ws(8 * c, x.device)), dtype_code(x.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n, c, h, w = ctx.shape
+        return g.to(ctx.dtype).view(1, c, 1, 1).expand(n, c, h, w)
+
+
+class CastFn(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        y = torch.empty_like(x, dtype=dtype)
+        call('ttg_cast', ptr(x), dtype_code(x.dtype), ptr(y), dtype_code(dtype), x.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return CastFn.apply(g, ctx.src), None
+
+
+# --------------------------------------------------------------------------- BatchNorm + LeakyReLU
+class BnActFn(Function):
+    """lrelu(batch_norm(x)) with batch statistics (train) or running statistics (eval)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, training, momentum, eps, slope):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        m = n * h * w
+        dev = x.device
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        invstd = torch.empty(c, dtype=torch.float32, device=dev)
+        if training:
+            ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
+            call('ttg_bn_stats', ptr(x), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
+                 ptr(running_var), ptr(num_batches), ptr(ws), dtype_code(x.dtype))
+        else:
+            call('ttg_bn_eval_stats', ptr(running_mean), ptr(running_var), eps, c, ptr(mean), ptr(invstd))
+        y = _empty_like(x)
+        call('ttg_bn_act_fwd', ptr(x), ptr(y), m, c, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), slope,
+             dtype_code(x.dtype))
+        ctx.save_for_backward(x, gamma, beta, mean, invstd)
+        ctx.slope, ctx.training = slope, training
+        return y
+
+    @staticmethod
+    def backward(ctx, ga):
+        if not ctx.training:
+            raise NotImplementedError('tartangan_b200: backward through eval-mode BatchNorm is not on the '
+                                      'reference path (D/G are always in train mode) and is not implemented')
+        x, gamma, beta, mean, invstd = ctx.saved_tensors
+        gx, ggamma, gbeta = BnActBwdFn.apply(x, ga, gamma, beta, mean, invstd, ctx.slope)
+        if state.inputs_only:
+            ggamma = gbeta = None
+        return gx, ggamma, gbeta, None, None, None, None, None, None, None
+
+
+class BnActBwdFn(Function):
+    @staticmethod
+    def forward(ctx, x, ga, gamma, beta, mean, invstd, slope):
+        x, ga = nhwc(x), nhwc(ga)
+        n, c, h, w = x.shape
+        dev = x.device
+        gx = _empty_like(x)
+        ggamma = torch.empty(c, dtype=torch.float32, device=dev)
+        gbeta = torch.empty(c, dtype=torch.float32, device=dev)
+        ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
+        call('ttg_bn_act_bwd', ptr(x), ptr(ga), ptr(gx), n * h * w, c, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta),
+             slope, ptr(ggamma), ptr(gbeta), ptr(ws), dtype_code(x.dtype))
+        ctx.save_for_backward(x, ga, gamma, beta, mean, invstd)
+        ctx.slope = slope
+        ctx.set_materialize_grads(False)
+        return gx, ggamma, gbeta
+
+    @staticmethod
+    def backward(ctx, u, u_gamma, u_beta):
+        if u_gamma is not None or u_beta is not None:
+            raise NotImplementedError('tartangan_b200: differentiating BatchNorm parameter gradients is not '
+                                      'supported (only d(input grad) is needed by the R1 penalty)')
+        if u is None:
+            return (None,) * 7
+        x, ga, gamma, beta, mean, invstd = ctx.saved_tensors
+        u = nhwc(u)
+        n, c, h, w = x.shape
+        dev = x.device
+        g_ga, g_x = _empty_like(x), _empty_like(x)
+        g_gamma = None if state.inputs_only else torch.empty(c, dtype=torch.float32, device=dev)
+        ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
+        call('ttg_bn_act_bwd2', ptr(x), ptr(ga), ptr(u), ptr(g_ga), ptr(g_x), n * h * w, c, ptr(mean), ptr(invstd),
+             ptr(gamma), ptr(beta), ctx.slope, ptr(g_gamma), ptr(ws), dtype_code(x.dtype))
+        return g_x, g_ga, g_gamma, None, None, None, None
+
+
+def bn_act(x, bn, slope=SLOPE):
+    """x -> lrelu(bn(x)) for an nn.BatchNorm2d-compatible module `bn` (or identity norm if None)."""
+    if bn is None:
+        return leaky_relu(x, slope)
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                         bn.training or bn.running_mean is None, bn.momentum, bn.eps, slope)
+
+
+class LeakyReluFn(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        ctx.save_for_backward(x)
+        ctx.slope = slope
+        y = _empty_like(x)
+        call('ttg_lrelu_fwd', ptr(x), ptr(y), x.numel(), slope, dtype_code(x.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return LeakyReluMaskFn.apply(x, g, ctx.slope), None
+
+
+class LeakyReluMaskFn(Function):
+    """out = g * lrelu'(x); linear in g, piecewise constant in x."""
+
+    @staticmethod
+    def forward(ctx, x, g, slope):
+        g = (nhwc(g) if g.dim() == 4 else _flat(g))
+        ctx.save_for_backward(x)
+        ctx.slope = slope
+        out = _empty_like(x)
+        call('ttg_lrelu_bwd', ptr(x), ptr(g), ptr(out), x.numel(), slope, dtype_code(x.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        x, = ctx.saved_tensors
+        return None, LeakyReluMaskFn.apply(x, u, ctx.slope), None
+
+
+def leaky_relu(x, slope=SLOPE):
+    return LeakyReluFn.apply(x, slope)
+
+
+# --------------------------------------------------------------------------- resampling
+def _pool2(x, scale):
+    x = nhwc(x)
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+    call('ttg_pool2_sum', ptr(x), ptr(y), n, h // 2, w // 2, c, scale, dtype_code(x.dtype))
+    return y
+
+
+def _up2(x, scale):
+    x = nhwc(x)
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, c, h * 2, w * 2, x.dtype, x.device)
+    call('ttg_upsample2', ptr(x), ptr(y), n, h, w, c, scale, dtype_code(x.dtype))
+    return y
+
+
+class Pool2Fn(Function):
+    """scale * 2x2 sum (AvgPool2d(2) when scale=0.25)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return _pool2(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Up2Fn.apply(g, ctx.scale), None
+
+
+class Up2Fn(Function):
+    """scale * nearest x2 upsample."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return _up2(x, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        return Pool2Fn.apply(g, ctx.scale), None
+
+
+def avg_pool2(x):
+    return Pool2Fn.apply(x, 0.25)
+
+
+def upsample2(x):
+    return Up2Fn.apply(x, 1.0)
+
+
+class BilinearDownFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        call('ttg_bilinear_down_fwd', ptr(x), ptr(y), n, h, w, c, dtype_code(x.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return BilinearDownTFn.apply(g)
+
+
+class BilinearDownTFn(Function):
+    @staticmethod
+    def forward(ctx, g):
+        g = nhwc(g)
+        n, c, ho, wo = g.shape
+        gx = empty_nhwc(n, c, ho * 2, wo * 2, g.dtype, g.device)
+        call('ttg_bilinear_down_bwd', ptr(g), ptr(gx), n, ho * 2, wo * 2, c, dtype_code(g.dtype))
+        return gx
+
+    @staticmethod
+    def backward(ctx, u):
+        return BilinearDownFn.apply(u)
+
+
+def bilinear_down(x):
+    return BilinearDownFn.apply(x)
+
+
+class AxpbyFn(Function):
+    """alpha*a + beta*b (same shape/dtype)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        ctx.alpha, ctx.beta = alpha, beta
+        if a.dim() == 4:
+            a, b = nhwc(a), nhwc(b)
+        else:
+            a, b = _flat(a), _flat(b)
+        out = _empty_like(a)
+        call('ttg_axpby', ptr(a), ptr(b), ptr(out), a.numel(), alpha, beta, dtype_code(a.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ga = g if ctx.alpha == 1.0 else ScaleFn.apply(g, ctx.alpha)
+        gb = g if ctx.beta == 1.0 else ScaleFn.apply(g, ctx.beta)
+        return ga, gb, None, None
+
+
+class ScaleFn(Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        out = _empty_like(x)
+        call('ttg_axpby', ptr(x), ptr(x), ptr(out), x.numel(), s, 0.0, dtype_code(x.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ScaleFn.apply(g, ctx.s), None
+
+
+def add(a, b):
+    return AxpbyFn.apply(a, b, 1.0, 1.0)
+
+
+def scale(x, s):
+    return ScaleFn.apply(x, float(s))
+
+
+class ForkFn(Function):
+    """Identity with two consumers; the backward adds the two gradients with our own kernel
+    instead of autograd's implicit accumulation."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None:
+            return g2
+        if g2 is None:
+            return g1
+        return AxpbyFn.apply(g1, g2, 1.0, 1.0)
+
+
+def fork(x):
+    return ForkFn.apply(x)
+
+
+class SpatialSumFn(Function):
+    """(N,C,H,W) -> fp32 (N,C): torch.sum(feats, [2,3])."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        n, c, h, w = x.shape
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        call('ttg_spatial_sum', ptr(x), ptr(out), n, h * w, c, dtype_code(x.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return SpatialBcastFn.apply(g, ctx.shape, ctx.dtype)
+
+
+class SpatialBcastFn(Function):
+    @staticmethod
+    def forward(ctx, g, shape, dtype):
+        n, c, h, w = shape
+        g = _flat(g)
+        out = empty_nhwc(n, c, h, w, dtype, g.device)
+        call('ttg_spatial_bcast', ptr(g), ptr(out), n, h * w, c, dtype_code(dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        return SpatialSumFn.apply(u), None, None
+
+
+def spatial_sum(x):
+    return SpatialSumFn.apply(x)
+
+
+class TanhFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        y = _empty_like(x)
+        call('ttg_tanh_fwd', ptr(x), ptr(y), x.numel())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        y, = ctx.saved_tensors
+        g = nhwc(g) if g.dim() == 4 else _flat(g)
+        gx = _empty_like(y)
+        call('ttg_tanh_bwd', ptr(y), ptr(g), ptr(gx), y.numel())
+        return gx
+
+
+def tanh(x):
+    return TanhFn.apply(x)
+
+
+# --------------------------------------------------------------------------- fp32 matmul / Linear
+def _mm(a, b, bias, ta, tb):
+    a, b = _flat(a), _flat(b)
+    m = a.shape[1] if ta else a.shape[0]
+    k = a.shape[0] if ta else a.shape[1]
+    n = b.shape[0] if tb else b.shape[1]
+    kb = b.shape[1] if tb else b.shape[0]
+    assert k == kb, (a.shape, b.shape, ta, tb)
+    out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    call('ttg_matmul_f32', ptr(a), ptr(b), ptr(bias), ptr(out), m, n, k, int(ta), int(tb))
+    return out
+
+
+class MatmulFn(Function):
+    """C = op(A) op(B) in fp32; closed under differentiation through the transpose flags."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb):
+        ctx.save_for_backward(a, b)
+        ctx.ta, ctx.tb = ta, tb
+        return _mm(a, b, None, ta, tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = MatmulFn.apply(g, b, False, not tb) if not ta else MatmulFn.apply(b, g, tb, True)
+        if ctx.needs_input_grad[1]:
+            gb = MatmulFn.apply(a, g, not ta, False) if not tb else MatmulFn.apply(g, a, True, ta)
+        return ga, gb, None, None
+
+
+class ColsumFn(Function):
+    """out[n] = scale * sum_m x[m,n]."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = _flat(x)
+        ctx.m, ctx.scale = x.shape[0], scale
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+        call('ttg_colsum_f32', ptr(x), ptr(out), x.shape[0], x.shape[1], scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return RowBcastFn.apply(g, ctx.m, ctx.scale), None
+
+
+class RowBcastFn(Function):
+    """out[m,n] = scale * g[n]."""
+
+    @staticmethod
+    def forward(ctx, g, m, scale):
+        g = _flat(g)
+        ctx.scale = scale
+        out = torch.empty((m, g.shape[0]), dtype=torch.float32, device=g.device)
+        call('ttg_rowbcast_f32', ptr(g), ptr(out), m, g.shape[0], scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        return ColsumFn.apply(u, ctx.scale), None, None
+
+
+class LinearFn(Function):
+    """y = x W^T + b (nn.Linear), fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return _mm(x, w, b, False, True)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = MatmulFn.apply(g, w, False, False)
+        if not state.inputs_only:
+            if ctx.needs_input_grad[1]:
+                gw = MatmulFn.apply(g, x, True, False)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                gb = ColsumFn.apply(g, 1.0)
+        return gx, gw, gb
+
+
+def linear(x, w, b=None):
+    return LinearFn.apply(x, w, b)
+
+
+# --------------------------------------------------------------------------- IQN head and losses
+class IqnHeadFn(Function):
+    """p_tau[r] for rows r = q*B + b (models/iqn.py:91-103 + Linear(C->1))."""
+
+    @staticmethod
+    def forward(ctx, feats, taus, we, be, wo, bo, nq):
+        feats, taus = _flat(feats), _flat(taus)
+        b, c = feats.shape
+        e = we.shape[1]
+        p_tau = torch.empty(b * nq, dtype=torch.float32, device=feats.device)
+        call('ttg_iqn_head_fwd', ptr(feats), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), ptr(bo), ptr(p_tau),
+             None, b, nq, c, e)
+        ctx.save_for_backward(feats, taus, we, be, wo)
+        ctx.nq = nq
+        return p_tau
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, taus, we, be, wo = ctx.saved_tensors
+        gf, gwe, gbe, gwo, gbo = IqnHeadBwdFn.apply(g, feats, taus, we, be, wo, ctx.nq)
+        if state.inputs_only:
+            gwe = gbe = gwo = gbo = None
+        return gf, None, gwe, gbe, gwo, gbo, None
+
+
+class IqnHeadBwdFn(Function):
+    @staticmethod
+    def forward(ctx, g, feats, taus, we, be, wo, nq):
+        g = _flat(g)
+        b, c = feats.shape
+        e = we.shape[1]
+        dev = feats.device
+        gf = torch.empty((b, c), dtype=torch.float32, device=dev)
+        gwe = torch.empty((c, e), dtype=torch.float32, device=dev)
+        gbe = torch.empty(c, dtype=torch.float32, device=dev)
+        gwo = torch.empty(wo.shape, dtype=torch.float32, device=dev)
+        gbo = torch.empty(1, dtype=torch.float32, device=dev)
+        call('ttg_iqn_head_bwd', ptr(g), ptr(feats), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), ptr(gf),
+             ptr(gwe), ptr(gbe), ptr(gwo), ptr(gbo), b, nq, c, e)
+        ctx.save_for_backward(g, taus, we, be, wo)
+        ctx.nq = nq
+        ctx.set_materialize_grads(False)
+        return gf, gwe, gbe, gwo, gbo
+
+    @staticmethod
+    def backward(ctx, ggf, ggwe, ggbe, ggwo, ggbo):
+        if any(t is not None for t in (ggwe, ggbe, ggwo, ggbo)):
+            raise NotImplementedError('tartangan_b200: second derivatives of IQN-head parameter gradients are '
+                                      'not supported (the R1 penalty only differentiates d p / d feats)')
+        if ggf is None:
+            return (None,) * 7
+        # gf = sum_q g * e(We,be,tau) * wo is independent of feats and has the same form as the forward
+        # with feats := ggf: d/dg is the forward itself (no bias), d/d(We,be,wo) is the backward.
+        g, taus, we, be, wo = ctx.saved_tensors
+        ggf = _flat(ggf)
+        b, c = ggf.shape
+        e = we.shape[1]
+        dev = ggf.device
+        cot_g = torch.empty(b * ctx.nq, dtype=torch.float32, device=dev)
+        call('ttg_iqn_head_fwd', ptr(ggf), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), None, ptr(cot_g), None,
+             b, ctx.nq, c, e)
+        gwe = gbe = gwo = None
+        if not state.inputs_only:
+            gwe = torch.empty((c, e), dtype=torch.float32, device=dev)
+            gbe = torch.empty(c, dtype=torch.float32, device=dev)
+            gwo = torch.empty(wo.shape, dtype=torch.float32, device=dev)
+            call('ttg_iqn_head_bwd', ptr(g), ptr(ggf), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), None,
+                 ptr(gwe), ptr(gbe), ptr(gwo), None, b, ctx.nq, c, e)
+        return cot_g, None, None, gwe, gbe, gwo, None
+
+
+class QuantileHuberFn(Function):
+    """iqn_loss (models/iqn.py:111-130)."""
+
+    @staticmethod
+    def forward(ctx, p_tau, target, taus, nq, k):
+        p_tau, target, taus = _flat(p_tau), _flat(target), _flat(taus)
+        b = target.numel()
+        loss = torch.empty((), dtype=torch.float32, device=p_tau.device)
+        call('ttg_quantile_huber_fwd', ptr(p_tau), ptr(target), ptr(taus), ptr(loss), b, nq, k)
+        ctx.save_for_backward(p_tau, target, taus)
+        ctx.nq, ctx.k = nq, k
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gloss):
+        p_tau, target, taus = ctx.saved_tensors
+        gp = torch.empty_like(p_tau)
+        call('ttg_quantile_huber_bwd', ptr(p_tau), ptr(target), ptr(taus), ptr(_flat(gloss)), ptr(gp),
+             target.numel(), ctx.nq, ctx.k)
+        return gp, None, None, None, None
+
+
+class BceLogitsFn(Function):
+    """nn.BCEWithLogitsLoss() (mean)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _flat(x), _flat(y)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        call('ttg_bce_logits_fwd', ptr(x), ptr(y), ptr(loss), x.numel())
+        ctx.save_for_backward(x, y)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gloss):
+        x, y = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        call('ttg_bce_logits_bwd', ptr(x), ptr(y), ptr(_flat(gloss)), ptr(gx), x.numel())
+        return gx, None
+
+
+class SqsumFn(Function):
+    """scale * sum(x^2) over an fp32 tensor (R1 reduction, models/losses.py:27-29)."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = _flat(x)
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        call('ttg_sqsum_f32', ptr(x), x.numel(), scale, ptr(out), ptr(_ws(8, x.device)))
+        ctx.save_for_backward(x)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return ScaleByDevFn.apply(x, g, 2.0 * ctx.scale), None
+
+
+class ScaleByDevFn(Function):
+    """x * (host * s) with s a device scalar (fp32 tensors)."""
+
+    @staticmethod
+    def forward(ctx, x, s, host):
+        x = _flat(x)
+        out = torch.empty_like(x)
+        call('ttg_scale_f32', ptr(x), ptr(out), x.numel(), host, ptr(_flat(s)))
+        ctx.save_for_backward(s)
+        ctx.host = host
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        s, = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError('tartangan_b200: gradient w.r.t. the scalar of ScaleByDevFn')
+        return ScaleByDevFn.apply(u, s, ctx.host), None, None
+
+
+# --------------------------------------------------------------------------- attention primitives
+class MaxPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        idx = torch.empty(n * (h // 2) * (w // 2) * c, dtype=torch.uint8, device=x.device)
+        call('ttg_maxpool2_fwd', ptr(x), ptr(y), ptr(idx), n, h // 2, w // 2, c, dtype_code(x.dtype))
+        ctx.save_for_backward(idx)
+        ctx.mark_non_differentiable(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, = ctx.saved_tensors
+        return MaxPoolScatterFn.apply(g, idx)
+
+
+class MaxPoolScatterFn(Function):
+    @staticmethod
+    def forward(ctx, g, idx):
+        g = nhwc(g)
+        n, c, ho, wo = g.shape
+        gx = empty_nhwc(n, c, ho * 2, wo * 2, g.dtype, g.device)
+        call('ttg_maxpool2_scatter', ptr(g), ptr(idx), ptr(gx), n, ho, wo, c, dtype_code(g.dtype))
+        ctx.save_for_backward(idx)
+        return gx
+
+    @staticmethod
+    def backward(ctx, u):
+        idx, = ctx.saved_tensors
+        return MaxPoolGatherFn.apply(u, idx), None
+
+
+class MaxPoolGatherFn(Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        call('ttg_maxpool2_gather', ptr(x), ptr(idx), ptr(y), n, h // 2, w // 2, c, dtype_code(x.dtype))
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, = ctx.saved_tensors
+        return MaxPoolScatterFn.apply(g, idx), None
+
+
+def max_pool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+def _bmm(a, b, ta, tb):
+    a, b = _flat(a), _flat(b)
+    bt = a.shape[0]
+    m = a.shape[2] if ta else a.shape[1]
+    k = a.shape[1] if ta else a.shape[2]
+    n = b.shape[1] if tb else b.shape[2]
+    out = torch.empty((bt, m, n), dtype=a.dtype, device=a.device)
+    call('ttg_bmm', ptr(a), ptr(b), ptr(out), bt, m, n, k, int(ta), int(tb), dtype_code(a.dtype))
+    return out
+
+
+class BmmFn(Function):
+    """Batched op(A) op(B) on (batch, rows, cols) tensors, fp32 accumulate."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb):
+        ctx.save_for_backward(a, b)
+        ctx.ta, ctx.tb = ta, tb
+        return _bmm(a, b, ta, tb)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.ta, ctx.tb
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = BmmFn.apply(g, b, False, not tb) if not ta else BmmFn.apply(b, g, tb, True)
+        if ctx.needs_input_grad[1]:
+            gb = BmmFn.apply(a, g, not ta, False) if not tb else BmmFn.apply(g, a, True, ta)
+        return ga, gb, None, None
+
+
+class SoftmaxFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _flat(x)
+        y = torch.empty_like(x)
+        call('ttg_softmax_fwd', ptr(x), ptr(y), x.numel() // x.shape[-1], x.shape[-1], dtype_code(x.dtype))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, = ctx.saved_tensors
+        return SoftmaxBwdFn.apply(y, g)
+
+
+class SoftmaxBwdFn(Function):
+    @staticmethod
+    def forward(ctx, y, g):
+        g = _flat(g)
+        gx = torch.empty_like(y)
+        call('ttg_softmax_bwd', ptr(y), ptr(g), ptr(gx), y.numel() // y.shape[-1], y.shape[-1], dtype_code(y.dtype))
+        ctx.save_for_backward(y, g)
+        return gx
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, w):
+        y, g = ctx.saved_tensors
+        w = _flat(w)
+        cot_g, cot_y = torch.empty_like(y), torch.empty_like(y)
+        call('ttg_softmax_bwd2', ptr(y), ptr(g), ptr(w), ptr(cot_g), ptr(cot_y), y.numel() // y.shape[-1],
+             y.shape[-1], dtype_code(y.dtype))
+        return cot_y, cot_g
+
+
+class ScaleDevFn(Function):
+    """x * s with s a one-element fp32 device tensor (attention gamma)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        out = _empty_like(x)
+        call('ttg_scale_dev', ptr(x), ptr(out), x.numel(), ptr(s), dtype_code(x.dtype))
+        ctx.save_for_backward(x, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        gx = ScaleDevFn.apply(g, s) if ctx.needs_input_grad[0] else None
+        gs = None
+        if ctx.needs_input_grad[1] and not state.inputs_only:
+            gs = DotFn.apply(g, x).reshape(s.shape)
+        return gx, gs
+
+
+class DotFn(Function):
+    """sum(a*b) -> fp32 scalar."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a = nhwc(a) if a.dim() == 4 else _flat(a)
+        b = nhwc(b) if b.dim() == 4 else _flat(b)
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        call('ttg_dot_f32out', ptr(a), ptr(b), ptr(out), a.numel(), ptr(_ws(8, a.device)), dtype_code(a.dtype))
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.reshape(1)
+        ga = ScaleDevFn.apply(b, g) if ctx.needs_input_grad[0] else None
+        gb = ScaleDevFn.apply(a, g) if ctx.needs_input_grad[1] else None
+        return ga, gb
+
+
+def ensure_internal(x):
+    """Accept the reference's fp32 NCHW tensors at any module boundary."""
+    if x.dim() != 4:
+        return x
+    if x.dtype == state.act_dtype and _is_nhwc(x):
+        return x
+    return ToInternal.apply(x, state.act_dtype)

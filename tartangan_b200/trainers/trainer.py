@@ -1,0 +1,256 @@
+"""Trainer base — interface of tartangan/trainers/trainer.py: the same CLI flags (two-phase
+argparse with @file support), epoch/batch loop, z / batch helpers, get_state/set_state and
+the checkpoint layout of components/model_checkpoint.py.  The loop is the CALLER of the hot
+path (train_batch); the observability side-cars of the reference (image sampler, FID, Katib /
+Kubeflow / TensorBoard sinks) are out of scope.
+"""
+import argparse
+import json
+import os
+import random
+import string
+from collections import defaultdict
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from .utils import set_device_from_args
+
+
+def type_or_none(type_):
+    def f(value):
+        return None if value in (None, 'None', 'none', '') else type_(value)
+    return f
+
+
+class SyntheticTartanDataset(torch.utils.data.Dataset):
+    """Deterministic tartan-shaped RGB images, fp32 CHW in [-1, 1]."""
+
+    def __init__(self, size, length=4096, seed=1234):
+        self.size, self.length, self.seed = size, length, seed
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, i):
+        return tartan_batch(self.seed + i, 1, self.size)[0]
+
+
+def tartan_batch(seed, batch, size):
+    g = torch.Generator().manual_seed(seed)
+    ys, xs = torch.meshgrid(torch.arange(size), torch.arange(size), indexing='ij')
+    twill = (((xs + ys) // 2) % 2).float()
+    out = torch.empty(batch, 3, size, size)
+    for i in range(batch):
+        n = int(torch.randint(3, 9, (1,), generator=g))
+        widths = torch.randint(1, max(2, size // 8) + 1, (n,), generator=g)
+        colours = torch.rand(n, 3, generator=g)
+        sett = torch.repeat_interleave(colours, widths, dim=0)
+        sett = torch.cat([sett, sett.flip(0)])
+        sett = sett.repeat(-(-size // sett.shape[0]), 1)[:size]
+        warp = sett.t()[:, None, :].expand(3, size, size)
+        weft = sett.t()[:, :, None].expand(3, size, size)
+        out[i] = (twill * warp + (1 - twill) * weft) * 2 - 1
+    return out
+
+
+class NpzImageDataset(torch.utils.data.Dataset):
+    """uint8 image stack stored in an .npz (key 'images' or first array), random-cropped to the
+    generator's output size and mapped to [-1, 1] (contract of image_bytes_dataset.py:44-49)."""
+
+    def __init__(self, path, size):
+        data = np.load(path)
+        key = 'images' if 'images' in data.files else data.files[0]
+        self.images, self.size = data[key], size
+
+    def __len__(self):
+        return len(self.images)
+
+    def __getitem__(self, i):
+        img = self.images[i]
+        h, w = img.shape[:2]
+        y = random.randint(0, h - self.size)
+        x = random.randint(0, w - self.size)
+        crop = torch.from_numpy(np.ascontiguousarray(img[y:y + self.size, x:x + self.size]))
+        return crop.permute(2, 0, 1).float() / 127.5 - 1.0
+
+
+class Trainer:
+    def __init__(self, args, components=()):
+        self.args = args
+        self.run_id = args.run_id if getattr(args, 'run_id', None) is not None else self._generate_run_id()
+        os.makedirs(self.output_root, exist_ok=True)
+        with open(f'{self.output_root}/config.args', 'w') as f:
+            json.dump({k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool, type(None)))}, f)
+        self.components = list(components)
+        self.steps = 0
+        self.epoch = 1
+
+    # ---- to be provided by CNNTrainer / IQNTrainer
+    def build_models(self):
+        raise NotImplementedError
+
+    def train_batch(self, imgs):
+        raise NotImplementedError
+
+    # ---- data
+    def prepare_dataset(self):
+        size = self.g.max_size
+        if self.args.data_path == 'synthetic':
+            return SyntheticTartanDataset(size)
+        if self.args.data_path.endswith('.npz'):
+            return NpzImageDataset(self.args.data_path, size)
+        raise NotImplementedError('tartangan_b200: data_path must be "synthetic" or an .npz of uint8 images; the '
+                                  'image-folder pipeline of the reference is outside the training-step scope')
+
+    def train(self, max_steps=None):
+        self.build_models()
+        self.dataset = self.prepare_dataset()
+        loader = torch.utils.data.DataLoader(self.dataset, batch_size=self.args.batch_size, shuffle=True,
+                                             drop_last=True)
+        logs = defaultdict(list)
+        self._maybe_resume()
+        try:
+            while self.epoch <= self.args.epochs:
+                for images in loader:
+                    metrics = self.train_batch(images)
+                    for name, value in metrics.items():
+                        logs[name].append(value)
+                    if self.steps and self.steps % self.args.checkpoint_freq == 0:
+                        self.save_checkpoint()
+                    if not self.args.quiet_logs or self.steps % self.args.log_iters == 0:
+                        print(f'step {self.steps} ' + ' '.join(f'{k}={v:.4f}' for k, v in metrics.items()), flush=True)
+                    self.steps += 1
+                    if max_steps is not None and self.steps >= max_steps:
+                        raise KeyboardInterrupt
+                self.epoch += 1
+        except KeyboardInterrupt:
+            pass
+        self.save_checkpoint()
+        return logs
+
+    # ---- helpers on the hot path (trainers/trainer.py:153-176)
+    def sample_z(self, n=None):
+        """z ~ N(0, I) from the CPU generator, then copied to the device (trainer.py:153-156)."""
+        if n is None:
+            n = self.args.batch_size
+        return torch.randn(n, self.gan_config.latent_dims).to(self.device)
+
+    def sample_g(self, n=None, target_g=False, **g_kwargs):
+        z = self.sample_z(n)
+        return (self.target_g if target_g else self.g)(z, **g_kwargs)
+
+    def make_adversarial_batch(self, real_data, **g_kwargs):
+        generated = self.sample_g(len(real_data), **g_kwargs)
+        batch = torch.cat([real_data, generated], dim=0)
+        labels = torch.zeros(len(batch), 1, device=self.device)
+        labels[:len(labels) // 2] = 1
+        return batch, labels
+
+    def make_generator_batch(self, real_data, **g_kwargs):
+        generated = self.sample_g(len(real_data), **g_kwargs)
+        return generated, torch.ones(len(generated), 1, device=self.device)
+
+    # ---- state / checkpoints (components/model_checkpoint.py:32-74 layout)
+    def get_state(self):
+        return dict(epoch=self.epoch, steps=self.steps)
+
+    def set_state(self, state):
+        for key, value in state.items():
+            setattr(self, key, value)
+
+    @property
+    def checkpoint_root(self):
+        return f'{self.output_root}/checkpoints/{self.steps}'
+
+    def save_checkpoint(self):
+        os.makedirs(self.checkpoint_root, exist_ok=True)
+        for obj, name in ((self.g, 'g.pt'), (self.target_g, 'g_target.pt'), (self.d, 'd.pt'),
+                          (self.optimizer_d, 'opt_d.pt'), (self.optimizer_g, 'opt_g.pt')):
+            torch.save(obj.state_dict(), f'{self.checkpoint_root}/{name}')
+        with open(f'{self.checkpoint_root}/trainer.json', 'w') as f:
+            json.dump(self.get_state(), f)
+
+    def load_checkpoint(self):
+        for attr, name in (('g', 'g.pt'), ('target_g', 'g_target.pt'), ('d', 'd.pt'),
+                           ('optimizer_d', 'opt_d.pt'), ('optimizer_g', 'opt_g.pt')):
+            obj = torch.load(f'{self.checkpoint_root}/{name}', weights_only=False, map_location=self.device)
+            sd = obj if isinstance(obj, dict) else obj.state_dict()     # reference saves whole objects
+            getattr(self, attr).load_state_dict(sd)
+        with open(f'{self.checkpoint_root}/trainer.json') as f:
+            self.set_state(json.load(f))
+
+    def _maybe_resume(self):
+        if getattr(self.args, 'resume_training_step', None):
+            self.steps = self.args.resume_training_step
+            self.load_checkpoint()
+        elif getattr(self.args, 'resume_training_latest', False):
+            root = f'{self.output_root}/checkpoints'
+            ids = sorted(int(d) for d in os.listdir(root) if d.isdigit()) if os.path.isdir(root) else []
+            if ids:
+                self.steps = ids[-1]
+                self.load_checkpoint()
+
+    def _generate_run_id(self, suffix_len=6):
+        now = datetime.now().strftime('%Y-%m-%d_%H-%M-%S')
+        return f'{now}_' + ''.join(random.sample(string.ascii_letters, suffix_len))
+
+    @property
+    def device(self):
+        return self.args.device
+
+    @property
+    def output_root(self):
+        return f'{self.args.output}/{self.run_id}'
+
+    # ---- CLI (trainer.py:236-313, model_checkpoint.py:110-117)
+    @classmethod
+    def get_component_classes(cls, args):
+        return []
+
+    @classmethod
+    def create_from_cli(cls, argv=None):
+        parser = argparse.ArgumentParser(description='TartanGAN trainer (B200)', fromfile_prefix_chars='@')
+        cls.add_args_to_parser(parser)
+        args = parser.parse_args(argv)
+        set_device_from_args(args)
+        print(f'Using device "{args.device}"')
+        return cls(args, [])
+
+    @classmethod
+    def add_args_to_parser(cls, p):
+        p.add_argument('data_path')
+        p.add_argument('--batch-size', type=int, default=128)
+        p.add_argument('--gen-freq', type=int, default=200, help='Output samples every N batches')
+        p.add_argument('--lr-g', type=float, default=1e-4, help='Learning rate for the generator')
+        p.add_argument('--lr-d', type=float, default=4e-4, help='Learning rate for the discriminator')
+        p.add_argument('--lr-target-g', type=float, default=1e-3,
+                       help='Exponential moving average factor for the target generator')
+        p.add_argument('--no-cuda', action='store_true')
+        p.add_argument('--epochs', type=int, default=10000)
+        p.add_argument('--output', default='output')
+        p.add_argument('--dataset-cache', default='cache/{root}_{size}.pkl')
+        p.add_argument('--grad-penalty', type=float, default=5.,
+                       help='Gradient penalty weight for discriminator on real data')
+        p.add_argument('--config', default='64', help='Id of configuration to use. See pluggan.py.')
+        p.add_argument('--model-scale', type=float, default=1.)
+        p.add_argument('--cache-dataset', action='store_true')
+        p.add_argument('--g-base', default='mlp')
+        p.add_argument('--norm', default='bn', help='"bn" (batchnorm) or "id" (identity)')
+        p.add_argument('--activation', default='relu', help='"relu" (LeakyReLU 0.2); selu/elu have no kernel')
+        p.add_argument('--quiet-logs', action='store_true')
+        p.add_argument('--log-iters', type=int, default=1000)
+        p.add_argument('--log-progress-newlines', action='store_true')
+        p.add_argument('--metrics-collector', default=None)
+        p.add_argument('--run-id', type=type_or_none(str), default=None)
+        p.add_argument('--fid', action='store_true')
+        p.add_argument('--checkpoint-freq', type=int, default=100000)
+        p.add_argument('--resume-training-step', type=type_or_none(int), default=None)
+        p.add_argument('--resume-training-latest', action='store_true')
+        # additive flags (defaults preserve the reference behaviour)
+        p.add_argument('--precision', default='bf16', choices=('bf16', 'fp32'),
+                       help='activation/conv-operand precision of the CUDA path')
+        p.add_argument('--num-quantiles', type=int, default=8, help='IQN quantile count (reference: 8)')
+        p.add_argument('--attention', type=type_or_none(str), default=None,
+                       help='comma-separated block indices with self-attention (overrides the config)')

@@ -1,0 +1,116 @@
+"""GPU parity of the whole training step: CUDA path (through the C ABI) vs the golden vectors
+produced by the unmodified reference, and vs the CPU oracle at reference channel widths."""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(kind, gan_config, batch, precision, norm='bn', **kw):
+    from tartangan_b200.trainers.cnn import CNNTrainer
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    cls = CNNTrainer if kind == 'cnn' else IQNTrainer
+    return make_trainer(cls, gan_config=gan_config, batch_size=batch, precision=precision, norm=norm, **kw)
+
+
+def _cfg(g):
+    from tartangan_b200.models.pluggan import GANConfig
+    return GANConfig(base_size=4, latent_dims=g['latent'], data_dims=3, blocks=tuple(g['blocks']),
+                     num_blocks_per_scale=1, attention=tuple(g['attention']))
+
+
+def _close(a, b, tol):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-6)) <= tol
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+def test_golden_fp32(case):
+    g = load_golden(case)
+    t = _trainer(g['kind'], _cfg(g), g['batch'], 'fp32', norm=g['norm'])
+    t.g.load_state_dict(g['init']['g'])
+    t.target_g.load_state_dict(g['init']['target_g'])
+    t.d.load_state_dict(g['init']['d'])
+    # module-level forward probes
+    pr = g['probe']
+    gsd = {k: v.clone() for k, v in t.g.state_dict().items()}
+    dsd = {k: v.clone() for k, v in t.d.state_dict().items()}
+    with torch.no_grad():
+        assert _close(t.g(pr['z'].cuda()), pr['g_out'], 2e-4)
+        if g['kind'] == 'iqn':
+            torch.manual_seed(pr['tau_seed'])
+            p, loss = t.d(pr['x'].cuda(), targets=torch.ones(g['batch'], 1, device='cuda'))
+            assert _close(p, pr['d_out'], 2e-4) and _close(loss, pr['d_loss'], 2e-4)
+        else:
+            assert _close(t.d(pr['x'].cuda()), pr['d_out'], 2e-4)
+    t.g.load_state_dict(gsd)
+    t.d.load_state_dict(dsd)
+    for s in range(g['steps']):
+        torch.manual_seed(g['seeds'][s])
+        m = t.train_batch(g['imgs'][s])
+        for k, v in g['metrics'][s].items():
+            assert abs(m[k] - v) <= 2e-3 * max(1.0, abs(v)), (s, k, m[k], v)
+        if s == 0:
+            for net, mod in (('d', t.d), ('g', t.g)):
+                grads = dict(mod.named_parameters())
+                for k, ref in g['grads0'][net].items():
+                    if float(ref.abs().max()) < 1e-6:
+                        continue            # analytically-zero bias grads: reference holds fp noise
+                    assert _close(grads[k].grad, ref, 5e-3), (net, k)
+    for net, mod in (('g', t.g), ('target_g', t.target_g), ('d', t.d)):
+        sd = mod.state_dict()
+        for k, ref in g['final'][net].items():
+            if ref.is_floating_point():
+                if k.endswith('.bias') and float((ref - g['init'][net][k]).abs().max()) > 0 and \
+                        float(g['grads0'].get(net, {}).get(k, torch.ones(1)).abs().max()) < 1e-6:
+                    continue        # Adam(beta1=0) turns fp noise on zero-gradient biases into +-lr steps
+                assert _close(sd[k], ref, 5e-3), (net, k)
+            else:
+                assert torch.equal(sd[k].cpu(), ref), (net, k)
+
+
+@pytest.mark.parametrize('kind', ['cnn', 'iqn'])
+def test_vs_oracle_reference_widths(kind):
+    """config '32' at the reference's real channel widths (128, 64, 32), batch 8, two steps, fp32."""
+    from oracle import tartan_oracle as O
+    from tartangan_b200.models.pluggan import GAN_CONFIGS
+    cfg = GAN_CONFIGS['32']
+    torch.manual_seed(0)
+    t = _trainer(kind, cfg, 8, 'fp32')
+    spec = O.Spec(4, cfg.latent_dims, 3, tuple(cfg.blocks), ())
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(kind, spec, cpu(t.g), cpu(t.target_g), cpu(t.d), 8)
+    for s in range(2):
+        imgs = O.tartan_batch(50 + s, 8, 32)
+        torch.manual_seed(300 + s)
+        ref = orc.train_batch(imgs)
+        torch.manual_seed(300 + s)
+        got = t.train_batch(imgs)
+        for k in ref:
+            assert abs(got[k] - ref[k]) <= 3e-3 * max(1.0, abs(ref[k])), (s, k, got[k], ref[k])
+    for k, v in orc.d.items():
+        if v.is_floating_point() and not k.endswith('.bias'):
+            assert _close(t.d.state_dict()[k], v, 1e-2), k
+
+
+@pytest.mark.parametrize('kind', ['cnn', 'iqn'])
+def test_bf16_step_tracks_oracle(kind):
+    """bf16 activations: losses of the first step within 5 % of the fp32 oracle."""
+    from oracle import tartan_oracle as O
+    from tartangan_b200.models.pluggan import GAN_CONFIGS
+    cfg = GAN_CONFIGS['32']
+    torch.manual_seed(0)
+    t = _trainer(kind, cfg, 8, 'bf16')
+    spec = O.Spec(4, cfg.latent_dims, 3, tuple(cfg.blocks), ())
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(kind, spec, cpu(t.g), cpu(t.target_g), cpu(t.d), 8)
+    imgs = O.tartan_batch(50, 8, 32)
+    torch.manual_seed(300)
+    ref = orc.train_batch(imgs)
+    torch.manual_seed(300)
+    got = t.train_batch(imgs)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 0.05 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
