@@ -128,17 +128,20 @@ def from_internal(x):
 
 
 # --------------------------------------------------------------------------- convolution
-_pack_cache = {}
-
-
 def _packed(w, mode, kind):
-    """Packed copy of a conv weight, cached on (storage, version)."""
-    key = (w.data_ptr(), kind, mode)
-    # _version catches in-place torch updates; _ttg_epoch is bumped by FusedAdam, whose kernel
-    # writes the flat parameter buffer behind autograd's back.
-    ver = (w._version, getattr(w, '_ttg_epoch', 0))
-    hit = _pack_cache.get(key)
-    if hit is not None and hit[0] == ver and hit[1].device == w.device and hit[2] == tuple(w.shape):
+    """Packed copy of a conv weight.  The cache lives ON the weight tensor (so it dies with it) and
+    is validated by (_version, _ttg_epoch, data_ptr): _version catches in-place torch updates,
+    _ttg_epoch is bumped by FusedAdam, whose kernel writes the flat buffer behind autograd's back."""
+    ver = (w._version, getattr(w, '_ttg_epoch', 0), w.data_ptr())
+    cache = getattr(w, '_ttg_pack', None)
+    if cache is None:
+        cache = {}
+        try:
+            w._ttg_pack = cache
+        except AttributeError:
+            pass
+    hit = cache.get((kind, mode))
+    if hit is not None and hit[0] == ver:
         return hit[1]
     cout, cin, k, _ = w.shape
     wd = w.detach()
@@ -150,9 +153,7 @@ def _packed(w, mode, kind):
         nbytes = _lib.lib.ttg_pack_weight_tc_bytes(cout, cin, k)
         wp = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         call('ttg_pack_weight_tc', ptr(wd), ptr(wp), cout, cin, k, mode)
-    if len(_pack_cache) > 4096:
-        _pack_cache.clear()
-    _pack_cache[key] = (ver, wp, tuple(w.shape))
+    cache[(kind, mode)] = (ver, wp)
     return wp
 
 
