@@ -55,6 +55,9 @@ size_t ttg_pack_weight_tc_bytes(int Cout, int Cin, int ksize);
 int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, int ksize, int mode, void* stream);
 int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                   int ksize, int up, int dtype_out, void* stream);
+int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                      int Cout, int ksize, int up, int dtype_out, const float* pre_scale, const float* pre_shift,
+                      float slope, void* stream);
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
                         int up, void* workspace, void* stream);
 size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);

@@ -100,8 +100,31 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per entry point (for the bench's gpu_launches counter)
+KERNELS_PER_CALL = {
+    'ttg_bn_stats': 2, 'ttg_bn_act_bwd': 3, 'ttg_bn_act_bwd2': 3, 'ttg_channel_sum': 2, 'ttg_sqsum_f32': 2,
+    'ttg_dot_f32out': 2, 'ttg_adam_flat': 2, 'ttg_spectral_norm': 5, 'ttg_spectral_norm_bwd': 2,
+    'ttg_conv2d_wgrad_tc': 2,
+}
+
+
+class Counters:
+    calls = 0
+    kernels = 0
+    profiler = None      # optional object with .record(name, args, start_event, end_event)
+
+
 def call(name, *args):
     """Invoke an `int ttg_*(..., stream)` entry point on the current stream."""
+    Counters.calls += 1
+    Counters.kernels += KERNELS_PER_CALL.get(name, 1)
+    prof = Counters.profiler
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RuntimeError(f'tartangan_b200: {name} failed: {last_error()}')
+    if prof is not None:
+        e1.record()
+        prof.record(name, args, e0, e1)

@@ -1,15 +1,365 @@
-// Tensor-core (tcgen05 / TMEM) implicit-GEMM convolution — placeholder entry points until the
-// kernels land; they fail loudly and the Python side keeps use_tc off.
-#include "common.cuh"
+// Tensor-core implicit-GEMM convolution for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM).
+// Replaces aten::convolution / convolution_backward for every nn.Conv2d of the residual blocks
+// (reference models/blocks/generator.py:41,44,52; discriminator.py:63,66,78) whose channel
+// counts are multiples of 16.  NHWC bf16 activations, k in {1,3}, stride 1, pad k/2.
+//
+// Tiling: one CTA = 16 rows x 8 cols = 128 output pixels of one image (UMMA M = 128).
+// The input halo tile (18 x 10 pixels) is staged ONCE in shared memory as 16-byte units
+// [channel/8][halo pixel][8 channels] — the SWIZZLE_NONE canonical layout — so that each of the
+// 9 filter taps is just a shifted descriptor start address (no im2col copies, no re-reads):
+//   fprop/dgrad: A = pixels x channels (K-major),  B = packed weights (K-major),  N = Cout
+//   wgrad      : A = gy^T   (MN-major, K = pixels), B = shifted x (MN-major),     N = Cin
+// Zero padding = zero-filled halo; nearest x2 upsample (generator.py:58) = (y>>1, x>>1) addressing;
+// the BatchNorm+LeakyReLU that precedes each conv can be applied while staging (pre_scale/shift).
+// The epilogue reads the fp32 accumulator from TMEM (tcgen05.ld 32x32b), adds the bias and
+// writes NHWC rows (one thread = one pixel = Cout contiguous channels).
+#include "tc_common.cuh"
 
+#define TC_TH 16
+#define TC_TW 8
+#define TC_STAGE_BYTES (32 * 1024)
+
+// ------------------------------------------------------------------ weight packing
+// mode 0 (fprop): wp[tap][ci/8][co][ci%8]            = w[co][ci][ky][kx]        (B: N=co, K=ci)
+// mode 1 (dgrad): wp[tap'][co/8][ci][co%8]           = w[co][ci][k-1-ky][k-1-kx] (B: N=ci, K=co)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Cout, int Cin, int k, int mode) {
+  int total = Cout * Cin * k * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int kx = i % k, ky = (i / k) % k, ci = (i / (k * k)) % Cin, co = i / (k * k * Cin);
+    bf16 v = __float2bfloat16_rn(w[i]);
+    if (mode == 0) {
+      int tap = ky * k + kx;
+      wp[(((long long)tap * (Cin / 8) + ci / 8) * Cout + co) * 8 + (ci % 8)] = v;
+    } else {
+      int tap = (k - 1 - ky) * k + (k - 1 - kx);
+      wp[(((long long)tap * (Cout / 8) + co / 8) * Cin + ci) * 8 + (co % 8)] = v;
+    }
+  }
+}
 extern "C" size_t ttg_pack_weight_tc_bytes(int Cout, int Cin, int ksize) { return (size_t)Cout * Cin * ksize * ksize * 2; }
-extern "C" int ttg_pack_weight_tc(const float*, void*, int, int, int, int, void*) {
-  return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_tc: not built in this revision");
+extern "C" int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, int ksize, int mode, void* stream) {
+  TTG_REQUIRE(Cout % 16 == 0 && Cin % 16 == 0, "pack_weight_tc: channels must be multiples of 16 (%d,%d)", Cout, Cin);
+  int total = Cout * Cin * ksize * ksize;
+  pack_weight_tc_kernel<<<ttg_grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, Cout, Cin, ksize, mode);
+  TTG_CHECK_LAUNCH("pack_weight_tc");
+  return TTG_OK;
 }
-extern "C" int ttg_conv2d_tc(const void*, const void*, const float*, void*, int, int, int, int, int, int, int, int, void*) {
-  return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_tc: not built in this revision");
+
+// ------------------------------------------------------------------ staging of an activation tile
+// Writes the [C/8][HP] x 16B image of the (TC_TH+2h) x (TC_TW+2h) halo tile at (y0-h, x0-h).
+template <int HALO>
+__device__ __forceinline__ void stage_tile(uint8_t* sA, const bf16* __restrict__ x, int n, int y0, int x0, int H, int W,
+                                           int C, int up, const float* __restrict__ pre_scale,
+                                           const float* __restrict__ pre_shift, float slope) {
+  constexpr int WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  const int c8n = C >> 3;
+  const int Hi = H >> up, Wi = W >> up;
+  for (int u = threadIdx.x; u < HP * c8n; u += blockDim.x) {
+    const int c8 = u % c8n, pix = u / c8n;
+    const int hy = pix / WH, hx = pix - hy * WH;
+    const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      v = *reinterpret_cast<const uint4*>(x + (((long long)n * Hi + (gy >> up)) * Wi + (gx >> up)) * C + c8 * 8);
+      if (pre_scale) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(h[j]);
+          const int c = c8 * 8 + 2 * j;
+          f.x = lrelu(f.x * pre_scale[c] + pre_shift[c], slope);
+          f.y = lrelu(f.y * pre_scale[c + 1] + pre_shift[c + 1], slope);
+          h[j] = __floats2bfloat162_rn(f.x, f.y);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(sA + ((size_t)c8 * HP + pix) * 16) = v;
+  }
 }
-extern "C" int ttg_conv2d_wgrad_tc(const void*, const void*, float*, int, int, int, int, int, int, int, void*, void*) {
-  return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_wgrad_tc: not built in this revision");
+
+// ------------------------------------------------------------------ fprop / dgrad
+template <int K>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                      const float* __restrict__ bias, void* __restrict__ y, int out_f32,
+                                                      int H, int W, int Cin, int Cout, int up,
+                                                      const float* __restrict__ pre_scale,
+                                                      const float* __restrict__ pre_shift, float slope, int stage_slices,
+                                                      int nstages, int tmem_cols) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t a_bytes = (uint32_t)(Cin >> 3) * HP * 16;
+  const uint32_t slice_bytes = (uint32_t)Cout * 32;                 // one K=16 slice of one tap: [2][Cout][8] bf16
+  const uint32_t stage_bytes = (uint32_t)stage_slices * slice_bytes;
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)nstages * stage_bytes);   // [0..1] stage free, [2] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH;
+  const int tile = blockIdx.x;
+  const int n = tile / (tiles_x * tiles_y), t2 = tile - n * tiles_x * tiles_y;
+  const int y0 = (t2 / tiles_x) * TC_TH, x0 = (t2 % tiles_x) * TC_TW;
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+  stage_tile<HALO>(sA, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k16n = Cin >> 4;
+  const int total_slices = K * K * k16n;
+  const int nchunks = (total_slices + stage_slices - 1) / stage_slices;
+  const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
+  const uint32_t sA_addr = smem_u32(sA);
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c % nstages;
+    if (c >= nstages) mbar_wait(&bars[s], (uint32_t)((c / nstages) - 1) & 1u);     // MMAs that read this stage are done
+    const int first = c * stage_slices;
+    const int cnt = min(stage_slices, total_slices - first);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wp) + (size_t)first * slice_bytes);
+      uint4* dst = reinterpret_cast<uint4*>(sW + (size_t)s * stage_bytes);
+      const int nvec = (int)((size_t)cnt * slice_bytes / 16);
+      for (int i = tid; i < nvec; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      const uint32_t sW_addr = smem_u32(sW + (size_t)s * stage_bytes);
+      for (int i = 0; i < cnt; ++i) {
+        const int slice = first + i;
+        const int tap = slice / k16n, j = slice - tap * k16n;
+        const int ky = tap / K, kx = tap - ky * K;
+        // A: rows = 16 groups of 8 pixels (SBO = one halo row), K chunks of 8 channels (LBO = HP units)
+        const uint64_t adesc = umma_desc(sA_addr + (uint32_t)((ky * WH + kx) + 2 * j * HP) * 16, HP * 16, WH * 16);
+        // B: rows = Cout (SBO = 8 rows x 16 B), K chunks (LBO = Cout units)
+        const uint64_t bdesc = umma_desc(sW_addr + (uint32_t)i * slice_bytes, (uint32_t)Cout * 16, 128);
+        umma_bf16(tmem_base, adesc, bdesc, idesc, slice > 0 ? 1u : 0u);
+      }
+      umma_commit(&bars[s]);
+      if (c == nchunks - 1) umma_commit(&bars[2]);
+    }
+  }
+
+  // ---- epilogue: thread = pixel (TMEM lane), columns = output channels
+  mbar_wait(&bars[2], 0);
+  tc_fence_after_sync();
+  const int m = tid, gy = y0 + (m >> 3), gx = x0 + (m & 7);
+  const bool valid = gy < H && gx < W;
+  const long long opix = ((long long)n * H + gy) * W + gx;
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (valid) {
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (bias ? bias[c0 + j] : 0.f);
+      if (out_f32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + opix * Cout + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4 o[2];
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(y) + opix * Cout + c0);
+        dst[0] = o[0]; dst[1] = o[1];
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
+
+static int g_conv_tc_smem[2] = {0, 0};
+
+extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                                 int Cout, int ksize, int up, int dtype_out, const float* pre_scale,
+                                 const float* pre_shift, float slope, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize %d unsupported", ksize);
+  TTG_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16 && Cin <= 256 && Cout <= 256,
+              "conv2d_tc: channels must be multiples of 16 in [16,256] (got %d -> %d)", Cin, Cout);
+  TTG_REQUIRE(up == 0 || (H % 2 == 0 && W % 2 == 0), "conv2d_tc: upsample needs even output size");
+  TTG_REQUIRE(dtype_out == TTG_BF16 || dtype_out == TTG_F32, "conv2d_tc: bad output dtype");
+  TTG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(wp) & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+  const int halo = ksize / 2;
+  const int HP = (TC_TW + 2 * halo) * (TC_TH + 2 * halo);
+  const int total_slices = ksize * ksize * (Cin / 16);
+  const int slice_bytes = Cout * 32;
+  int stage_slices = TC_STAGE_BYTES / slice_bytes;
+  if (stage_slices < 1) stage_slices = 1;
+  if (stage_slices > total_slices) stage_slices = total_slices;
+  const int nstages = total_slices > stage_slices ? 2 : 1;
+  const int smem = (Cin / 8) * HP * 16 + nstages * stage_slices * slice_bytes + 64;
+  const long long tiles = (long long)N * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
+  TTG_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv2d_tc: bad problem size");
+  const int ki = ksize == 3 ? 1 : 0;
+  if (smem > g_conv_tc_smem[ki]) {
+    cudaError_t e = ksize == 3
+        ? cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        : cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    g_conv_tc_smem[ki] = smem;
+  }
+  const int cols = (int)tmem_cols_for(Cout);
+  if (ksize == 3)
+    conv_tc_kernel<3><<<(unsigned)tiles, 128, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, dtype_out == TTG_F32, H, W,
+                                                         Cin, Cout, up, pre_scale, pre_shift, slope, stage_slices, nstages, cols);
+  else
+    conv_tc_kernel<1><<<(unsigned)tiles, 128, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, dtype_out == TTG_F32, H, W,
+                                                         Cin, Cout, up, pre_scale, pre_shift, slope, stage_slices, nstages, cols);
+  TTG_CHECK_LAUNCH("conv2d_tc");
+  return TTG_OK;
+}
+
+extern "C" int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                             int Cout, int ksize, int up, int dtype_out, void* stream) {
+  return ttg_conv2d_tc_pre(x, wp, bias, y, N, H, W, Cin, Cout, ksize, up, dtype_out, nullptr, nullptr, 1.f, stream);
+}
+
+// ------------------------------------------------------------------ wgrad
+// gw[co][ci][ky][kx] += sum over the CTA's pixel tiles of gy[p,co] * x[p+tap,ci].
+// grid = (pixel splits, tap groups, Cout halves).  Per tile and tap: 8 MMAs (K = 2 rows x 8 pixels),
+// M = 128 output channels (rows >= Cout are padding), N = Cin, accumulators: taps_per_group x Cin columns.
+template <int K>
+__global__ void __launch_bounds__(128) conv_wgrad_tc_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy,
+                                                            float* __restrict__ gw, int N, int H, int W, int Cin, int Cout,
+                                                            int up, int taps_per_group, int tmem_cols) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH, NPIX = TC_TH * TC_TW;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t x_bytes = (uint32_t)(Cin >> 3) * HP * 16;
+  uint8_t* sX = smem;
+  uint8_t* sG = smem + x_bytes;                       // [16 co-groups][128 pixels] x 16 B (always 128 rows)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 16 * NPIX * 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tap0 = blockIdx.y * taps_per_group;
+  const int ntaps = min(taps_per_group, K * K - tap0);
+  const int co_base = blockIdx.z * 128;
+  const int co_cnt = min(128, Cout - co_base);
+
+  if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 32) { mbar_init(&bars[0], 1); mbar_fence_init(); }
+  // zero the padding rows of the gy tile once (rows >= co_cnt are never rewritten)
+  for (int u = tid; u < 16 * NPIX; u += blockDim.x) *reinterpret_cast<uint4*>(sG + (size_t)u * 16) = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH;
+  const long long total_tiles = (long long)N * tiles_x * tiles_y;
+  const uint32_t idesc = umma_idesc_bf16(128, Cin, 1, 1);
+  const uint32_t sX_addr = smem_u32(sX), sG_addr = smem_u32(sG);
+  const int g8n = co_cnt >> 3;
+  uint32_t phase = 0;
+  bool first = true;
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n = (int)(tile / (tiles_x * tiles_y)), t2 = (int)(tile - (long long)n * tiles_x * tiles_y);
+    const int y0 = (t2 / tiles_x) * TC_TH, x0 = (t2 % tiles_x) * TC_TW;
+    if (!first) { mbar_wait(&bars[0], phase); phase ^= 1u; }       // previous tile's MMAs have consumed the smem
+    stage_tile<HALO>(sX, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+    for (int u = tid; u < NPIX * g8n; u += blockDim.x) {
+      const int g8 = u % g8n, pix = u / g8n;
+      const int py = y0 + (pix >> 3), px = x0 + (pix & 7);
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (py < H && px < W) v = *reinterpret_cast<const uint4*>(gy + (((long long)n * H + py) * W + px) * Cout + co_base + g8 * 8);
+      *reinterpret_cast<uint4*>(sG + ((size_t)g8 * NPIX + pix) * 16) = v;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after_sync();
+      for (int t = 0; t < ntaps; ++t) {
+        const int tap = tap0 + t, ky = tap / K, kx = tap - ky * K;
+#pragma unroll 1
+        for (int r = 0; r < TC_TH / 2; ++r) {
+          // A = gy^T (MN-major): M groups of 8 channels (SBO = 128 pixels x 16 B), K = pixels: 8 per row (16 B apart), rows LBO apart
+          const uint64_t adesc = umma_desc(sG_addr + (uint32_t)(2 * r * TC_TW) * 16, TC_TW * 16, NPIX * 16);
+          // B = shifted x (MN-major): N groups of 8 channels (SBO = HP x 16 B), K = pixels of halo rows 2r+ky, 2r+1+ky
+          const uint64_t bdesc = umma_desc(sX_addr + (uint32_t)((2 * r + ky) * WH + kx) * 16, WH * 16, HP * 16);
+          umma_bf16(tmem_base + (uint32_t)(t * Cin), adesc, bdesc, idesc, (first && r == 0) ? 0u : 1u);
+        }
+      }
+      umma_commit(&bars[0]);
+    }
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(&bars[0], phase);
+    tc_fence_after_sync();
+    const int co = co_base + tid;                     // TMEM lane = output channel
+    for (int t = 0; t < ntaps; ++t) {
+      const int tap = tap0 + t;
+      for (int c0 = 0; c0 < Cin; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * Cin + c0), r);
+        tmem_ld_wait();
+        if (tid < co_cnt) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(gw + ((long long)co * Cin + c0 + j) * (K * K) + tap, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+static int g_wgrad_tc_smem[2] = {0, 0};
+
 extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int, int, int) { return 16; }
+
+extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                                   int ksize, int up, void* workspace, void* stream) {
+  (void)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad_tc: ksize %d unsupported", ksize);
+  TTG_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16 && Cin <= 256 && Cout <= 256,
+              "conv2d_wgrad_tc: channels must be multiples of 16 in [16,256] (got %d -> %d)", Cin, Cout);
+  TTG_REQUIRE(up == 0 || (H % 2 == 0 && W % 2 == 0), "conv2d_wgrad_tc: upsample needs even output size");
+  const int taps = ksize * ksize;
+  int tpg = 512 / Cin;                 // accumulator columns: taps_per_group * Cin <= 512
+  if (tpg > taps) tpg = taps;
+  const int groups = (taps + tpg - 1) / tpg;
+  const int halves = (Cout + 127) / 128;
+  const int halo = ksize / 2;
+  const int HP = (TC_TW + 2 * halo) * (TC_TH + 2 * halo);
+  const int smem = (Cin / 8) * HP * 16 + 16 * TC_TH * TC_TW * 16 + 64;
+  const long long tiles = (long long)N * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
+  int per_sm = (200 * 1024) / smem;
+  const int cols = (int)tmem_cols_for(tpg * Cin);
+  if (per_sm > 512 / cols) per_sm = 512 / cols;
+  if (per_sm < 1) per_sm = 1;
+  long long splits = (long long)ttg_num_sms() * per_sm / (groups * halves);
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = tiles;
+  const int ki = ksize == 3 ? 1 : 0;
+  if (smem > g_wgrad_tc_smem[ki]) {
+    cudaError_t e = ksize == 3
+        ? cudaFuncSetAttribute(conv_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+        : cudaFuncSetAttribute(conv_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
+    g_wgrad_tc_smem[ki] = smem;
+  }
+  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+  dim3 grid((unsigned)splits, groups, halves);
+  if (ksize == 3)
+    conv_wgrad_tc_kernel<3><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);
+  else
+    conv_wgrad_tc_kernel<1><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);
+  TTG_CHECK_LAUNCH("conv2d_wgrad_tc");
+  return TTG_OK;
+}

@@ -23,7 +23,7 @@ SLOPE = 0.2
 class _State:
     act_dtype = torch.bfloat16     # precision mode for activations ('bf16' default)
     inputs_only = False            # set by gradient_penalty: skip parameter gradients
-    use_tc = False                 # tensor-core conv kernels when shapes allow (off until conv_tc lands)
+    use_tc = True                  # tensor-core conv kernels when shapes allow
     launches = 0                   # kernels launched through the C ABI (bench counter)
 
 

@@ -1,0 +1,95 @@
+"""Per-entry-point device timing with CUDA events on the launching stream (bench / tuning aid).
+
+    with KernelProfiler() as prof:
+        trainer.train_batch(...)
+    prof.summary()  -> rows sorted by total device time, with algorithmic bytes / flops where modelled
+"""
+from collections import defaultdict
+
+import torch
+
+from . import _lib
+
+
+def _conv_key(args):
+    # (x, wp, bias, y, N, H, W, Cin, Cout, k, up, ...)
+    n, h, w, cin, cout, k, up = args[4:11]
+    return f'N{n} {h}x{w} {cin}->{cout} k{k} up{up}'
+
+
+def _conv_bytes_flops(args, elt=2):
+    n, h, w, cin, cout, k, up = args[4:11]
+    pix_out = n * h * w
+    pix_in = pix_out >> (2 * up)
+    return (pix_in * cin + pix_out * cout) * elt, 2.0 * pix_out * cin * cout * k * k
+
+
+def _wgrad_key(args):
+    n, h, w, cin, cout, k, up = args[3:10]
+    return f'N{n} {h}x{w} {cin}->{cout} k{k} up{up}'
+
+
+def _wgrad_bytes_flops(args, elt=2):
+    n, h, w, cin, cout, k, up = args[3:10]
+    pix_out = n * h * w
+    return ((pix_out >> (2 * up)) * cin + pix_out * cout) * elt, 2.0 * pix_out * cin * cout * k * k
+
+
+class KernelProfiler:
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        _lib.Counters.profiler = self
+        return self
+
+    def __exit__(self, *a):
+        _lib.Counters.profiler = None
+
+    def record(self, name, args, e0, e1):
+        key, nbytes, flops = '', 0, 0.0
+        if name in ('ttg_conv2d_tc', 'ttg_conv2d_direct'):
+            key = _conv_key(args)
+            nbytes, flops = _conv_bytes_flops(args)
+        elif name in ('ttg_conv2d_wgrad_tc', 'ttg_conv2d_wgrad_direct'):
+            key = _wgrad_key(args)
+            nbytes, flops = _wgrad_bytes_flops(args)
+        elif name in ('ttg_bn_stats',):
+            key = f'M{args[1]} C{args[2]}'
+            nbytes = args[1] * args[2] * 2
+        elif name == 'ttg_bn_act_fwd':
+            key = f'M{args[2]} C{args[3]}'
+            nbytes = args[2] * args[3] * 2 * 2
+        elif name == 'ttg_bn_act_bwd':
+            key = f'M{args[3]} C{args[4]}'
+            nbytes = args[3] * args[4] * 2 * 5          # reduce reads x,ga; apply reads x,ga writes gx
+        elif name == 'ttg_bn_act_bwd2':
+            key = f'M{args[5]} C{args[6]}'
+            nbytes = args[5] * args[6] * 2 * 8          # reduce reads 3; apply reads 3 writes 2
+        self.events.append((name, key, nbytes, flops, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = defaultdict(lambda: [0, 0.0, 0, 0.0])
+        for name, key, nbytes, flops, e0, e1 in self.events:
+            a = agg[(name, key)]
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += nbytes
+            a[3] += flops
+        rows = [dict(name=n, key=k, calls=v[0], ms=v[1], bytes=v[2], flops=v[3]) for (n, k), v in agg.items()]
+        rows.sort(key=lambda r: -r['ms'])
+        return rows
+
+    def by_name(self):
+        rows = self.summary()
+        agg = defaultdict(lambda: dict(calls=0, ms=0.0, bytes=0, flops=0.0))
+        for r in rows:
+            a = agg[r['name']]
+            a['calls'] += r['calls']
+            a['ms'] += r['ms']
+            a['bytes'] += r['bytes']
+            a['flops'] += r['flops']
+        out = [dict(name=k, **v) for k, v in agg.items()]
+        out.sort(key=lambda r: -r['ms'])
+        return out
