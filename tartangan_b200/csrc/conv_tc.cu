@@ -47,33 +47,139 @@ extern "C" int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, i
 
 // ------------------------------------------------------------------ staging of an activation tile
 // Writes the [C/8][HP] x 16B image of the (TC_TH+2h) x (TC_TW+2h) halo tile at (y0-h, x0-h).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int HALO>
+__device__ __forceinline__ bool tile_src(int u, int c8n, int n, int y0, int x0, int H, int W, int C, int up,
+                                         long long& src_elem, uint32_t& dst_unit) {
+  constexpr int WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  const int c8 = u % c8n, pix = u / c8n;
+  const int hy = pix / WH, hx = pix - hy * WH;
+  const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
+  dst_unit = (uint32_t)(c8 * HP + pix);
+  const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+  src_elem = ok ? ((((long long)n * (H >> up) + (gy >> up)) * (W >> up) + (gx >> up)) * C + c8 * 8) : 0;
+  return ok;
+}
+
+// asynchronous version (LDGSTS, zero-fill outside the image); caller waits with cp_async_wait_all()
+template <int HALO>
+__device__ __forceinline__ void stage_tile_async(uint8_t* sA, const bf16* __restrict__ x, int n, int y0, int x0, int H,
+                                                 int W, int C, int up, int nthr) {
+  constexpr int HP = (TC_TW + 2 * HALO) * (TC_TH + 2 * HALO);
+  const int c8n = C >> 3;
+  const uint32_t base = smem_u32(sA);
+  for (int u = threadIdx.x; u < HP * c8n; u += nthr) {
+    long long se; uint32_t du;
+    const bool ok = tile_src<HALO>(u, c8n, n, y0, x0, H, W, C, up, se, du);
+    cp_async16(base + du * 16, x + se, ok ? 16u : 0u);
+  }
+}
+
+// register version, 4 loads in flight per thread, optional fused BatchNorm+LeakyReLU transform
 template <int HALO>
 __device__ __forceinline__ void stage_tile(uint8_t* sA, const bf16* __restrict__ x, int n, int y0, int x0, int H, int W,
                                            int C, int up, const float* __restrict__ pre_scale,
-                                           const float* __restrict__ pre_shift, float slope) {
-  constexpr int WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+                                           const float* __restrict__ pre_shift, float slope, int nthr) {
+  constexpr int HP = (TC_TW + 2 * HALO) * (TC_TH + 2 * HALO);
   const int c8n = C >> 3;
-  const int Hi = H >> up, Wi = W >> up;
-  for (int u = threadIdx.x; u < HP * c8n; u += blockDim.x) {
-    const int c8 = u % c8n, pix = u / c8n;
-    const int hy = pix / WH, hx = pix - hy * WH;
-    const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      v = *reinterpret_cast<const uint4*>(x + (((long long)n * Hi + (gy >> up)) * Wi + (gx >> up)) * C + c8 * 8);
-      if (pre_scale) {
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const int total = HP * c8n;
+  for (int base = 0; base < total; base += 4 * nthr) {
+    uint4 v[4]; uint32_t du[4]; bool live[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(h[j]);
-          const int c = c8 * 8 + 2 * j;
-          f.x = lrelu(f.x * pre_scale[c] + pre_shift[c], slope);
-          f.y = lrelu(f.y * pre_scale[c + 1] + pre_shift[c + 1], slope);
-          h[j] = __floats2bfloat162_rn(f.x, f.y);
-        }
+    for (int j = 0; j < 4; ++j) {
+      const int u = base + j * nthr + threadIdx.x;
+      live[j] = u < total;
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      du[j] = 0;
+      if (live[j]) {
+        long long se;
+        if (tile_src<HALO>(u, c8n, n, y0, x0, H, W, C, up, se, du[j])) v[j] = __ldg(reinterpret_cast<const uint4*>(x + se));
+        else du[j] |= 0x80000000u;       // mark padding: stays exactly zero (padding applies after the activation)
       }
     }
-    *reinterpret_cast<uint4*>(sA + ((size_t)c8 * HP + pix) * 16) = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!live[j]) continue;
+      const bool pad = du[j] & 0x80000000u;
+      const uint32_t unit = du[j] & 0x7fffffffu;
+      if (pre_scale && !pad) {
+        const int c8 = unit / HP;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[j]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 f = __bfloat1622float2(h[q]);
+          const int c = c8 * 8 + 2 * q;
+          f.x = lrelu(f.x * pre_scale[c] + pre_shift[c], slope);
+          f.y = lrelu(f.y * pre_scale[c + 1] + pre_shift[c + 1], slope);
+          h[q] = __floats2bfloat162_rn(f.x, f.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = v[j];
+    }
+  }
+}
+
+// Fast staging for the persistent kernel (units per halo row <= 128): every thread owns one fixed
+// (column, channel-group) position of the halo row and walks down the rows, so all div/mod work is
+// done once per kernel and a 16-byte unit costs ~10 instructions instead of ~70.
+struct RowStager {
+  int q_hx, q_c8, r0, rpp, active;     // fixed per thread
+};
+template <int HALO>
+__device__ __forceinline__ RowStager make_row_stager(int C, int tid) {
+  constexpr int WH = TC_TW + 2 * HALO;
+  const int c8n = C >> 3, upr = WH * c8n;
+  RowStager rs;
+  rs.rpp = 128 / upr;
+  const int q = tid % upr;
+  rs.r0 = tid / upr;
+  rs.active = tid < upr * rs.rpp;
+  rs.q_hx = q / c8n;
+  rs.q_c8 = q - rs.q_hx * c8n;
+  return rs;
+}
+template <int HALO, bool ASYNC>
+__device__ __forceinline__ void stage_rows(const RowStager& rs, uint8_t* sA, const bf16* __restrict__ x, int n, int y0,
+                                           int x0, int H, int W, int C, int up, const float* __restrict__ pre_scale,
+                                           const float* __restrict__ pre_shift, float slope) {
+  constexpr int WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  if (!rs.active) return;
+  const int gx = x0 + rs.q_hx - HALO;
+  const bool xok = gx >= 0 && gx < W;
+  const int Wi = W >> up, Hi = H >> up;
+  const bf16* col = x + ((long long)n * Hi * Wi + (gx >> up)) * C + rs.q_c8 * 8;
+  uint32_t dst = smem_u32(sA) + (uint32_t)(rs.q_c8 * HP + rs.r0 * WH + rs.q_hx) * 16;
+  const uint32_t dstep = (uint32_t)(rs.rpp * WH) * 16;
+  float sc[8], sh[8];
+  if constexpr (!ASYNC) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = pre_scale[rs.q_c8 * 8 + j]; sh[j] = pre_shift[rs.q_c8 * 8 + j]; }
+  }
+  for (int r = rs.r0; r < HH; r += rs.rpp, dst += dstep) {
+    const int gy = y0 + r - HALO;
+    const bool ok = xok && gy >= 0 && gy < H;
+    const bf16* src = ok ? col + (long long)(gy >> up) * Wi * C : x;
+    if constexpr (ASYNC) {
+      cp_async16(dst, src, ok ? 16u : 0u);
+    } else {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) {
+        v = __ldg(reinterpret_cast<const uint4*>(src));
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float2 f = __bfloat1622float2(h[q]);
+          f.x = lrelu(f.x * sc[2 * q] + sh[2 * q], slope);
+          f.y = lrelu(f.y * sc[2 * q + 1] + sh[2 * q + 1], slope);
+          h[q] = __floats2bfloat162_rn(f.x, f.y);
+        }
+      }
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
   }
 }
 
@@ -103,7 +209,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const bf16* __restrict__ x
 
   if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
-  stage_tile<HALO>(sA, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope);
+  stage_tile<HALO>(sA, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope, 128);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -179,6 +285,195 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const bf16* __restrict__ x
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// ------------------------------------------------------------------ fprop / dgrad, persistent (weights resident)
+// For layers whose packed filter fits in shared memory (C <= 64): one CTA loops over tiles with the
+// filter loaded once, two activation buffers and two TMEM accumulators, so that per tile the
+// cp.async loads of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+template <int HALO>
+__device__ __forceinline__ void conv_tc_epilogue(uint32_t tacc, int warp, int tid, int n, int y0, int x0, int H, int W,
+                                                 int Cout, const float* __restrict__ bias, void* __restrict__ y, int out_f32) {
+  const int gy = y0 + (tid >> 3), gx = x0 + (tid & 7);
+  const bool valid = gy < H && gx < W;
+  const long long opix = ((long long)n * H + gy) * W + gx;
+  for (int c0 = 0; c0 < Cout; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (valid) {
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(r[j]) + (bias ? bias[c0 + j] : 0.f);
+      if (out_f32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + opix * Cout + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4 o[2];
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(y) + opix * Cout + c0);
+        dst[0] = o[0]; dst[1] = o[1];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised persistent kernel: warps 0-3 stage tiles (cp.async, NBUF-deep ring) and run the
+// epilogue; warp 4 only issues tcgen05.mma.  Hand-offs are mbarriers (full/empty per activation slot,
+// full/empty per TMEM accumulator), so loads of tile i+NBUF-1, MMAs of tile i and the epilogue of
+// tile i-1 are in flight together and nobody waits for the single MMA-issuing thread.
+template <int K, int NBUF>
+__global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                              const float* __restrict__ bias, void* __restrict__ y,
+                                                              int out_f32, int H, int W, int Cin, int Cout, int up,
+                                                              const float* __restrict__ pre_scale,
+                                                              const float* __restrict__ pre_shift, float slope,
+                                                              int total_tiles, int tmem_cols) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  // DIST tiles are prefetched ahead; NBUF - DIST >= 2 leaves a slot of slack so that re-using a slot never
+  // waits on MMAs issued in the previous iteration.  The epilogue runs LAG tiles behind over 4 accumulators.
+  constexpr int DIST = NBUF > 2 ? NBUF - 2 : 1;
+  constexpr int LAG = 2, NACC = 4;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k16n = Cin >> 4;
+  const uint32_t slice_bytes = (uint32_t)Cout * 32;
+  const uint32_t w_bytes = (uint32_t)(K * K * k16n) * slice_bytes;
+  const uint32_t a_bytes = (uint32_t)(Cin >> 3) * HP * 16;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + w_bytes;                                               // NBUF slots
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + NBUF * (size_t)a_bytes);  // slot staged (128 arrivals)
+  uint64_t* empty = full + NBUF;                                              // slot consumed by the MMAs (commit)
+  uint64_t* acc_full = empty + NBUF;                                          // accumulator ready (commit)
+  uint64_t* acc_empty = acc_full + NACC;                                      // accumulator drained (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  auto tile_coords = [&](int j, int& n, int& y0, int& x0) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    n = tile / tiles_img;
+    const int t2 = tile - n * tiles_img;
+    y0 = (t2 / tiles_x) * TC_TH;
+    x0 = (t2 % tiles_x) * TC_TW;
+  };
+
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_fence_init();
+  }
+  if (warp < 4)
+    for (int i = tid; i < (int)(w_bytes / 16); i += 128)
+      reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ loaders + epilogue (128 threads)
+    const bool fast_stage = WH * (Cin >> 3) <= 128;
+    const RowStager rs = make_row_stager<HALO>(fast_stage ? Cin : 16, tid);
+    auto stage = [&](int j) {           // always commits one cp.async group (possibly empty)
+      if (j < T) {
+        const int s = j % NBUF;
+        if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u);   // MMAs of tile j-NBUF done with the slot
+        int n, y0, x0;
+        tile_coords(j, n, y0, x0);
+        uint8_t* dst = sA + (size_t)s * a_bytes;
+        if (fast_stage) {
+          if (pre_scale) stage_rows<HALO, false>(rs, dst, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope);
+          else stage_rows<HALO, true>(rs, dst, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+        } else {
+          if (pre_scale) stage_tile<HALO>(dst, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope, 128);
+          else stage_tile_async<HALO>(dst, x, n, y0, x0, H, W, Cin, up, 128);
+        }
+      }
+      cp_async_commit();
+    };
+    auto epilogue = [&](int j) {
+      const int acc = j & (NACC - 1);
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      tc_fence_after_sync();
+      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+    };
+#pragma unroll
+    for (int d = 0; d < DIST; ++d) stage(d);
+    for (int it = 0; it < T; ++it) {
+      stage(it + DIST);
+      cp_async_wait_group<DIST>();       // this thread's part of tile `it` has landed
+      fence_proxy_async_smem();          // ... and is visible to the tensor-core proxy
+      mbar_arrive(&full[it % NBUF]);
+      if (it >= LAG) epilogue(it - LAG);
+    }
+    for (int j = T > LAG ? T - LAG : 0; j < T; ++j) epilogue(j);
+    cp_async_wait_all();
+  } else {
+    // ------------------------------------------------------------ MMA issuer (warp 4)
+    const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
+    const uint64_t b0 = umma_desc(smem_u32(sW), (uint32_t)Cout * 16, 128);
+    const uint32_t b_step = slice_bytes >> 4;
+    for (int it = 0; it < T; ++it) {
+      const int s = it % NBUF, acc = it & (NACC - 1);
+      mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+      if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), HP * 16, WH * 16);
+        const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
+        uint32_t sl = 0;
+#pragma unroll
+        for (int tap = 0; tap < K * K; ++tap) {
+          const int ky = tap / K, kx = tap % K;
+          for (int j = 0; j < k16n; ++j, ++sl)
+            umma_bf16(dacc, a0 + (uint64_t)((ky * WH + kx) + 2 * j * HP), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[acc]);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+template <int K, int NBUF>
+static int launch_conv_tc_persist(const void* x, const void* wp, const float* bias, void* y, int out_f32, int H, int W,
+                                  int Cin, int Cout, int up, const float* pre_scale, const float* pre_shift, float slope,
+                                  long long tiles, int psmem, int pcols, int per_sm, cudaStream_t st) {
+  static int smem_set = 0;
+  if (psmem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set = psmem;
+  }
+  long long grid = (long long)ttg_num_sms() * per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc_persist_kernel<K, NBUF><<<(unsigned)grid, 160, psmem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
+                                                                     Cout, up, pre_scale, pre_shift, slope, (int)tiles, pcols);
+  TTG_CHECK_LAUNCH("conv2d_tc_persist");
+  return TTG_OK;
+}
+
+#define TC_RESIDENT_W_BYTES (80 * 1024)
+
 static int g_conv_tc_smem[2] = {0, 0};
 
 extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
@@ -203,6 +498,23 @@ extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bia
   const int smem = (Cin / 8) * HP * 16 + nstages * stage_slices * slice_bytes + 64;
   const long long tiles = (long long)N * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
   TTG_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv2d_tc: bad problem size");
+  const int w_bytes = total_slices * slice_bytes;
+  if (w_bytes <= TC_RESIDENT_W_BYTES) {
+    const int a_bytes = (Cin / 8) * HP * 16;
+    const int nbuf = a_bytes <= 12 * 1024 ? 4 : (a_bytes <= 24 * 1024 ? 3 : 2);
+    const int psmem = w_bytes + nbuf * a_bytes + 256;
+    const int pcols = (int)tmem_cols_for(4 * Cout);
+    int per_sm = (200 * 1024) / psmem;
+    if (per_sm > 512 / pcols) per_sm = 512 / pcols;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const int of32 = dtype_out == TTG_F32;
+#define TTG_PERSIST(KK, NB) launch_conv_tc_persist<KK, NB>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, pre_shift, \
+                                                        slope, tiles, psmem, pcols, per_sm, st)
+    if (ksize == 3) return nbuf == 4 ? TTG_PERSIST(3, 4) : nbuf == 3 ? TTG_PERSIST(3, 3) : TTG_PERSIST(3, 2);
+    return nbuf == 4 ? TTG_PERSIST(1, 4) : nbuf == 3 ? TTG_PERSIST(1, 3) : TTG_PERSIST(1, 2);
+#undef TTG_PERSIST
+  }
   const int ki = ksize == 3 ? 1 : 0;
   if (smem > g_conv_tc_smem[ki]) {
     cudaError_t e = ksize == 3
@@ -269,7 +581,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_tc_kernel(const bf16* __restri
     const int n = (int)(tile / (tiles_x * tiles_y)), t2 = (int)(tile - (long long)n * tiles_x * tiles_y);
     const int y0 = (t2 / tiles_x) * TC_TH, x0 = (t2 % tiles_x) * TC_TW;
     if (!first) { mbar_wait(&bars[0], phase); phase ^= 1u; }       // previous tile's MMAs have consumed the smem
-    stage_tile<HALO>(sX, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+    stage_tile<HALO>(sX, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f, 128);
     for (int u = tid; u < NPIX * g8n; u += blockDim.x) {
       const int g8 = u % g8n, pix = u / g8n;
       const int py = y0 + (pix >> 3), px = x0 + (pix & 7);

@@ -1,0 +1,69 @@
+"""Micro-benchmark of single kernels through the C ABI (CUDA events, L2 flushed between runs).
+    python tools/kbench.py conv 256 128 128 16 16 3 [reps]
+    python tools/kbench.py wgrad 256 128 128 16 16 3
+    python tools/kbench.py bn 4194304 16
+"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tartangan_b200 import ops, _lib
+from tartangan_b200._lib import call, ptr
+
+def timeit(fn, reps=10):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+def main():
+    kind = sys.argv[1]
+    a = [int(v) for v in sys.argv[2:]]
+    bf = torch.bfloat16
+    if kind in ('conv', 'wgrad', 'convd'):
+        n, h, w, cin, cout, k = a[:6]
+        reps = a[6] if len(a) > 6 else 10
+        x = ops.empty_nhwc(n, cin, h, w, bf, 'cuda'); x.normal_()
+        wt = torch.randn(cout, cin, k, k, device='cuda') * 0.05
+        nbytes = n * h * w * (cin + cout) * 2
+        flops = 2.0 * n * h * w * cin * cout * k * k
+        if kind == 'conv':
+            wp = ops._packed(wt, 0, 'tc')
+            y = ops.empty_nhwc(n, cout, h, w, bf, 'cuda')
+            fn = lambda: call('ttg_conv2d_tc', ptr(x), ptr(wp), None, ptr(y), n, h, w, cin, cout, k, 0, _lib.BF16)
+        elif kind == 'convd':
+            wp = ops._packed(wt, 0, 'direct')
+            y = ops.empty_nhwc(n, cout, h, w, bf, 'cuda')
+            fn = lambda: call('ttg_conv2d_direct', ptr(x), ptr(wp), None, ptr(y), n, h, w, cin, cout, k, 0, _lib.BF16, _lib.BF16)
+        else:
+            gy = ops.empty_nhwc(n, cout, h, w, bf, 'cuda'); gy.normal_()
+            gw = torch.empty(cout, cin, k, k, device='cuda')
+            ws = torch.empty(16, device='cuda')
+            fn = lambda: call('ttg_conv2d_wgrad_tc', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, 0, ptr(ws))
+        med, best = timeit(fn, reps)
+        print(f'{kind} N{n} {h}x{w} {cin}->{cout} k{k}: median {med*1e3:.1f} us  best {best*1e3:.1f} us  '
+              f'{nbytes/med/1e6:.0f} GB/s  {flops/med/1e9:.1f} TFLOP/s')
+    elif kind == 'bn':
+        m, c = a[:2]
+        x = torch.randn(m, c, device='cuda').to(bf)
+        mean = torch.zeros(c, device='cuda'); inv = torch.ones(c, device='cuda')
+        ws = torch.empty(5 * c, dtype=torch.float64, device='cuda')
+        y = torch.empty_like(x)
+        fn = lambda: call('ttg_bn_stats', ptr(x), m, c, 1e-5, 0.1, ptr(mean), ptr(inv), None, None, None, ptr(ws), _lib.BF16)
+        med, best = timeit(fn)
+        print(f'bn_stats M{m} C{c}: {med*1e3:.1f} us {m*c*2/med/1e6:.0f} GB/s')
+        fn = lambda: call('ttg_bn_act_fwd', ptr(x), ptr(y), m, c, ptr(mean), ptr(inv), ptr(inv), ptr(mean), 0.2, _lib.BF16)
+        med, best = timeit(fn)
+        print(f'bn_act_fwd M{m} C{c}: {med*1e3:.1f} us {m*c*4/med/1e6:.0f} GB/s')
+        g = torch.empty(c, device='cuda')
+        fn = lambda: call('ttg_bn_act_bwd', ptr(x), ptr(y), ptr(y), m, c, ptr(mean), ptr(inv), ptr(inv), ptr(mean), 0.2, ptr(g), ptr(g), ptr(ws), _lib.BF16)
+        med, best = timeit(fn)
+        print(f'bn_act_bwd M{m} C{c}: {med*1e3:.1f} us {m*c*10/med/1e6:.0f} GB/s')
+
+main()

@@ -1,0 +1,35 @@
+"""Print headline metrics + hottest SASS lines (stall samples) of an .ncu-rep."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, vals = rows[0], rows[2]
+keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__occupancy_limit',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_bytes.sum ', 'sm__inst_executed.sum ', 'launch__grid_size',
+        'smsp__inst_executed.sum', 'sm__cycles_elapsed.max', 'lts__t_sector_hit_rate.pct']
+for i, h in enumerate(hdr):
+    if any(h == k.strip() or (k.endswith('limit') and k in h) for k in keys):
+        print(f'{h} = {vals[i]} {rows[1][i]}')
+st = []
+for i, h in enumerate(hdr):
+    if 'pcsamp_warps_issue_stalled' in h and 'not_issued' not in h:
+        try: st.append((float(vals[i].replace(',', '')), h.split('stalled_')[1]))
+        except Exception: pass
+st.sort(reverse=True)
+print('stalls:', ', '.join(f'{n}={int(v)}' for v, n in st[:8]))
+src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(src.splitlines()))
+hdr = rows[1]
+ci = {h: i for i, h in enumerate(hdr)}
+col, ex = ci['Warp Stall Sampling (All Samples)'], ci['Instructions Executed']
+rs = []
+for idx, r in enumerate(rows[2:]):
+    try: rs.append((int(r[col]), idx, r[ci['Source']].strip()[:100], r[ex]))
+    except Exception: pass
+tot = sum(v for v, *_ in rs)
+print('total samples', tot, 'instructions', len(rs))
+for v, idx, s, e in sorted(rs, reverse=True)[:top]:
+    print(f'{v:6d} {100*v/max(tot,1):5.1f}%  #{idx:4d} x{e:>8s}  {s}')
