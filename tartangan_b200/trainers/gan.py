@@ -77,12 +77,28 @@ class GanTrainer(Trainer):
         raise NotImplementedError
 
     # ------------------------------------------------------------------ one optimisation step
-    def _allreduce(self, optimizer):
-        if self.world_size > 1:
-            flat = optimizer._ensure_flat()
-            torch.distributed.all_reduce(flat.grad)
-            ops.call('ttg_axpby', ops.ptr(flat.grad), ops.ptr(flat.grad), ops.ptr(flat.grad), flat.numel,
-                     1.0 / self.world_size, 0.0, 0)
+    def _reducer(self, optimizer):
+        """Bucketed all-reduce over the optimiser's flat gradient buffer (data parallel only)."""
+        if self.world_size == 1:
+            return None
+        flat = optimizer._ensure_flat()
+        red = getattr(optimizer, '_ttg_reducer', None)
+        if red is None or red.flat_grad is not flat.grad:
+            from ..parallel import BucketedAllReduce
+            red = BucketedAllReduce(flat.params, flat.offsets, flat.grad, num_buckets=2)
+            optimizer._ttg_reducer = red
+        return red
+
+    def _backward(self, loss, optimizer):
+        """loss.backward() with the gradient exchange overlapped: the loss is scaled by 1/world so the
+        summed gradients are the global-batch average."""
+        red = self._reducer(optimizer)
+        if red is None:
+            loss.backward()
+            return
+        red.begin()
+        loss.backward(torch.full_like(loss, 1.0 / self.world_size))
+        red.finish()
 
     def d_step(self, imgs):
         toggle_grad(self.g, False)
@@ -98,8 +114,7 @@ class GanTrainer(Trainer):
         if self.args.grad_penalty:
             gp = gradient_penalty(p_real, real)
             d_loss = ops.AxpbyFn.apply(d_loss, gp, 1.0, float(self.args.grad_penalty))
-        d_loss.backward()
-        self._allreduce(self.optimizer_d)
+        self._backward(d_loss, self.optimizer_d)
         self.optimizer_d.step()
         return d_loss, gp
 
@@ -109,8 +124,7 @@ class GanTrainer(Trainer):
         self.optimizer_g.zero_grad()
         fake = self.sample_g(len(imgs))
         g_loss = self.g_loss(fake)
-        g_loss.backward()
-        self._allreduce(self.optimizer_g)
+        self._backward(g_loss, self.optimizer_g)
         # Adam and the EMA of target_g (update_target_generator) are one kernel
         self.optimizer_g.ema_target = self._flat_target()
         self.optimizer_g.ema_lr = float(self.args.lr_target_g)

@@ -1,0 +1,142 @@
+"""CPU-only checks of the host side: C-ABI surface, module/state-dict parity with the reference's
+initial states (golden), loud failure without CUDA, flat parameter buffers, and the data-parallel
+gradient exchange over gloo (world size 2)."""
+import functools
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+
+def test_header_and_library_agree():
+    from tartangan_b200 import _lib
+    protos = _lib.parse_header()
+    assert len(protos) >= 55
+    _lib.lib.load()                     # raises if any declared symbol is missing from the .so
+    assert _lib.lib.ttg_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+    out = subprocess.run(['nm', '-D', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if ' T ttg_' in l}
+    assert set(protos) <= exported, set(protos) - exported
+
+
+def _build(kind, g):
+    from tartangan_b200.models import pluggan
+    from tartangan_b200.models.blocks import (DiscriminatorOutput, GeneratorInputMLP, GeneratorOutput,
+                                               IQNDiscriminatorOutput, ResidualDiscriminatorBlock,
+                                               ResidualGeneratorBlock)
+    from tartangan_b200.models.layers import BatchNorm2d
+    from torch import nn
+    cfg = pluggan.GANConfig(base_size=4, latent_dims=g['latent'], data_dims=3, blocks=tuple(g['blocks']),
+                            num_blocks_per_scale=1, attention=tuple(g['attention']))
+    norm = {'bn': BatchNorm2d, 'id': nn.Identity}[g['norm']]
+    gf = dict(input_factory=GeneratorInputMLP,
+              block_factory=functools.partial(ResidualGeneratorBlock, norm_factory=norm),
+              output_factory=functools.partial(GeneratorOutput, norm_factory=norm))
+    torch.manual_seed(0)
+    gen = pluggan.Generator(cfg, **gf)
+    tgt = pluggan.Generator(cfg, **gf)
+    dcls, ocls = ((pluggan.Discriminator, DiscriminatorOutput) if kind == 'cnn'
+                  else (pluggan.IQNDiscriminator, IQNDiscriminatorOutput))
+    d = dcls(cfg, block_factory=functools.partial(ResidualDiscriminatorBlock, norm_factory=norm),
+             output_factory=functools.partial(ocls, norm_factory=norm))
+    return gen, tgt, d
+
+
+def test_modules_match_reference_initial_state(golden):
+    """Same seed -> same parameter tensors under the same state-dict keys as the reference modules."""
+    g = golden
+    gen, tgt, d = _build(g['kind'], g)
+    for name, mod in (('g', gen), ('d', d)):
+        ref, sd = g['init'][name], mod.state_dict()
+        assert list(sd.keys()) == list(ref.keys())
+        for k, v in ref.items():
+            if k.endswith('gamma'):
+                continue                       # the golden script sets attention gamma to 0.5 after init
+            assert torch.equal(sd[k], v), (name, k)
+    assert gen.max_size == g['size']
+
+
+def test_no_cpu_fallback():
+    g = load_golden('cnn_tiny')
+    gen, _, d = _build('cnn', g)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        gen(torch.randn(2, g['latent']))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        d(torch.randn(2, 3, g['size'], g['size']))
+    from tartangan_b200.trainers.utils import set_device_from_args
+    import argparse
+    with pytest.raises(RuntimeError):
+        set_device_from_args(argparse.Namespace(no_cuda=True))
+
+
+def test_flat_params_views():
+    from tartangan_b200.optim import FlatParams
+    ps = [torch.nn.Parameter(torch.randn(3, 5)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(2, 2, 3))]
+    before = [p.detach().clone() for p in ps]
+    flat = FlatParams(ps)
+    assert flat.intact() and flat.numel % 4 == 0
+    for p, b, o in zip(ps, before, flat.offsets):
+        assert torch.equal(p.data, b) and o % 4 == 0
+        assert p.data_ptr() == flat.data.data_ptr() + 4 * o
+    flat.attach_grads()
+    ps[1].grad.add_(1.0)
+    assert float(flat.grad.sum()) == 7.0
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tartangan_b200.optim import FlatParams
+    from tartangan_b200.parallel import BucketedAllReduce, shard_batch
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 6), torch.nn.Tanh(), torch.nn.Linear(6, 6), torch.nn.Tanh(), torch.nn.Linear(6, 6), torch.nn.Linear(6, 1))
+    flat = FlatParams(list(model.parameters()))
+    red = BucketedAllReduce(flat.params, flat.offsets, flat.grad, num_buckets=2)
+    assert len(red.buckets) >= 2 and red.buckets[0][0] == 0 and red.buckets[-1][1] == flat.numel
+    assert all(a[1] == b[0] for a, b in zip(red.buckets, red.buckets[1:]))      # contiguous cover
+    assert sorted(i for _, _, m in red.buckets for i in m) == list(range(len(flat.params)))
+    torch.manual_seed(7)
+    x = torch.randn(8, 6)
+    xs = x[shard_batch(8, world, rank)]
+    flat.attach_grads()
+    red.begin()
+    loss = model(xs).pow(2).mean()
+    loss.backward(torch.full_like(loss, 1.0 / world))
+    red.finish()
+    if rank == 0:
+        torch.save(flat.grad.clone(), out)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gloo_world2(tmp_path):
+    """Two ranks, each on half the batch: exchanged gradients equal the full-batch gradient."""
+    out = str(tmp_path / 'grad.pt')
+    port = 29500 + os.getpid() % 1000
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    from tartangan_b200.optim import FlatParams
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 6), torch.nn.Tanh(), torch.nn.Linear(6, 6), torch.nn.Tanh(), torch.nn.Linear(6, 6), torch.nn.Linear(6, 1))
+    flat = FlatParams(list(model.parameters()))
+    flat.attach_grads()
+    torch.manual_seed(7)
+    x = torch.randn(8, 6)
+    model(x).pow(2).mean().backward()
+    assert torch.allclose(got, flat.grad, atol=1e-6)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '1'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'images/sec' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
