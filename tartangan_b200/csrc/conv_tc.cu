@@ -46,7 +46,10 @@ extern "C" int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, i
 }
 
 // ------------------------------------------------------------------ staging of an activation tile
-// Writes the [C/8][HP] x 16B image of the (TC_TH+2h) x (TC_TW+2h) halo tile at (y0-h, x0-h).
+// Writes the [halo row][C/8][halo col] x 16B image of the (TC_TH+2h) x (TC_TW+2h) halo tile at (y0-h, x0-h):
+// unit index = (hy * C/8 + c8) * WH + hx.  Rows of 8 pixels are contiguous (one 8 x 16 B core matrix), the next
+// channel group is WH units away and the next halo row C/8 * WH units away, so both the vertical filter taps
+// and the channel groups are reachable with ONE uniform descriptor stride (used by wgrad to fold ky into N).
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -59,7 +62,7 @@ __device__ __forceinline__ bool tile_src(int u, int c8n, int n, int y0, int x0, 
   const int c8 = u % c8n, pix = u / c8n;
   const int hy = pix / WH, hx = pix - hy * WH;
   const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
-  dst_unit = (uint32_t)(c8 * HP + pix);
+  dst_unit = (uint32_t)((hy * c8n + c8) * WH + hx);
   const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
   src_elem = ok ? ((((long long)n * (H >> up) + (gy >> up)) * (W >> up) + (gx >> up)) * C + c8 * 8) : 0;
   return ok;
@@ -107,7 +110,7 @@ __device__ __forceinline__ void stage_tile(uint8_t* sA, const bf16* __restrict__
       const bool pad = du[j] & 0x80000000u;
       const uint32_t unit = du[j] & 0x7fffffffu;
       if (pre_scale && !pad) {
-        const int c8 = unit / HP;
+        const int c8 = (int)(unit / (TC_TW + 2 * HALO)) % c8n;
         __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[j]);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -152,8 +155,9 @@ __device__ __forceinline__ void stage_rows(const RowStager& rs, uint8_t* sA, con
   const bool xok = gx >= 0 && gx < W;
   const int Wi = W >> up, Hi = H >> up;
   const bf16* col = x + ((long long)n * Hi * Wi + (gx >> up)) * C + rs.q_c8 * 8;
-  uint32_t dst = smem_u32(sA) + (uint32_t)(rs.q_c8 * HP + rs.r0 * WH + rs.q_hx) * 16;
-  const uint32_t dstep = (uint32_t)(rs.rpp * WH) * 16;
+  const int c8n = C >> 3;
+  uint32_t dst = smem_u32(sA) + (uint32_t)((rs.r0 * c8n + rs.q_c8) * WH + rs.q_hx) * 16;
+  const uint32_t dstep = (uint32_t)(rs.rpp * c8n * WH) * 16;
   float sc[8], sh[8];
   if constexpr (!ASYNC) {
 #pragma unroll
@@ -241,8 +245,9 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const bf16* __restrict__ x
         const int slice = first + i;
         const int tap = slice / k16n, j = slice - tap * k16n;
         const int ky = tap / K, kx = tap - ky * K;
-        // A: rows = 16 groups of 8 pixels (SBO = one halo row), K chunks of 8 channels (LBO = HP units)
-        const uint64_t adesc = umma_desc(sA_addr + (uint32_t)((ky * WH + kx) + 2 * j * HP) * 16, HP * 16, WH * 16);
+        // A: rows = 16 groups of 8 pixels (SBO = one halo row = C/8*WH units), K chunks of 8 channels (LBO = WH units)
+        const int c8n = Cin >> 3;
+        const uint64_t adesc = umma_desc(sA_addr + (uint32_t)((ky * c8n * WH + kx) + 2 * j * WH) * 16, WH * 16, c8n * WH * 16);
         // B: rows = Cout (SBO = 8 rows x 16 B), K chunks (LBO = Cout units)
         const uint64_t bdesc = umma_desc(sW_addr + (uint32_t)i * slice_bytes, (uint32_t)Cout * 16, 128);
         umma_bf16(tmem_base, adesc, bdesc, idesc, slice > 0 ? 1u : 0u);
@@ -434,14 +439,15 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
       if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
       tc_fence_after_sync();
       if (lane == 0) {
-        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), HP * 16, WH * 16);
+        const int c8n = Cin >> 3;
+        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
         const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
         uint32_t sl = 0;
 #pragma unroll
         for (int tap = 0; tap < K * K; ++tap) {
           const int ky = tap / K, kx = tap % K;
           for (int j = 0; j < k16n; ++j, ++sl)
-            umma_bf16(dacc, a0 + (uint64_t)((ky * WH + kx) + 2 * j * HP), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
+            umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
         }
         umma_commit(&empty[s]);
         umma_commit(&acc_full[acc]);
@@ -599,8 +605,9 @@ __global__ void __launch_bounds__(128) conv_wgrad_tc_kernel(const bf16* __restri
         for (int r = 0; r < TC_TH / 2; ++r) {
           // A = gy^T (MN-major): M groups of 8 channels (SBO = 128 pixels x 16 B), K = pixels: 8 per row (16 B apart), rows LBO apart
           const uint64_t adesc = umma_desc(sG_addr + (uint32_t)(2 * r * TC_TW) * 16, TC_TW * 16, NPIX * 16);
-          // B = shifted x (MN-major): N groups of 8 channels (SBO = HP x 16 B), K = pixels of halo rows 2r+ky, 2r+1+ky
-          const uint64_t bdesc = umma_desc(sX_addr + (uint32_t)((2 * r + ky) * WH + kx) * 16, WH * 16, HP * 16);
+          // B = shifted x (MN-major): N groups of 8 channels (SBO = WH units), K = pixels of halo rows 2r+ky, 2r+1+ky
+          const int c8n = Cin >> 3;
+          const uint64_t bdesc = umma_desc(sX_addr + (uint32_t)((2 * r + ky) * c8n * WH + kx) * 16, c8n * WH * 16, WH * 16);
           umma_bf16(tmem_base + (uint32_t)(t * Cin), adesc, bdesc, idesc, (first && r == 0) ? 0u : 1u);
         }
       }
@@ -630,6 +637,166 @@ __global__ void __launch_bounds__(128) conv_wgrad_tc_kernel(const bf16* __restri
   if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+// ------------------------------------------------------------------ wgrad, persistent + warp-specialised
+// warps 0-3 stage (x halo tile, gy tile) pairs with cp.async into an NBUF ring; warps 4-6 each issue the
+// MMAs of a share of the accumulator "units" (disjoint TMEM columns, so the issuing threads never touch
+// the same accumulator); accumulators stay in TMEM over all tiles of the CTA; one atomic epilogue.
+// For Cin <= 80 a unit is a filter column kx with N = 3*Cin: the [row][c8][col] tile layout makes the
+// three vertical taps one uniform-stride B operand, so gy^T (the A operand, mostly padding rows for
+// small Cout) is read 3 instead of 9 times per K step; with Cout <= 64 the MMA uses M = 64.
+template <int K, int NBUF>
+__global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy,
+                                                               float* __restrict__ gw, int N, int H, int W, int Cin,
+                                                               int Cout, int up, int units_per_group, int fuse,
+                                                               int tmem_cols, int g_bytes) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH, NPIX = TC_TH * TC_TW;
+  constexpr int DIST = NBUF > 2 ? NBUF - 2 : 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c8n = Cin >> 3;
+  const uint32_t x_bytes = (uint32_t)c8n * HP * 16;
+  uint8_t* sG = smem;                                   // NBUF gy tiles, [co/8][128 pixels] x 16 B
+  uint8_t* sX = smem + (size_t)NBUF * g_bytes;          // NBUF x halo tiles
+  // barriers live at the end of the allocation (the host pads so that an A descriptor that starts in
+  // the last gy slot never leaves the allocation)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NBUF * (g_bytes + x_bytes));
+  uint64_t* empty = full + NBUF;
+  uint64_t* done = empty + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int units_total = fuse ? K : K * K;
+  const int NU = fuse ? K * Cin : Cin;                  // accumulator columns per unit
+  const int unit0 = blockIdx.y * units_per_group;
+  const int nunits = min(units_per_group, units_total - unit0);
+  const int n_issuers = min(3, nunits);
+  const int co_base = blockIdx.z * 128;
+  const int co_cnt = min(128, Cout - co_base);
+  const bool m64 = Cout <= 64;
+  const int g8n = co_cnt >> 3;
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
+  const int total_tiles = N * tiles_img;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_coords = [&](int j, int& n, int& y0, int& x0) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    n = tile / tiles_img;
+    const int t2 = tile - n * tiles_img;
+    y0 = (t2 / tiles_x) * TC_TH;
+    x0 = (t2 % tiles_x) * TC_TW;
+  };
+
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], (uint32_t)n_issuers); }
+    mbar_init(done, (uint32_t)n_issuers);
+    mbar_fence_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    const bool fast_stage = WH * c8n <= 128;
+    const RowStager rs = make_row_stager<HALO>(fast_stage ? Cin : 16, tid);
+    auto stage = [&](int j) {
+      if (j < T) {
+        const int s = j % NBUF;
+        if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u);
+        int n, y0, x0;
+        tile_coords(j, n, y0, x0);
+        uint8_t* dx = sX + (size_t)s * x_bytes;
+        if (fast_stage) stage_rows<HALO, true>(rs, dx, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+        else stage_tile_async<HALO>(dx, x, n, y0, x0, H, W, Cin, up, 128);
+        const uint32_t dg = smem_u32(sG + (size_t)s * g_bytes);
+        for (int u = tid; u < NPIX * g8n; u += 128) {
+          const int g8 = u % g8n, pix = u / g8n;
+          const int py = y0 + (pix >> 3), px = x0 + (pix & 7);
+          const bool ok = py < H && px < W;
+          const bf16* src = ok ? gy + (((long long)n * H + py) * W + px) * Cout + co_base + g8 * 8 : gy;
+          cp_async16(dg + (uint32_t)(g8 * NPIX + pix) * 16, src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < DIST; ++d) stage(d);
+    for (int it = 0; it < T; ++it) {
+      stage(it + DIST);
+      cp_async_wait_group<DIST>();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[it % NBUF]);
+    }
+    cp_async_wait_all();
+    if (T > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after_sync();
+      // accumulator row -> TMEM lane: M=128: row = lane; M=64: rows 16w..16w+15 live in lanes 32w..32w+15
+      const int row = m64 ? (warp * 16 + lane) : tid;
+      const bool valid = (m64 ? lane < 16 : true) && row < co_cnt;
+      const int co = co_base + row;
+      for (int t = 0; t < nunits; ++t) {
+        const int u = unit0 + t;
+        for (int c0 = 0; c0 < NU; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NU + c0), r);
+          tmem_ld_wait();
+          if (valid) {
+            const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
+            const int tap = fuse ? ky * K + u : u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(gw + ((long long)co * Cin + ci0 + j) * (K * K) + tap, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  } else if (warp - 4 < n_issuers) {
+    const int me = warp - 4;
+    const uint32_t idesc = umma_idesc_bf16(m64 ? 64 : 128, NU, 1, 1);
+    for (int it = 0; it < T; ++it) {
+      const int s = it % NBUF;
+      mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        // A = gy^T (MN-major): channel groups SBO = 128 px x 16 B apart, pixels 16 B apart, rows (8 px) LBO apart
+        const uint64_t a0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
+        // B = shifted x (MN-major): N groups (c8, and ky when fused) WH units apart, halo rows c8n*WH units apart
+        const uint64_t b0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * WH) * 16, WH * 16);
+        for (int t = me; t < nunits; t += 3) {
+          const int u = unit0 + t;
+          const int ky = fuse ? 0 : u / K, kx = fuse ? u : u - ky * K;
+          const uint32_t dcol = tmem_base + (uint32_t)(t * NU);
+          const uint64_t bt = b0 + (uint64_t)(ky * c8n * WH + kx);
+#pragma unroll
+          for (int r = 0; r < TC_TH / 2; ++r)
+            umma_bf16(dcol, a0 + (uint64_t)(2 * r * TC_TW), bt + (uint64_t)(2 * r * c8n * WH), idesc,
+                      (it == 0 && r == 0) ? 0u : 1u);
+        }
+        umma_commit(&empty[s]);
+        if (it == T - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+template <int K, int NBUF>
+static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int up,
+                           int upg, int fuse, int cols, int g_bytes, int smem, dim3 grid, cudaStream_t st) {
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_ws_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  conv_wgrad_tc_ws_kernel<K, NBUF><<<grid, 224, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
+                                                           fuse, cols, g_bytes);
+  TTG_CHECK_LAUNCH("conv2d_wgrad_tc_ws");
+  return TTG_OK;
+}
+
 static int g_wgrad_tc_smem[2] = {0, 0};
 
 extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int, int, int) { return 16; }
@@ -655,6 +822,41 @@ extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int
   const int cols = (int)tmem_cols_for(tpg * Cin);
   if (per_sm > 512 / cols) per_sm = 512 / cols;
   if (per_sm < 1) per_sm = 1;
+  {
+    // persistent warp-specialised variant when at least two (x, gy) slots fit in shared memory
+    const int fuse = (ksize == 3 && 3 * Cin <= 256) ? 1 : 0;
+    const int units_total = fuse ? 3 : taps;
+    const int NU = fuse ? 3 * Cin : Cin;
+    int upg = 512 / NU;
+    if (upg > units_total) upg = units_total;
+    const int wgroups = (units_total + upg - 1) / upg;
+    upg = (units_total + wgroups - 1) / wgroups;                 // balance units over the groups
+    const int wcols = (int)tmem_cols_for(upg * NU);
+    const int x_bytes = (Cin / 8) * HP * 16;
+    const int g_bytes = ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
+    const int reach = (Cout <= 64 ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
+    int nbuf = (200 * 1024 - reach) / (x_bytes + g_bytes);
+    if (nbuf > 4) nbuf = 4;
+    if (nbuf >= 2) {
+      int wper_sm = 512 / wcols;
+      int body = nbuf * (x_bytes + g_bytes);
+      const int need = (nbuf - 1) * g_bytes + reach;
+      if (body < need) body = need;
+      const int wsmem = body + 256;
+      if (wper_sm > (220 * 1024) / wsmem) wper_sm = (220 * 1024) / wsmem;
+      if (wper_sm > 4) wper_sm = 4;
+      if (wper_sm < 1) wper_sm = 1;
+      long long wsplits = (long long)ttg_num_sms() * wper_sm / (wgroups * halves);
+      if (wsplits < 1) wsplits = 1;
+      if (wsplits > tiles) wsplits = tiles;
+      cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+      dim3 wgrid((unsigned)wsplits, wgroups, halves);
+#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gw, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, st)
+      if (ksize == 3) return nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
+      return nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
+#undef TTG_WG
+    }
+  }
   long long splits = (long long)ttg_num_sms() * per_sm / (groups * halves);
   if (splits < 1) splits = 1;
   if (splits > tiles) splits = tiles;
