@@ -58,6 +58,15 @@ int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int
 int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
                       int Cout, int ksize, int up, int dtype_out, const float* pre_scale, const float* pre_shift,
                       float slope, void* stream);
+/* channel-padded variants: Cin/Cout are the padded GEMM sizes (16), cin_real/cout_real the channel counts in memory
+ * (RGB layers: Cin == 3 first D conv discriminator.py:63, Cout == 3 image gradient / generator.py:124) */
+int ttg_pack_weight_tc_pad(const float* w, void* wp, int Cout, int Cin, int CoutP, int CinP, int ksize, int mode,
+                           void* stream);
+int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                     int cin_real, int cout_real, int ksize, int up, int dtype_out, const float* pre_scale,
+                     const float* pre_shift, float slope, void* stream);
+int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                           int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
                         int up, void* workspace, void* stream);
 size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);

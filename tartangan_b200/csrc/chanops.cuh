@@ -6,9 +6,10 @@
 #include "common.cuh"
 
 // Op concept for reductions:
-//   static constexpr int NIN, NACC;
-//   const T* in[NIN];
-//   __device__ void acc(const float* v /*NIN*/, int c, float* a /*NACC*/) const;
+//   static constexpr int NIN, NACC;   const T* in[NIN];
+//   template <int V> struct P { ... };                       per-thread cache of per-channel parameters
+//   template <int V> __device__ void load(int c0, P<V>&) const;   (channels c0..c0+V-1, loaded ONCE per thread)
+//   template <int V> __device__ void acc(const float* v /*NIN*/, int j, const P<V>&, float* a /*NACC*/) const;
 template <typename T, int V, class Op>
 __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, int C, double* __restrict__ out) {
   extern __shared__ float s_acc[];   // [NACC][C]
@@ -23,8 +24,38 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
 #pragma unroll
     for (int j = 0; j < V; ++j) a[k][j] = 0.f;
   if (rsub < rpi) {
-    for (long long r = (long long)blockIdx.x * rpi + rsub; r < M; r += (long long)gridDim.x * rpi) {
-      const long long base = r * C + (long long)g * V;
+    typename Op::template P<V> prm;
+    op.template load<V>(g * V, prm);
+    constexpr int U = 2;                           // rows in flight per thread
+    const long long rstep = (long long)gridDim.x * rpi;
+    long long r0 = (long long)blockIdx.x * rpi + rsub;
+    for (; r0 + (U - 1) * rstep < M; r0 += U * rstep) {
+      float v[U][Op::NIN][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long base = (r0 + u * rstep) * C + (long long)g * V;
+#pragma unroll
+        for (int t = 0; t < Op::NIN; ++t) {
+          if constexpr (V == 1) v[u][t][0] = to_f(op.in[t][base]);
+          else { Vec<T> q; q.load(op.in[t] + base); q.unpack(v[u][t]); }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float vin[Op::NIN], acc[Op::NACC];
+#pragma unroll
+          for (int t = 0; t < Op::NIN; ++t) vin[t] = v[u][t][j];
+#pragma unroll
+          for (int k = 0; k < Op::NACC; ++k) acc[k] = a[k][j];
+          op.template acc<V>(vin, j, prm, acc);
+#pragma unroll
+          for (int k = 0; k < Op::NACC; ++k) a[k][j] = acc[k];
+        }
+    }
+    for (; r0 < M; r0 += rstep) {
+      const long long base = r0 * C + (long long)g * V;
       float v[Op::NIN][V];
 #pragma unroll
       for (int t = 0; t < Op::NIN; ++t) {
@@ -38,11 +69,26 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
         for (int t = 0; t < Op::NIN; ++t) vin[t] = v[t][j];
 #pragma unroll
         for (int k = 0; k < Op::NACC; ++k) acc[k] = a[k][j];
-        op.acc(vin, g * V + j, acc);
+        op.template acc<V>(vin, j, prm, acc);
 #pragma unroll
         for (int k = 0; k < Op::NACC; ++k) a[k][j] = acc[k];
       }
     }
+  }
+  // block reduction: lanes that own the same channel group are first combined with warp shuffles
+  // (power-of-two group counts), then one shared-memory atomic per (warp, channel)
+  const bool pow2 = (groups & (groups - 1)) == 0 && groups <= 32;
+  if (pow2) {
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float t = a[k][j];
+        for (int o = 16; o >= groups; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        a[k][j] = t;
+      }
+  }
+  if (rsub < rpi && (!pow2 || (threadIdx.x & 31) < groups)) {
 #pragma unroll
     for (int k = 0; k < Op::NACC; ++k)
 #pragma unroll
@@ -69,7 +115,7 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN) && C / Vec<T>::N <= 256) {
     constexpr int V = Vec<T>::N;
     int rpi = 256 / (C / V);
-    int grid = ttg_grid_for(M, rpi * 8, 4);
+    int grid = ttg_grid_for(M, rpi * 4, 8);
     chan_reduce_kernel<T, V, Op><<<grid, 256, smem, st>>>(op, M, C, out);
   } else {
     if (C > 256) return ttg_set_error(TTG_ERR_UNSUPPORTED, "%s: C=%d needs C%%%d==0 and 16B alignment", name, C, Vec<T>::N);
@@ -83,32 +129,51 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
 
 // Op concept for maps:
 //   static constexpr int NIN, NOUT;  const T* in[NIN];  T* out[NOUT];
-//   __device__ void apply(const float* v, int c, float* o) const;
+//   template <int V> struct P;  load<V>(c0, P&);  apply<V>(const float* v, int j, const P<V>&, float* o)
+// When the grid stride keeps every thread on the same channel group (`invariant`), the per-channel
+// parameters are loaded once per thread instead of once per element.
 template <typename T, int V, class Op>
-__global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, int C) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long base = i * V;
-    const int c0 = (int)(base % C);
-    float v[Op::NIN][V], o[Op::NOUT][V];
+__global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, int C, int invariant) {
+  constexpr int U = 2;                             // vectors in flight per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  typename Op::template P<V> prm;
+  if (invariant && i0 < nvec) op.template load<V>((int)((i0 * V) % C), prm);
+  for (; i0 < nvec; i0 += U * stride) {
+    float v[U][Op::NIN][V];
 #pragma unroll
-    for (int t = 0; t < Op::NIN; ++t) {
-      if constexpr (V == 1) v[t][0] = to_f(op.in[t][base]);
-      else { Vec<T> q; q.load(op.in[t] + base); q.unpack(v[t]); }
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+#pragma unroll
+        for (int t = 0; t < Op::NIN; ++t) {
+          if constexpr (V == 1) v[u][t][0] = to_f(op.in[t][i]);
+          else { Vec<T> q; q.load(op.in[t] + i * V); q.unpack(v[u][t]); }
+        }
+      }
     }
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      float vin[Op::NIN], vout[Op::NOUT];
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec) {
+        const long long base = i * V;
+        if (!invariant) op.template load<V>((int)(base % C), prm);
+        float o[Op::NOUT][V];
 #pragma unroll
-      for (int t = 0; t < Op::NIN; ++t) vin[t] = v[t][j];
-      op.apply(vin, c0 + j, vout);
+        for (int j = 0; j < V; ++j) {
+          float vin[Op::NIN], vout[Op::NOUT];
 #pragma unroll
-      for (int t = 0; t < Op::NOUT; ++t) o[t][j] = vout[t];
-    }
+          for (int t = 0; t < Op::NIN; ++t) vin[t] = v[u][t][j];
+          op.template apply<V>(vin, j, prm, vout);
 #pragma unroll
-    for (int t = 0; t < Op::NOUT; ++t) {
-      if constexpr (V == 1) op.out[t][base] = from_f<T>(o[t][0]);
-      else { Vec<T> q; q.pack(o[t]); q.store(op.out[t] + base); }
+          for (int t = 0; t < Op::NOUT; ++t) o[t][j] = vout[t];
+        }
+#pragma unroll
+        for (int t = 0; t < Op::NOUT; ++t) {
+          if constexpr (V == 1) op.out[t][base] = from_f<T>(o[t][0]);
+          else { Vec<T> q; q.pack(o[t]); q.store(op.out[t] + base); }
+        }
+      }
     }
   }
 }
@@ -122,9 +187,13 @@ static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStre
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN + Op::NOUT)) {
     constexpr int V = Vec<T>::N;
     long long nvec = n / V;
-    chan_map_kernel<T, V, Op><<<ttg_grid_for(nvec, 256 * 2), 256, 0, st>>>(op, nvec, C);
+    int grid = ttg_grid_for(nvec, 256 * 2);
+    int inv = ((long long)grid * 256 * V) % C == 0;
+    chan_map_kernel<T, V, Op><<<grid, 256, 0, st>>>(op, nvec, C, inv);
   } else {
-    chan_map_kernel<T, 1, Op><<<ttg_grid_for(n, 256 * 4), 256, 0, st>>>(op, n, C);
+    int grid = ttg_grid_for(n, 256 * 4);
+    int inv = ((long long)grid * 256) % C == 0;
+    chan_map_kernel<T, 1, Op><<<grid, 256, 0, st>>>(op, n, C, inv);
   }
   TTG_CHECK_LAUNCH(name);
   return TTG_OK;

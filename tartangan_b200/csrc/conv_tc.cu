@@ -126,6 +126,56 @@ __device__ __forceinline__ void stage_tile(uint8_t* sA, const bf16* __restrict__
   }
 }
 
+// Channel-padded variants for the RGB layers (Cin == 3 first D conv, Cout == 3 image gradients / last G conv):
+// the tensors in HBM keep their real channel count, the shared-memory / weight images are padded to 16 with
+// zeros, so these layers run on the same tensor-core kernels.
+__global__ void pack_weight_tc_pad_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Cout, int Cin, int CoutP,
+                                          int CinP, int k, int mode) {
+  int total = Cout * Cin * k * k;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int kx = i % k, ky = (i / k) % k, ci = (i / (k * k)) % Cin, co = i / (k * k * Cin);
+    bf16 v = __float2bfloat16_rn(w[i]);
+    if (mode == 0) {
+      int tap = ky * k + kx;
+      wp[(((long long)tap * (CinP / 8) + ci / 8) * CoutP + co) * 8 + (ci % 8)] = v;
+    } else {
+      int tap = (k - 1 - ky) * k + (k - 1 - kx);
+      wp[(((long long)tap * (CoutP / 8) + co / 8) * CinP + ci) * 8 + (co % 8)] = v;
+    }
+  }
+}
+extern "C" int ttg_pack_weight_tc_pad(const float* w, void* wp, int Cout, int Cin, int CoutP, int CinP, int ksize, int mode,
+                                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(CoutP % 16 == 0 && CinP % 16 == 0 && Cout <= CoutP && Cin <= CinP, "pack_weight_tc_pad: bad padding");
+  cudaMemsetAsync(wp, 0, (size_t)CoutP * CinP * ksize * ksize * 2, st);
+  int total = Cout * Cin * ksize * ksize;
+  pack_weight_tc_pad_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(w, (bf16*)wp, Cout, Cin, CoutP, CinP, ksize, mode);
+  TTG_CHECK_LAUNCH("pack_weight_tc_pad");
+  return TTG_OK;
+}
+
+// stage a tile of a tensor with c_real (<= 8) channels into the C-channel (padded) shared-memory image
+template <int HALO>
+__device__ __forceinline__ void stage_tile_pad(uint8_t* sA, const bf16* __restrict__ x, int n, int y0, int x0, int H, int W,
+                                               int C, int c_real, int up, int nthr) {
+  constexpr int WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  const int c8n = C >> 3, Hi = H >> up, Wi = W >> up;
+  for (int pix = threadIdx.x; pix < HP; pix += nthr) {
+    const int hy = pix / WH, hx = pix - hy * WH;
+    const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const unsigned short* src = reinterpret_cast<const unsigned short*>(x) +
+                                  (((long long)n * Hi + (gy >> up)) * Wi + (gx >> up)) * c_real;
+      for (int c = 0; c < c_real; ++c) w[c >> 1] |= (uint32_t)src[c] << (16 * (c & 1));
+    }
+    uint8_t* d = sA + (size_t)((hy * c8n) * WH + hx) * 16;
+    *reinterpret_cast<uint4*>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int c8 = 1; c8 < c8n; ++c8) *reinterpret_cast<uint4*>(d + (size_t)c8 * WH * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // Fast staging for the persistent kernel (units per halo row <= 128): every thread owns one fixed
 // (column, channel-group) position of the halo row and walks down the rows, so all div/mod work is
 // done once per kernel and a 16-byte unit costs ~10 instructions instead of ~70.
@@ -296,7 +346,24 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const bf16* __restrict__ x
 // cp.async loads of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 template <int HALO>
 __device__ __forceinline__ void conv_tc_epilogue(uint32_t tacc, int warp, int tid, int n, int y0, int x0, int H, int W,
-                                                 int Cout, const float* __restrict__ bias, void* __restrict__ y, int out_f32) {
+                                                 int Cout, const float* __restrict__ bias, void* __restrict__ y, int out_f32,
+                                                 int cout_real = 0) {
+  if (cout_real && cout_real != Cout) {           // padded output channels: scalar stores of the real ones
+    const int gy = y0 + (tid >> 3), gx = x0 + (tid & 7);
+    const bool valid = gy < H && gx < W;
+    const long long opix = ((long long)n * H + gy) * W + gx;
+    uint32_t r[16];
+    tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16), r);
+    tmem_ld_wait();
+    if (valid) {
+      for (int j = 0; j < cout_real; ++j) {
+        const float f = __uint_as_float(r[j]) + (bias ? bias[j] : 0.f);
+        if (out_f32) reinterpret_cast<float*>(y)[opix * cout_real + j] = f;
+        else reinterpret_cast<bf16*>(y)[opix * cout_real + j] = __float2bfloat16_rn(f);
+      }
+    }
+    return;
+  }
   const int gy = y0 + (tid >> 3), gx = x0 + (tid & 7);
   const bool valid = gy < H && gx < W;
   const long long opix = ((long long)n * H + gy) * W + gx;
@@ -341,7 +408,7 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
                                                               int out_f32, int H, int W, int Cin, int Cout, int up,
                                                               const float* __restrict__ pre_scale,
                                                               const float* __restrict__ pre_shift, float slope,
-                                                              int total_tiles, int tmem_cols) {
+                                                              int total_tiles, int tmem_cols, int cin_real, int cout_real) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   // DIST tiles are prefetched ahead; NBUF - DIST >= 2 leaves a slot of slack so that re-using a slot never
   // waits on MMAs issued in the previous iteration.  The epilogue runs LAG tiles behind over 4 accumulators.
@@ -397,7 +464,9 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
         int n, y0, x0;
         tile_coords(j, n, y0, x0);
         uint8_t* dst = sA + (size_t)s * a_bytes;
-        if (fast_stage) {
+        if (cin_real != Cin) {
+          stage_tile_pad<HALO>(dst, x, n, y0, x0, H, W, Cin, cin_real, up, 128);
+        } else if (fast_stage) {
           if (pre_scale) stage_rows<HALO, false>(rs, dst, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope);
           else stage_rows<HALO, true>(rs, dst, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
         } else {
@@ -413,7 +482,7 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
       tile_coords(j, n, y0, x0);
       mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
       tc_fence_after_sync();
-      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
+      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32, cout_real);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
     };
@@ -463,7 +532,7 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
 template <int K, int NBUF>
 static int launch_conv_tc_persist(const void* x, const void* wp, const float* bias, void* y, int out_f32, int H, int W,
                                   int Cin, int Cout, int up, const float* pre_scale, const float* pre_shift, float slope,
-                                  long long tiles, int psmem, int pcols, int per_sm, cudaStream_t st) {
+                                  long long tiles, int psmem, int pcols, int per_sm, int cin_real, int cout_real, cudaStream_t st) {
   static int smem_set = 0;
   if (psmem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
@@ -473,7 +542,7 @@ static int launch_conv_tc_persist(const void* x, const void* wp, const float* bi
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
   conv_tc_persist_kernel<K, NBUF><<<(unsigned)grid, 160, psmem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
-                                                                     Cout, up, pre_scale, pre_shift, slope, (int)tiles, pcols);
+                                                                     Cout, up, pre_scale, pre_shift, slope, (int)tiles, pcols, cin_real, cout_real);
   TTG_CHECK_LAUNCH("conv2d_tc_persist");
   return TTG_OK;
 }
@@ -482,17 +551,24 @@ static int launch_conv_tc_persist(const void* x, const void* wp, const float* bi
 
 static int g_conv_tc_smem[2] = {0, 0};
 
-extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
-                                 int Cout, int ksize, int up, int dtype_out, const float* pre_scale,
-                                 const float* pre_shift, float slope, void* stream) {
+// Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
+// tensors in memory (equal to Cin / Cout except for the RGB layers).
+extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                                int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
+                                const float* pre_scale, const float* pre_shift, float slope, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const bool padded = cin_real != Cin || cout_real != Cout;
+  TTG_REQUIRE(cin_real >= 1 && cin_real <= Cin && cout_real >= 1 && cout_real <= Cout, "conv2d_tc: bad real channel counts");
+  TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || (cout_real <= 16 && Cout == 16)) && !pre_scale),
+              "conv2d_tc: channel padding supports <= 8 real input channels / Cout padded to 16, without prologue");
   TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize %d unsupported", ksize);
   TTG_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16 && Cin <= 256 && Cout <= 256,
               "conv2d_tc: channels must be multiples of 16 in [16,256] (got %d -> %d)", Cin, Cout);
   TTG_REQUIRE(up == 0 || (H % 2 == 0 && W % 2 == 0), "conv2d_tc: upsample needs even output size");
   TTG_REQUIRE(dtype_out == TTG_BF16 || dtype_out == TTG_F32, "conv2d_tc: bad output dtype");
-  TTG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(wp) & 15) == 0, "conv2d_tc: pointers must be 16-byte aligned");
+  TTG_REQUIRE(padded || ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0),
+              "conv2d_tc: activation pointers must be 16-byte aligned");
+  TTG_REQUIRE((reinterpret_cast<uintptr_t>(wp) & 15) == 0, "conv2d_tc: weight pointer must be 16-byte aligned");
   const int halo = ksize / 2;
   const int HP = (TC_TW + 2 * halo) * (TC_TH + 2 * halo);
   const int total_slices = ksize * ksize * (Cin / 16);
@@ -505,6 +581,7 @@ extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bia
   const long long tiles = (long long)N * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
   TTG_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv2d_tc: bad problem size");
   const int w_bytes = total_slices * slice_bytes;
+  TTG_REQUIRE(!padded || w_bytes <= TC_RESIDENT_W_BYTES, "conv2d_tc: padded layers must fit the resident-filter kernel");
   if (w_bytes <= TC_RESIDENT_W_BYTES) {
     const int a_bytes = (Cin / 8) * HP * 16;
     const int nbuf = a_bytes <= 12 * 1024 ? 4 : (a_bytes <= 24 * 1024 ? 3 : 2);
@@ -516,7 +593,7 @@ extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bia
     if (per_sm < 1) per_sm = 1;
     const int of32 = dtype_out == TTG_F32;
 #define TTG_PERSIST(KK, NB) launch_conv_tc_persist<KK, NB>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, pre_shift, \
-                                                        slope, tiles, psmem, pcols, per_sm, st)
+                                                        slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st)
     if (ksize == 3) return nbuf == 4 ? TTG_PERSIST(3, 4) : nbuf == 3 ? TTG_PERSIST(3, 3) : TTG_PERSIST(3, 2);
     return nbuf == 4 ? TTG_PERSIST(1, 4) : nbuf == 3 ? TTG_PERSIST(1, 3) : TTG_PERSIST(1, 2);
 #undef TTG_PERSIST
@@ -540,9 +617,14 @@ extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bia
   return TTG_OK;
 }
 
+extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                                 int Cout, int ksize, int up, int dtype_out, const float* pre_scale,
+                                 const float* pre_shift, float slope, void* stream) {
+  return ttg_conv2d_tc_ex(x, wp, bias, y, N, H, W, Cin, Cout, Cin, Cout, ksize, up, dtype_out, pre_scale, pre_shift, slope, stream);
+}
 extern "C" int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
                              int Cout, int ksize, int up, int dtype_out, void* stream) {
-  return ttg_conv2d_tc_pre(x, wp, bias, y, N, H, W, Cin, Cout, ksize, up, dtype_out, nullptr, nullptr, 1.f, stream);
+  return ttg_conv2d_tc_ex(x, wp, bias, y, N, H, W, Cin, Cout, Cin, Cout, ksize, up, dtype_out, nullptr, nullptr, 1.f, stream);
 }
 
 // ------------------------------------------------------------------ wgrad
@@ -648,7 +730,7 @@ template <int K, int NBUF>
 __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy,
                                                                float* __restrict__ gw, int N, int H, int W, int Cin,
                                                                int Cout, int up, int units_per_group, int fuse,
-                                                               int tmem_cols, int g_bytes) {
+                                                               int tmem_cols, int g_bytes, int cin_real, int cout_real) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH, NPIX = TC_TH * TC_TW;
   constexpr int DIST = NBUF > 2 ? NBUF - 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -705,9 +787,23 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
         int n, y0, x0;
         tile_coords(j, n, y0, x0);
         uint8_t* dx = sX + (size_t)s * x_bytes;
-        if (fast_stage) stage_rows<HALO, true>(rs, dx, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+        if (cin_real != Cin) stage_tile_pad<HALO>(dx, x, n, y0, x0, H, W, Cin, cin_real, up, 128);
+        else if (fast_stage) stage_rows<HALO, true>(rs, dx, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
         else stage_tile_async<HALO>(dx, x, n, y0, x0, H, W, Cin, up, 128);
         const uint32_t dg = smem_u32(sG + (size_t)s * g_bytes);
+        if (cout_real != Cout) {                      // padded gy (<= 8 real channels): scalar loads
+          for (int pix = tid; pix < NPIX; pix += 128) {
+            const int py = y0 + (pix >> 3), px = x0 + (pix & 7);
+            uint32_t w4[4] = {0u, 0u, 0u, 0u};
+            if (py < H && px < W) {
+              const unsigned short* src = reinterpret_cast<const unsigned short*>(gy) + (((long long)n * H + py) * W + px) * cout_real;
+              for (int c = 0; c < cout_real; ++c) w4[c >> 1] |= (uint32_t)src[c] << (16 * (c & 1));
+            }
+            uint8_t* d = sG + (size_t)s * g_bytes + (size_t)pix * 16;
+            *reinterpret_cast<uint4*>(d) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            for (int g8 = 1; g8 < g8n; ++g8) *reinterpret_cast<uint4*>(d + (size_t)g8 * NPIX * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else
         for (int u = tid; u < NPIX * g8n; u += 128) {
           const int g8 = u % g8n, pix = u / g8n;
           const int py = y0 + (pix >> 3), px = x0 + (pix & 7);
@@ -743,8 +839,11 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
           if (valid) {
             const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
             const int tap = fuse ? ky * K + u : u;
+            if (co < cout_real) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(gw + ((long long)co * Cin + ci0 + j) * (K * K) + tap, __uint_as_float(r[j]));
+              for (int j = 0; j < 16; ++j)
+                if (ci0 + j < cin_real) atomicAdd(gw + ((long long)co * cin_real + ci0 + j) * (K * K) + tap, __uint_as_float(r[j]));
+            }
           }
         }
       }
@@ -784,7 +883,8 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
 
 template <int K, int NBUF>
 static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int up,
-                           int upg, int fuse, int cols, int g_bytes, int smem, dim3 grid, cudaStream_t st) {
+                           int upg, int fuse, int cols, int g_bytes, int smem, dim3 grid, int cin_real, int cout_real,
+                           cudaStream_t st) {
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_ws_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -792,7 +892,7 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
     smem_set = smem;
   }
   conv_wgrad_tc_ws_kernel<K, NBUF><<<grid, 224, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
-                                                           fuse, cols, g_bytes);
+                                                           fuse, cols, g_bytes, cin_real, cout_real);
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc_ws");
   return TTG_OK;
 }
@@ -801,10 +901,19 @@ static int g_wgrad_tc_smem[2] = {0, 0};
 
 extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int, int, int) { return 16; }
 
+extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                                      int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
 extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                    int ksize, int up, void* workspace, void* stream) {
+  return ttg_conv2d_wgrad_tc_ex(x, gy, gw, N, H, W, Cin, Cout, Cin, Cout, ksize, up, workspace, stream);
+}
+extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                                      int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
   (void)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool padded = cin_real != Cin || cout_real != Cout;
+  TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || cout_real <= 8)),
+              "conv2d_wgrad_tc: channel padding supports <= 8 real channels");
   TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad_tc: ksize %d unsupported", ksize);
   TTG_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0 && Cin >= 16 && Cout >= 16 && Cin <= 256 && Cout <= 256,
               "conv2d_wgrad_tc: channels must be multiples of 16 in [16,256] (got %d -> %d)", Cin, Cout);
@@ -849,14 +958,15 @@ extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int
       long long wsplits = (long long)ttg_num_sms() * wper_sm / (wgroups * halves);
       if (wsplits < 1) wsplits = 1;
       if (wsplits > tiles) wsplits = tiles;
-      cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+      cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st);
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
-#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gw, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, st)
+#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gw, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, st)
       if (ksize == 3) return nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
       return nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
 #undef TTG_WG
     }
   }
+  TTG_REQUIRE(!padded, "conv2d_wgrad_tc: padded layers must fit the persistent kernel");
   long long splits = (long long)ttg_num_sms() * per_sm / (groups * halves);
   if (splits < 1) splits = 1;
   if (splits > tiles) splits = tiles;

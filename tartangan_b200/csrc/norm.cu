@@ -9,10 +9,12 @@
 #include "chanops.cuh"
 
 // ---------------------------------------------------------------- statistics
-template <typename T> struct StatsOp {
+struct NoParams { template <int V> struct P {}; template <int V> __device__ __forceinline__ void load(int, P<V>&) const {} };
+
+template <typename T> struct StatsOp : NoParams {
   static constexpr int NIN = 1, NACC = 2;
   const T* in[1];
-  __device__ __forceinline__ void acc(const float* v, int, float* a) const { a[0] += v[0]; a[1] += v[0] * v[0]; }
+  template <int V> __device__ __forceinline__ void acc(const float* v, int, const P<V>&, float* a) const { a[0] += v[0]; a[1] += v[0] * v[0]; }
 };
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, float eps, float momentum,
@@ -71,9 +73,13 @@ template <typename T> struct BnActFwdOp {
   static constexpr int NIN = 1, NOUT = 1;
   const T* in[1]; T* out[1];
   const float *mean, *invstd, *gamma, *beta; float slope;
-  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
-    float y = (v[0] - mean[c]) * invstd[c] * gamma[c] + beta[c];
-    o[0] = lrelu(y, slope);
+  template <int V> struct P { float a[V], b[V]; };     // y = x*a + b
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
+#pragma unroll
+    for (int j = 0; j < V; ++j) { float a = invstd[c0 + j] * gamma[c0 + j]; p.a[j] = a; p.b[j] = beta[c0 + j] - mean[c0 + j] * a; }
+  }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int j, const P<V>& p, float* o) const {
+    o[0] = lrelu(v[0] * p.a[j] + p.b[j], slope);
   }
 };
 
@@ -89,13 +95,24 @@ extern "C" int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const 
 
 // ---------------------------------------------------------------- backward
 // d = ga * lrelu'(y);  gx = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
+// per-channel cache shared by the backward ops: xhat = x*r - mr,  y = g*xhat + b
+template <int V> struct BnChan { float r[V], mr[V], g[V], b[V]; };
+template <int V> __device__ __forceinline__ void bn_chan_load(int c0, BnChan<V>& p, const float* mean, const float* invstd,
+                                                              const float* gamma, const float* beta) {
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    p.r[j] = invstd[c0 + j]; p.mr[j] = mean[c0 + j] * invstd[c0 + j]; p.g[j] = gamma[c0 + j]; p.b[j] = beta[c0 + j];
+  }
+}
 template <typename T> struct BnActBwdRedOp {
   static constexpr int NIN = 2, NACC = 2;
   const T* in[2];   // x, ga
   const float *mean, *invstd, *gamma, *beta; float slope;
-  __device__ __forceinline__ void acc(const float* v, int c, float* a) const {
-    float xh = (v[0] - mean[c]) * invstd[c];
-    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
+  template <int V> using P = BnChan<V>;
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const { bn_chan_load<V>(c0, p, mean, invstd, gamma, beta); }
+  template <int V> __device__ __forceinline__ void acc(const float* v, int j, const P<V>& p, float* a) const {
+    float xh = v[0] * p.r[j] - p.mr[j];
+    float d = v[1] * lrelu_mask(xh * p.g[j] + p.b[j], slope);
     a[0] += d; a[1] += d * xh;
   }
 };
@@ -103,11 +120,16 @@ template <typename T> struct BnActBwdMapOp {
   static constexpr int NIN = 2, NOUT = 1;
   const T* in[2]; T* out[1];
   const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
-  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
-    float xh = (v[0] - mean[c]) * invstd[c];
-    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
-    float db = (float)sums[c] * invM, cc = (float)sums[C + c] * invM;
-    o[0] = gamma[c] * invstd[c] * (d - db - xh * cc);
+  template <int V> struct P { BnChan<V> c; float db[V], cc[V]; };
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
+    bn_chan_load<V>(c0, p.c, mean, invstd, gamma, beta);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { p.db[j] = (float)sums[c0 + j] * invM; p.cc[j] = (float)sums[C + c0 + j] * invM; }
+  }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int j, const P<V>& p, float* o) const {
+    float xh = v[0] * p.c.r[j] - p.c.mr[j];
+    float d = v[1] * lrelu_mask(xh * p.c.g[j] + p.c.b[j], slope);
+    o[0] = p.c.g[j] * p.c.r[j] * (d - p.db[j] - xh * p.cc[j]);
   }
 };
 __global__ void bn_param_grads_kernel(const double* sums, int C, float* ggamma, float* gbeta) {
@@ -151,9 +173,11 @@ template <typename T> struct BnActBwd2RedOp {
   static constexpr int NIN = 3, NACC = 5;
   const T* in[3];   // x, ga, u
   const float *mean, *invstd, *gamma, *beta; float slope;
-  __device__ __forceinline__ void acc(const float* v, int c, float* a) const {
-    float xh = (v[0] - mean[c]) * invstd[c];
-    float d = v[1] * lrelu_mask(xh * gamma[c] + beta[c], slope);
+  template <int V> using P = BnChan<V>;
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const { bn_chan_load<V>(c0, p, mean, invstd, gamma, beta); }
+  template <int V> __device__ __forceinline__ void acc(const float* v, int j, const P<V>& p, float* a) const {
+    float xh = v[0] * p.r[j] - p.mr[j];
+    float d = v[1] * lrelu_mask(xh * p.g[j] + p.b[j], slope);
     float u = v[2];
     a[0] += d; a[1] += d * xh; a[2] += u; a[3] += u * xh; a[4] += u * d;
   }
@@ -162,17 +186,25 @@ template <typename T> struct BnActBwd2MapOp {
   static constexpr int NIN = 3, NOUT = 2;
   const T* in[3]; T* out[2];   // out: g_ga, g_x
   const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
-  __device__ __forceinline__ void apply(const float* v, int c, float* o) const {
-    float r = invstd[c], g = gamma[c];
-    float xh = (v[0] - mean[c]) * r;
-    float m = lrelu_mask(xh * g + beta[c], slope);
+  template <int V> struct P { BnChan<V> c; float db[V], cc[V], ub[V], e[V], k[V]; };   // k = cc*e - cov
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
+    bn_chan_load<V>(c0, p.c, mean, invstd, gamma, beta);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float db = (float)sums[c0 + j] * invM, cc = (float)sums[C + c0 + j] * invM;
+      float ub = (float)sums[2 * C + c0 + j] * invM, e = (float)sums[3 * C + c0 + j] * invM;
+      float cov = (float)sums[4 * C + c0 + j] * invM - ub * db;
+      p.db[j] = db; p.cc[j] = cc; p.ub[j] = ub; p.e[j] = e; p.k[j] = cc * e - cov;
+    }
+  }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int j, const P<V>& p, float* o) const {
+    float r = p.c.r[j], g = p.c.g[j];
+    float xh = v[0] * r - p.c.mr[j];
+    float m = lrelu_mask(xh * g + p.c.b[j], slope);
     float d = v[1] * m, u = v[2];
-    float db = (float)sums[c] * invM, cc = (float)sums[C + c] * invM;
-    float ub = (float)sums[2 * C + c] * invM, e = (float)sums[3 * C + c] * invM;
-    float cov = (float)sums[4 * C + c] * invM - ub * db;
-    float Pd = d - db - xh * cc, Pu = u - ub - xh * e;
+    float Pd = d - p.db[j] - xh * p.cc[j], Pu = u - p.ub[j] - xh * p.e[j];
     o[0] = m * g * r * Pu;
-    o[1] = g * r * r * (xh * (cc * e - cov) - e * Pd - cc * Pu);
+    o[1] = g * r * r * (xh * p.k[j] - p.e[j] * Pd - p.cc[j] * Pu);
   }
 };
 __global__ void bn_bwd2_gamma_kernel(const double* sums, const float* invstd, long long M, int C, float* ggamma) {
@@ -210,15 +242,15 @@ extern "C" int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, voi
 }
 
 // ---------------------------------------------------------------- plain LeakyReLU (--norm id)
-template <typename T> struct LreluOp {     // y = lrelu(x)
+template <typename T> struct LreluOp : NoParams {     // y = lrelu(x)
   static constexpr int NIN = 1, NOUT = 1;
   const T* in[1]; T* out[1]; float slope;
-  __device__ __forceinline__ void apply(const float* v, int, float* o) const { o[0] = lrelu(v[0], slope); }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int, const P<V>&, float* o) const { o[0] = lrelu(v[0], slope); }
 };
-template <typename T> struct LreluMaskMulOp {   // out = g * lrelu'(x)
+template <typename T> struct LreluMaskMulOp : NoParams {   // out = g * lrelu'(x)
   static constexpr int NIN = 2, NOUT = 1;
   const T* in[2]; T* out[1]; float slope;
-  __device__ __forceinline__ void apply(const float* v, int, float* o) const { o[0] = v[1] * lrelu_mask(v[0], slope); }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int, const P<V>&, float* o) const { o[0] = v[1] * lrelu_mask(v[0], slope); }
 };
 extern "C" int ttg_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, void* stream) {
   TTG_DISPATCH(dtype, {
@@ -236,10 +268,10 @@ extern "C" int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n
 }
 
 // ---------------------------------------------------------------- per-channel sum (conv bias gradient)
-template <typename T> struct SumOp {
+template <typename T> struct SumOp : NoParams {
   static constexpr int NIN = 1, NACC = 1;
   const T* in[1];
-  __device__ __forceinline__ void acc(const float* v, int, float* a) const { a[0] += v[0]; }
+  template <int V> __device__ __forceinline__ void acc(const float* v, int, const P<V>&, float* a) const { a[0] += v[0]; }
 };
 __global__ void d2f_kernel(const double* s, int n, float* o) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -150,15 +150,25 @@ def _packed(w, mode, kind):
         wp = torch.empty(k * k * cin * cout, dtype=torch.float32, device=w.device)
         call('ttg_pack_weight_direct', ptr(wd), ptr(wp), cout, cin, k, mode)
     else:
-        nbytes = _lib.lib.ttg_pack_weight_tc_bytes(cout, cin, k)
+        coutp, cinp = _pad16(cout), _pad16(cin)
+        nbytes = _lib.lib.ttg_pack_weight_tc_bytes(coutp, cinp, k)
         wp = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        call('ttg_pack_weight_tc', ptr(wd), ptr(wp), cout, cin, k, mode)
+        if (coutp, cinp) == (cout, cin):
+            call('ttg_pack_weight_tc', ptr(wd), ptr(wp), cout, cin, k, mode)
+        else:
+            call('ttg_pack_weight_tc_pad', ptr(wd), ptr(wp), cout, cin, coutp, cinp, k, mode)
     cache[(kind, mode)] = (ver, wp)
     return wp
 
 
+def _pad16(c):
+    """Channel counts <= 8 (the RGB layers) are zero-padded to 16 inside the tensor-core kernels."""
+    return 16 if c <= 8 else c
+
+
 def _tc_ok(dtype, cin, cout):
-    return state.use_tc and dtype == torch.bfloat16 and cin % 16 == 0 and cout % 16 == 0 and cin <= 256 and cout <= 256
+    ok = lambda c: c <= 8 or (c % 16 == 0 and c <= 256)
+    return state.use_tc and dtype == torch.bfloat16 and ok(cin) and ok(cout)
 
 
 def _conv_raw(x, w, bias, mode, up, out_dtype=None):
@@ -173,8 +183,8 @@ def _conv_raw(x, w, bias, mode, up, out_dtype=None):
     y = empty_nhwc(n, c_out_eff, h, wd_, out_dtype, x.device)
     if _tc_ok(x.dtype, cin, cout) and out_dtype in (torch.bfloat16, torch.float32):
         wp = _packed(w, mode, 'tc')
-        call('ttg_conv2d_tc', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, up,
-             dtype_code(out_dtype))
+        call('ttg_conv2d_tc_ex', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, _pad16(c_in_eff), _pad16(c_out_eff),
+             c_in_eff, c_out_eff, k, up, dtype_code(out_dtype), None, None, 1.0)
     else:
         wp = _packed(w, mode, 'direct')
         call('ttg_conv2d_direct', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, up,
@@ -243,7 +253,8 @@ class ConvWgradFn(Function):
         gw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
         if _tc_ok(x.dtype, cin, cout) and gy.dtype == torch.bfloat16:
             ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
-            call('ttg_conv2d_wgrad_tc', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up, ptr(ws))
+            call('ttg_conv2d_wgrad_tc_ex', ptr(x), ptr(gy), ptr(gw), n, h, w, _pad16(cin), _pad16(cout), cin, cout, k, up,
+                 ptr(ws))
         else:
             call('ttg_conv2d_wgrad_direct', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up,
                  dtype_code(x.dtype), dtype_code(gy.dtype))
