@@ -128,6 +128,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH, help='per-GPU batch (default: the BASELINE workload)')
     ap.add_argument('--precision', default='bf16')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='disable CUDA-graph execution of the step')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel event timing table here (JSON)')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -147,7 +148,8 @@ def main():
     from tartangan_b200.trainers.trainer import tartan_batch
 
     torch.manual_seed(0)                     # model init: same on every rank
-    trainer = make_trainer(IQNTrainer, config=CONFIG, batch_size=args.batch, precision=args.precision)
+    trainer = make_trainer(IQNTrainer, config=CONFIG, batch_size=args.batch, precision=args.precision,
+                           cuda_graph=not args.eager)
     torch.manual_seed(1000 + rank)           # z / tau stream
     base = tartan_batch(1234 + rank, 32, SIZE)
     host = base.repeat((args.batch + 31) // 32, 1, 1, 1)[:args.batch].contiguous().pin_memory()
@@ -167,8 +169,10 @@ def main():
     k0 = _lib.Counters.kernels
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         trainer.train_batch(dev, as_floats=False)
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # CPU time to enqueue one step
     e1.record()
     barrier()
     launches = _lib.Counters.kernels - k0
@@ -187,6 +191,8 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
     # ---- per-kernel device timing of one more step (CUDA events on the launching stream)
+    trainer.args.cuda_graph = False          # the per-kernel breakdown needs eager launches
+    trainer.train_batch(dev, as_floats=False)
     with KernelProfiler() as prof:
         trainer.train_batch(dev, as_floats=False)
     rows, by_name = prof.summary(), prof.by_name()
@@ -221,7 +227,7 @@ def main():
             'e2e': {'value': e2e_val, 'unit': 'images/sec', 'h2d_bytes_per_step':
                     (host.numel() * 4 + 2 * args.batch * 256 * 4 + 3 * args.batch * 8 * 4) * world,
                     'd2h_bytes_per_step': 12 * world},
-            'gpu_launches': launches,
+            'gpu_launches': launches, 'host_issue_ms_per_step': host_issue_ms,
             'clocks': sampler.result(),
             'roofline': roof,
         }

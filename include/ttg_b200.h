@@ -77,8 +77,8 @@ size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);
  * workspace: ttg_bn_workspace_bytes(C) bytes. */
 size_t ttg_bn_workspace_bytes(int C);
 int ttg_bn_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* invstd,
-                 float* running_mean, float* running_var, long long* num_batches, void* workspace, int dtype,
-                 void* stream);
+                 float* running_mean, float* running_var, long long* num_batches, void* workspace,
+                 long long count_mult, int dtype, void* stream);
 int ttg_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
                       float* invstd, void* stream);
 int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const float* mean, const float* invstd,
@@ -107,6 +107,9 @@ int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float sc
 int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream);
 int ttg_bilinear_down_fwd(const void* x, void* y, int N, int Hi, int Wi, int C, int dtype, void* stream);
 int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream);
+/* fused residual joins: h + nearest_up2(skip) (generator.py:58-62) and avg_pool2(h) + skip (discriminator.py:67,95) */
+int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, int dtype, void* stream);
+int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream);
 int ttg_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int dtype, void* stream);
 int ttg_scale_f32(const float* x, float* out, long long n, float host_scale, const float* dev_scale, void* stream);
 int ttg_spatial_sum(const void* x, float* out, int N, int HW, int C, int dtype, void* stream);

@@ -17,7 +17,7 @@ template <typename T> struct StatsOp : NoParams {
   template <int V> __device__ __forceinline__ void acc(const float* v, int, const P<V>&, float* a) const { a[0] += v[0]; a[1] += v[0] * v[0]; }
 };
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, float eps, float momentum,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, long long count_mult, int C, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches) {
@@ -29,7 +29,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M,
     mean[c] = (float)m;
     invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean) {
-      double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+      const double Mu = (double)M * (double)count_mult;     // element count the reference op would have seen
+      double unbiased = Mu > 1 ? var * Mu / (Mu - 1.0) : var;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
     }
@@ -41,16 +42,16 @@ extern "C" size_t ttg_bn_workspace_bytes(int C) { return sizeof(double) * 5 * (s
 
 extern "C" int ttg_bn_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* invstd,
                             float* running_mean, float* running_var, long long* num_batches, void* workspace,
-                            int dtype, void* stream) {
+                            long long count_mult, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  TTG_REQUIRE(M > 0 && C > 0, "bn_stats: empty input");
+  TTG_REQUIRE(M > 0 && C > 0 && count_mult >= 1, "bn_stats: empty input");
   double* ws = (double*)workspace;
   TTG_DISPATCH(dtype, {
     StatsOp<T> op; op.in[0] = (const T*)x;
     int rc = launch_chan_reduce<T>("bn_stats", op, M, C, ws, st);
     if (rc) return rc;
   });
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, M, C, eps, momentum, mean, invstd, running_mean,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, M, count_mult, C, eps, momentum, mean, invstd, running_mean,
                                                        running_var, num_batches);
   TTG_CHECK_LAUNCH("bn_finalize");
   return TTG_OK;

@@ -163,6 +163,63 @@ extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, in
   return TTG_OK;
 }
 
+// out[n,oy,ox,c] = h[n,oy,ox,c] + s[n,oy/2,ox/2,c]   (residual add with the nearest-upsampled skip folded in)
+template <typename T, int V>
+__global__ void add_up2_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C) {
+  const int cv = C / V; const int Hi = Ho / 2, Wi = Wo / 2;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
+    float a[V], b[V];
+    Ld<T, V>::ld(h + i * V, a);
+    Ld<T, V>::ld(s + (((long long)n * Hi + (oy >> 1)) * Wi + (ox >> 1)) * C + c, b);
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] += b[j];
+    Ld<T, V>::st(y + i * V, a);
+  }
+}
+extern "C" int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "add_up2: odd output size");
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { add_up2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 512), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
+    else { add_up2_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 1024), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
+  });
+  TTG_CHECK_LAUNCH("add_up2");
+  return TTG_OK;
+}
+
+// out[n,oy,ox,c] = scale * sum_{2x2} h + s[n,oy,ox,c]   (AvgPool2d(2) of the conv path + skip, one pass)
+template <typename T, int V>
+__global__ void pool2_add_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C, float scale) {
+  const int cv = C / V; const int Wi = Wo * 2;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % cv) * V; long long p = i / cv;
+    int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
+    const T* src = h + (((long long)n * Ho * 2 + oy * 2) * Wi + ox * 2) * C + c;
+    float a[V], b[V], acc[V], sk[V];
+    Ld<T, V>::ld(src, a); Ld<T, V>::ld(src + C, b);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = a[j] + b[j];
+    Ld<T, V>::ld(src + (long long)Wi * C, a); Ld<T, V>::ld(src + (long long)Wi * C + C, b);
+    Ld<T, V>::ld(s + i * V, sk);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = (acc[j] + a[j] + b[j]) * scale + sk[j];
+    Ld<T, V>::st(y + i * V, acc);
+  }
+}
+extern "C" int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_DISPATCH(dtype, {
+    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { pool2_add_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
+    else { pool2_add_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
+  });
+  TTG_CHECK_LAUNCH("pool2_add");
+  return TTG_OK;
+}
+
 // out = alpha*a + beta*b
 template <typename T, int V>
 __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long nvec, float alpha, float beta) {

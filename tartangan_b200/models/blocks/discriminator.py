@@ -73,11 +73,13 @@ class ResidualDiscriminatorBlock(nn.Module):
     def forward(self, x):
         x = ops.ensure_internal(x)
         xs, xh = ops.fork(x)
-        h = run_layers(self.convs, xh)
+        layers = list(self.convs)
+        fuse_pool = isinstance(layers[-1], AvgPool2d)
+        h = run_layers(layers[:-1] if fuse_pool else layers, xh)
         xs = self.interpolate(xs)
         if self.project_input is not None:
             xs = run_layers(self.project_input, xs)
-        return ops.add(xs, h)
+        return ops.avg_pool2_add(h, xs) if fuse_pool else ops.add(xs, h)
 
 
 class DiscriminatorOutput(nn.Module):

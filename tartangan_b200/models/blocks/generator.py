@@ -2,9 +2,11 @@
 
 Same constructors, defaults and state-dict keys; the forward passes run the
 hand-written kernels.  Fusions relative to the reference module graph: the nearest
-x2 upsample (generator.py:58) is folded into the addressing of the first 3x3 conv
-and of the 1x1 skip projection (never materialised), and each BatchNorm+LeakyReLU
-pair is one kernel.
+x2 upsample (generator.py:58) is never materialised — the leading BatchNorm+LeakyReLU
+and the 1x1 skip projection run at low resolution (they commute with nearest
+upsampling, batch statistics included), the first 3x3 conv reads its input through
+(y>>1, x>>1) addressing and the residual add reads the skip the same way; each
+BatchNorm+LeakyReLU pair is one kernel.
 """
 import functools
 
@@ -54,13 +56,11 @@ class ResidualGeneratorBlock(nn.Module):
 
     def forward(self, x):
         x = ops.ensure_internal(x)
-        if self.upsample:
-            x = ops.upsample2(x)
         xs, xh = ops.fork(x)
-        h = run_layers(self.convs, xh)
+        h = run_layers(self.convs, xh, up_first=self.upsample)
         if self.project_input is not None:
-            xs = run_layers(self.project_input, xs)
-        return ops.add(xs, h)
+            xs = run_layers(self.project_input, xs)      # 1x1 conv commutes with nearest upsampling: run it low-res
+        return ops.add_up2(h, xs) if self.upsample else ops.add(xs, h)
 
 
 class GeneratorInputMLP(nn.Module):

@@ -103,19 +103,35 @@ def native(factory):
     return factory
 
 
-def run_layers(layers, x):
-    """Run an nn.Sequential-style list, fusing (BatchNorm2d | Identity) + LeakyReLU pairs into one op."""
+def run_layers(layers, x, up_first=False):
+    """Run an nn.Sequential-style list, fusing (BatchNorm2d | Identity) + LeakyReLU pairs into one op.
+
+    up_first=True: x is the LOW-resolution input of a block that starts with a nearest x2 upsample.
+    Element-wise layers before the first conv run at low resolution (they commute with nearest
+    upsampling, batch statistics included) and that conv reads its input through (y>>1, x>>1)
+    addressing, so the upsampled tensor is never written."""
     layers = list(layers)
     i = 0
+    pending_up = up_first
     while i < len(layers):
         m = layers[i]
         nxt = layers[i + 1] if i + 1 < len(layers) else None
         if isinstance(m, BatchNorm2d) and isinstance(nxt, LeakyReLU):
-            x = ops.bn_act(ops.ensure_internal(x), m, nxt.negative_slope)
+            x = ops.bn_act(ops.ensure_internal(x), m, nxt.negative_slope, 4 if pending_up else 1)
             i += 2
         elif isinstance(m, nn.Identity):
+            i += 1
+        elif pending_up and isinstance(m, Conv2d):
+            x = m(x, up=1)
+            pending_up = False
+            i += 1
+        elif pending_up and not isinstance(m, LeakyReLU):
+            x = m(ops.upsample2(x))          # unknown layer type: materialise the upsample first
+            pending_up = False
             i += 1
         else:
             x = m(x)
             i += 1
+    if pending_up:
+        x = ops.upsample2(x)
     return x

@@ -25,6 +25,7 @@ class _State:
     inputs_only = False            # set by gradient_penalty: skip parameter gradients
     use_tc = True                  # tensor-core conv kernels when shapes allow
     launches = 0                   # kernels launched through the C ABI (bench counter)
+    pack_generation = 0            # bumped to invalidate every packed-weight cache (CUDA-graph capture)
 
 
 state = _State()
@@ -132,7 +133,7 @@ def _packed(w, mode, kind):
     """Packed copy of a conv weight.  The cache lives ON the weight tensor (so it dies with it) and
     is validated by (_version, _ttg_epoch, data_ptr): _version catches in-place torch updates,
     _ttg_epoch is bumped by FusedAdam, whose kernel writes the flat buffer behind autograd's back."""
-    ver = (w._version, getattr(w, '_ttg_epoch', 0), w.data_ptr())
+    ver = (w._version, getattr(w, '_ttg_epoch', 0), w.data_ptr(), state.pack_generation)
     cache = getattr(w, '_ttg_pack', None)
     if cache is None:
         cache = {}
@@ -310,7 +311,7 @@ class BnActFn(Function):
     """lrelu(batch_norm(x)) with batch statistics (train) or running statistics (eval)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, training, momentum, eps, slope):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, training, momentum, eps, slope, count_mult=1):
         x = nhwc(x)
         n, c, h, w = x.shape
         m = n * h * w
@@ -320,7 +321,7 @@ class BnActFn(Function):
         if training:
             ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
             call('ttg_bn_stats', ptr(x), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
-                 ptr(running_var), ptr(num_batches), ptr(ws), dtype_code(x.dtype))
+                 ptr(running_var), ptr(num_batches), ptr(ws), count_mult, dtype_code(x.dtype))
         else:
             call('ttg_bn_eval_stats', ptr(running_mean), ptr(running_var), eps, c, ptr(mean), ptr(invstd))
         y = _empty_like(x)
@@ -339,7 +340,7 @@ class BnActFn(Function):
         gx, ggamma, gbeta = BnActBwdFn.apply(x, ga, gamma, beta, mean, invstd, ctx.slope)
         if state.inputs_only:
             ggamma = gbeta = None
-        return gx, ggamma, gbeta, None, None, None, None, None, None, None
+        return gx, ggamma, gbeta, None, None, None, None, None, None, None, None
 
 
 class BnActBwdFn(Function):
@@ -378,12 +379,14 @@ class BnActBwdFn(Function):
         return g_x, g_ga, g_gamma, None, None, None, None
 
 
-def bn_act(x, bn, slope=SLOPE):
-    """x -> lrelu(bn(x)) for an nn.BatchNorm2d-compatible module `bn` (or identity norm if None)."""
+def bn_act(x, bn, slope=SLOPE, count_mult=1):
+    """x -> lrelu(bn(x)) for an nn.BatchNorm2d-compatible module `bn` (or identity norm if None).
+    count_mult=4: x is the low-resolution source of a nearest x2 upsample; statistics are identical,
+    only the unbiased running-variance correction uses the upsampled element count."""
     if bn is None:
         return leaky_relu(x, slope)
     return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                         bn.training or bn.running_mean is None, bn.momentum, bn.eps, slope)
+                         bn.training or bn.running_mean is None, bn.momentum, bn.eps, slope, count_mult)
 
 
 class LeakyReluFn(Function):
@@ -465,6 +468,47 @@ class Up2Fn(Function):
     @staticmethod
     def backward(ctx, g):
         return Pool2Fn.apply(g, ctx.scale), None
+
+
+class AddUp2Fn(Function):
+    """h + nearest_up2(s): the generator's residual join with the upsample of the skip folded in."""
+
+    @staticmethod
+    def forward(ctx, h, s):
+        h, s = nhwc(h), nhwc(s)
+        n, c, ho, wo = h.shape
+        y = _empty_like(h)
+        call('ttg_add_up2', ptr(h), ptr(s), ptr(y), n, ho, wo, c, dtype_code(h.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, Pool2Fn.apply(g, 1.0)
+
+
+class Pool2AddFn(Function):
+    """scale * pool2sum(h) + s: the discriminator's residual join with AvgPool2d(2) folded in."""
+
+    @staticmethod
+    def forward(ctx, h, s, scale):
+        ctx.scale = scale
+        h, s = nhwc(h), nhwc(s)
+        n, c, ho, wo = s.shape
+        y = _empty_like(s)
+        call('ttg_pool2_add', ptr(h), ptr(s), ptr(y), n, ho, wo, c, scale, dtype_code(h.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return Up2Fn.apply(g, ctx.scale), g, None
+
+
+def add_up2(h, s):
+    return AddUp2Fn.apply(h, s)
+
+
+def avg_pool2_add(h, s):
+    return Pool2AddFn.apply(h, s, 0.25)
 
 
 def avg_pool2(x):

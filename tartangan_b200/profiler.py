@@ -51,6 +51,16 @@ class KernelProfiler:
         if name in ('ttg_conv2d_tc', 'ttg_conv2d_direct'):
             key = _conv_key(args)
             nbytes, flops = _conv_bytes_flops(args)
+        elif name == 'ttg_conv2d_tc_ex':        # (x, wp, bias, y, N, H, W, CinP, CoutP, cin, cout, k, up, ...)
+            a = list(args[:4]) + list(args[4:7]) + [args[9], args[10], args[11], args[12]]
+            key = _conv_key(a)
+            nbytes, flops = _conv_bytes_flops(a)
+            name = 'ttg_conv2d_tc'
+        elif name == 'ttg_conv2d_wgrad_tc_ex':  # (x, gy, gw, N, H, W, CinP, CoutP, cin, cout, k, up, ws)
+            a = list(args[:3]) + list(args[3:6]) + [args[8], args[9], args[10], args[11]]
+            key = _wgrad_key(a)
+            nbytes, flops = _wgrad_bytes_flops(a)
+            name = 'ttg_conv2d_wgrad_tc'
         elif name in ('ttg_conv2d_wgrad_tc', 'ttg_conv2d_wgrad_direct'):
             key = _wgrad_key(args)
             nbytes, flops = _wgrad_bytes_flops(args)

@@ -89,18 +89,22 @@ class GanTrainer(Trainer):
             optimizer._ttg_reducer = red
         return red
 
-    def _backward(self, loss, optimizer):
-        """loss.backward() with the gradient exchange overlapped: the loss is scaled by 1/world so the
-        summed gradients are the global-batch average."""
-        red = self._reducer(optimizer)
-        if red is None:
+    def _backward(self, loss, optimizer, overlap=True):
+        """loss.backward(); in data parallel the loss is scaled by 1/world so the SUMMED gradients are the
+        global-batch average, and (eager mode) the exchange is overlapped with the rest of backward."""
+        if self.world_size == 1:
             loss.backward()
             return
-        red.begin()
+        red = self._reducer(optimizer) if overlap else None
+        if red is not None:
+            red.begin()
         loss.backward(torch.full_like(loss, 1.0 / self.world_size))
-        red.finish()
+        if red is not None:
+            red.finish()
 
-    def d_step(self, imgs):
+    # The step is cut into four segments so that the same code runs eagerly or as CUDA graphs
+    # (one graph on a single GPU; three graphs with the two gradient exchanges between them otherwise).
+    def d_forward_backward(self, imgs, overlap=True):
         toggle_grad(self.g, False)
         toggle_grad(self.d, True)
         self.optimizer_d.zero_grad()
@@ -114,33 +118,177 @@ class GanTrainer(Trainer):
         if self.args.grad_penalty:
             gp = gradient_penalty(p_real, real)
             d_loss = ops.AxpbyFn.apply(d_loss, gp, 1.0, float(self.args.grad_penalty))
-        self._backward(d_loss, self.optimizer_d)
-        self.optimizer_d.step()
-        return d_loss, gp
+        self._backward(d_loss, self.optimizer_d, overlap)
+        return d_loss.detach(), (gp.detach() if gp is not None else None)
 
-    def g_step(self, imgs):
+    def d_update(self):
+        self.optimizer_d.step()
+
+    def g_forward_backward(self, imgs, overlap=True):
         toggle_grad(self.g, True)
         toggle_grad(self.d, False)
         self.optimizer_g.zero_grad()
         fake = self.sample_g(len(imgs))
         g_loss = self.g_loss(fake)
-        self._backward(g_loss, self.optimizer_g)
+        self._backward(g_loss, self.optimizer_g, overlap)
+        return g_loss.detach()
+
+    def g_update(self):
         # Adam and the EMA of target_g (update_target_generator) are one kernel
         self.optimizer_g.ema_target = self._flat_target()
         self.optimizer_g.ema_lr = float(self.args.lr_target_g)
         self.optimizer_g.step()
-        return g_loss
+
+    def d_step(self, imgs):
+        out = self.d_forward_backward(imgs)
+        self.d_update()
+        return out
+
+    def g_step(self, imgs):
+        out = self.g_forward_backward(imgs)
+        self.g_update()
+        return out
 
     def train_batch(self, imgs, as_floats=True):
-        imgs = imgs.to(self.device, non_blocking=True)
         self.g.train()
         self.d.train()
-        d_loss, gp = self.d_step(imgs)
-        g_loss = self.g_step(imgs)
+        if getattr(self.args, 'cuda_graph', False) and len(imgs) == self.args.batch_size:
+            d_loss, gp, g_loss = self._train_batch_graphed(imgs)
+        else:
+            imgs = imgs.to(self.device, non_blocking=True)
+            d_loss, gp = self.d_step(imgs)
+            g_loss = self.g_step(imgs)
         if not as_floats:
-            return dict(g_loss=g_loss.detach(), d_loss=d_loss.detach(), gp=gp)
-        gp_val = float(gp.detach()) * self.args.grad_penalty if gp is not None else 0.
-        return dict(g_loss=float(g_loss.detach()), d_loss=float(d_loss.detach()), gp=gp_val)
+            return dict(g_loss=g_loss, d_loss=d_loss, gp=gp)
+        gp_val = float(gp) * self.args.grad_penalty if gp is not None else 0.
+        return dict(g_loss=float(g_loss), d_loss=float(d_loss), gp=gp_val)
+
+    # ------------------------------------------------------------------ CUDA-graph execution
+    def _n_tau_draws(self):
+        return 3 if hasattr(self.d, 'to_output') and hasattr(self.d.to_output, 'iqn') else 0
+
+    def sample_z(self, n=None):
+        st = getattr(self, '_st', None)
+        if st is not None and st['active']:          # graph capture: read the static buffer
+            z = st['z'][st['zi']]
+            st['zi'] += 1
+            return z
+        return super().sample_z(n)
+
+    def _static_taus(self, rows):
+        st = self._st
+        if not st['active']:
+            return torch.rand(rows, 1).to(self.device)
+        t = st['tau'][st['ti']]
+        st['ti'] += 1
+        return t
+
+    def _stage_inputs(self, imgs):
+        """Draw z / tau from the CPU generator in the reference's order (trainer.py:153-156, iqn.py:105-108:
+        z, tau, tau, z, tau) into pinned buffers and copy them, with the images, into the static device
+        buffers the graphs read."""
+        st = self._st
+        b, nq = self.args.batch_size, (self.d.to_output.iqn.num_quantiles if st['tau'] else 0)
+        order = ['z0'] + (['t0', 't1'] if st['tau'] else []) + ['z1'] + (['t2'] if st['tau'] else [])
+        for key in order:
+            i = int(key[1])
+            if key[0] == 'z':
+                torch.randn(b, self.gan_config.latent_dims, out=st['z_pin'][i])
+                st['z'][i].copy_(st['z_pin'][i], non_blocking=True)
+            else:
+                torch.rand(b * nq, 1, out=st['tau_pin'][i])
+                st['tau'][i].copy_(st['tau_pin'][i], non_blocking=True)
+        st['imgs'].copy_(imgs, non_blocking=True)
+
+    def _capture(self, imgs):
+        dev, b = self.device, self.args.batch_size
+        nt = self._n_tau_draws()
+        nq = self.d.to_output.iqn.num_quantiles if nt else 0
+        self._st = st = dict(
+            imgs=torch.empty((b,) + tuple(imgs.shape[1:]), dtype=torch.float32, device=dev),
+            z=[torch.empty(b, self.gan_config.latent_dims, device=dev) for _ in range(2)],
+            z_pin=[torch.empty(b, self.gan_config.latent_dims).pin_memory() for _ in range(2)],
+            tau=[torch.empty(b * nq, 1, device=dev) for _ in range(nt)],
+            tau_pin=[torch.empty(b * nq, 1).pin_memory() for _ in range(nt)], zi=0, ti=0, active=False)
+        # warm-up (eager, on a side stream as torch.cuda.graph requires): sets lazy kernel attributes, flattens
+        # the parameter buffers, fills the packed-weight caches.  RNG state is restored afterwards so that the
+        # first graphed step consumes the same draws an eager first step would have.
+        rng = torch.get_rng_state()
+        saved = [{k: v.clone() for k, v in m.state_dict().items()} for m in (self.g, self.target_g, self.d)]
+        for opt in (self.optimizer_d, self.optimizer_g):
+            opt._ensure_flat()
+        opt_saved = [(o._m.clone(), o._v.clone(), o._step.clone()) for o in (self.optimizer_d, self.optimizer_g)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            x = imgs.to(dev)
+            for _ in range(2):
+                self.d_step(x)
+                self.g_step(x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for m, sd in zip((self.g, self.target_g, self.d), saved):
+            m.load_state_dict(sd)
+        for opt, (m_, v_, s_) in zip((self.optimizer_d, self.optimizer_g), opt_saved):
+            opt._m.copy_(m_); opt._v.copy_(v_); opt._step.copy_(s_)
+        torch.set_rng_state(rng)
+        ops.state.pack_generation += 1          # every packed weight is re-packed (and captured) at first use
+        # route z / tau draws to the static buffers while capturing
+        if nt:
+            self.d.to_output.iqn.tau_source = self._static_taus
+        self._stage_inputs(imgs)
+        st['zi'] = st['ti'] = 0
+        st['active'] = True
+        graphs, pool = [], None
+        out = {}
+        from .. import _lib
+        k_before = _lib.Counters.kernels
+
+        def seg(fn):
+            nonlocal pool
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                fn()
+            pool = g.pool()
+            graphs.append(g)
+
+        overlap = False                           # exchanges happen between graphs
+        if self.world_size == 1:
+            def whole():
+                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap)
+                self.d_update()
+                out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
+                self.g_update()
+            seg(whole)
+            self._segments = [(graphs[0], None)]
+        else:
+            def s1():
+                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap)
+            def s2():
+                self.d_update()
+                out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
+            seg(s1); seg(s2); seg(self.g_update)
+            gd, gg = self.optimizer_d._ensure_flat().grad, self.optimizer_g._ensure_flat().grad
+            self._segments = [(graphs[0], gd), (graphs[1], gg), (graphs[2], None)]
+        self._graph_out = out
+        self._graph_kernels = _lib.Counters.kernels - k_before      # kernels recorded in the graphs = launched per replay
+        st['active'] = False
+        torch.cuda.synchronize()
+        # the capture pass itself executed nothing: restore nothing, the first replay is step 1
+
+    def _train_batch_graphed(self, imgs):
+        if getattr(self, '_segments', None) is None:
+            self._capture(imgs)
+        else:
+            self._stage_inputs(imgs)
+        from .. import _lib
+        _lib.Counters.kernels += self._graph_kernels
+        for graph, exchange in self._segments:
+            graph.replay()
+            if exchange is not None:
+                torch.distributed.all_reduce(exchange)
+        o = self._graph_out
+        return o['d_loss'], o['gp'], o['g_loss']
 
     def _flat_target(self):
         if self._target_flat is None or not self._target_flat.intact():

@@ -252,5 +252,7 @@ class Trainer:
         p.add_argument('--precision', default='bf16', choices=('bf16', 'fp32'),
                        help='activation/conv-operand precision of the CUDA path')
         p.add_argument('--num-quantiles', type=int, default=8, help='IQN quantile count (reference: 8)')
+        p.add_argument('--cuda-graph', action='store_true',
+                       help='run the training step as CUDA graphs (static shapes; z/tau staged from the CPU generator)')
         p.add_argument('--attention', type=type_or_none(str), default=None,
                        help='comma-separated block indices with self-attention (overrides the config)')

@@ -55,7 +55,7 @@ def main():
         mean = torch.zeros(c, device='cuda'); inv = torch.ones(c, device='cuda')
         ws = torch.empty(5 * c, dtype=torch.float64, device='cuda')
         y = torch.empty_like(x)
-        fn = lambda: call('ttg_bn_stats', ptr(x), m, c, 1e-5, 0.1, ptr(mean), ptr(inv), None, None, None, ptr(ws), _lib.BF16)
+        fn = lambda: call('ttg_bn_stats', ptr(x), m, c, 1e-5, 0.1, ptr(mean), ptr(inv), None, None, None, ptr(ws), 1, _lib.BF16)
         med, best = timeit(fn)
         print(f'bn_stats M{m} C{c}: {med*1e3:.1f} us {m*c*2/med/1e6:.0f} GB/s')
         fn = lambda: call('ttg_bn_act_fwd', ptr(x), ptr(y), m, c, ptr(mean), ptr(inv), ptr(inv), ptr(mean), 0.2, _lib.BF16)
