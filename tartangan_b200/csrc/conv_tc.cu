@@ -402,7 +402,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // epilogue; warp 4 only issues tcgen05.mma.  Hand-offs are mbarriers (full/empty per activation slot,
 // full/empty per TMEM accumulator), so loads of tile i+NBUF-1, MMAs of tile i and the epilogue of
 // tile i-1 are in flight together and nobody waits for the single MMA-issuing thread.
-template <int K, int NBUF>
+template <int K, int NBUF, bool LEAN>
 __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                               const float* __restrict__ bias, void* __restrict__ y,
                                                               int out_f32, int H, int W, int Cin, int Cout, int up,
@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
         int n, y0, x0;
         tile_coords(j, n, y0, x0);
         uint8_t* dst = sA + (size_t)s * a_bytes;
-        if (cin_real != Cin) {
+        if constexpr (LEAN) {         // common case only: keeps the instruction footprint small
+          stage_rows<HALO, true>(rs, dst, x, n, y0, x0, H, W, Cin, up, nullptr, nullptr, 1.f);
+        } else if (cin_real != Cin) {
           stage_tile_pad<HALO>(dst, x, n, y0, x0, H, W, Cin, cin_real, up, 128);
         } else if (fast_stage) {
           if (pre_scale) stage_rows<HALO, false>(rs, dst, x, n, y0, x0, H, W, Cin, up, pre_scale, pre_shift, slope);
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
       tile_coords(j, n, y0, x0);
       mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
       tc_fence_after_sync();
-      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32, cout_real);
+      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32, LEAN ? 0 : cout_real);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
     };
@@ -529,19 +531,19 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
-template <int K, int NBUF>
+template <int K, int NBUF, bool LEAN>
 static int launch_conv_tc_persist(const void* x, const void* wp, const float* bias, void* y, int out_f32, int H, int W,
                                   int Cin, int Cout, int up, const float* pre_scale, const float* pre_shift, float slope,
                                   long long tiles, int psmem, int pcols, int per_sm, int cin_real, int cout_real, cudaStream_t st) {
   static int smem_set = 0;
   if (psmem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<K, NBUF, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     smem_set = psmem;
   }
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
-  conv_tc_persist_kernel<K, NBUF><<<(unsigned)grid, 160, psmem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
+  conv_tc_persist_kernel<K, NBUF, LEAN><<<(unsigned)grid, 160, psmem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
                                                                      Cout, up, pre_scale, pre_shift, slope, (int)tiles, pcols, cin_real, cout_real);
   TTG_CHECK_LAUNCH("conv2d_tc_persist");
   return TTG_OK;
@@ -592,8 +594,11 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     const int of32 = dtype_out == TTG_F32;
-#define TTG_PERSIST(KK, NB) launch_conv_tc_persist<KK, NB>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, pre_shift, \
-                                                        slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st)
+    const bool lean = !padded && !pre_scale && (TC_TW + 2 * halo) * (Cin / 8) <= 128;
+#define TTG_PERSIST(KK, NB) (lean ? launch_conv_tc_persist<KK, NB, true>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, \
+                                        pre_shift, slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st)              \
+                                  : launch_conv_tc_persist<KK, NB, false>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, \
+                                        pre_shift, slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st))
     if (ksize == 3) return nbuf == 4 ? TTG_PERSIST(3, 4) : nbuf == 3 ? TTG_PERSIST(3, 3) : TTG_PERSIST(3, 2);
     return nbuf == 4 ? TTG_PERSIST(1, 4) : nbuf == 3 ? TTG_PERSIST(1, 3) : TTG_PERSIST(1, 2);
 #undef TTG_PERSIST

@@ -161,4 +161,5 @@ def test_cuda_graph_step_matches_eager(kind):
             assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (s, k, a[k], b[k])
     for k, v in res[0][1].items():
         if v.is_floating_point() and 'running' not in k and not k.endswith('.bias'):
-            assert _params_close(res[1][1][k], v, lr=4e-4 * 3), k
+            drift = float((res[1][1][k].float() - v.float()).abs().mean())
+            assert drift <= 0.25 * 4e-4 * 3, (k, drift)      # far below the 3*lr an element can move
