@@ -176,6 +176,8 @@ int ttg_dot_f32out(const void* a, const void* b, float* out, long long n, void* 
  * conv_factory kwarg of the blocks: generator.py:34, discriminator.py:28,52) */
 int ttg_spectral_norm(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
                       int n_iter, float eps, void* workspace, void* stream);
+int ttg_spectral_norm_sigma(const float* w, const float* u, const float* v, float* w_out, float* sigma, int rows,
+                            int cols, void* workspace, void* stream);
 /* g_w = (g - dot(g, w_out) * u v^T) / sigma */
 int ttg_spectral_norm_bwd(const float* g, const float* w_out, const float* u, const float* v, const float* sigma,
                           float* gw, int rows, int cols, void* workspace, void* stream);

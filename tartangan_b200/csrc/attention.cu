@@ -282,6 +282,30 @@ extern "C" int ttg_spectral_norm(const float* w, float* u, float* v, float* w_ou
   TTG_CHECK_LAUNCH("spectral_norm_scale");
   return TTG_OK;
 }
+// eval mode: sigma = u^T W v with the given (already normalised) u, v; no update
+__global__ void sn_sigma_kernel(const float* __restrict__ w, const float* __restrict__ u, const float* __restrict__ v,
+                                float* __restrict__ norms, int rows, int cols) {
+  const int lane = threadIdx.x & 31; const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp < rows) {
+    float s = 0.f;
+    const float* wr = w + (long long)warp * cols;
+    for (int c = lane; c < cols; c += 32) s += wr[c] * v[c];
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(&norms[0], s * u[warp]);
+  }
+}
+__global__ void sn_copy_sigma_kernel(const float* norms, float* sigma) { sigma[0] = norms[0]; }
+extern "C" int ttg_spectral_norm_sigma(const float* w, const float* u, const float* v, float* w_out, float* sigma, int rows,
+                                       int cols, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* norms = (float*)workspace;
+  sn_reset_kernel<<<1, 1, 0, st>>>(norms);
+  sn_sigma_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, u, v, norms, rows, cols);
+  sn_copy_sigma_kernel<<<1, 1, 0, st>>>(norms, sigma);
+  sn_scale_kernel<<<ttg_grid_for((long long)rows * cols, 1024), 256, 0, st>>>(w, sigma, w_out, (long long)rows * cols);
+  TTG_CHECK_LAUNCH("spectral_norm_sigma");
+  return TTG_OK;
+}
 // g_w = (g - dot(g, w_out) * u v^T) / sigma
 __global__ void sn_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ v,
                               const float* __restrict__ sigma, const double* __restrict__ dot, float* __restrict__ gw, int rows, int cols) {

@@ -135,3 +135,27 @@ def run_layers(layers, x, up_first=False):
     if pending_up:
         x = ops.upsample2(x)
     return x
+
+
+class SpectralNormConv2d(Conv2d):
+    """Conv2d whose weight is divided by its largest singular value, estimated with one power-iteration
+    step per training forward — the semantics of torch.nn.utils.spectral_norm (the hook API that
+    tartangan/prep4web.py:33-51 strips): parameters `weight_orig`, buffers `weight_u`, `weight_v`.
+    Plugs into the blocks through their conv_factory seam (generator.py:34, discriminator.py:28,52)."""
+
+    def __init__(self, *args, n_power_iterations=1, eps=1e-12, **kw):
+        super().__init__(*args, **kw)
+        w = self.weight
+        del self._parameters['weight']
+        self.register_parameter('weight_orig', nn.Parameter(w.data))
+        rows, cols = w.shape[0], w[0].numel()
+        u = torch.nn.functional.normalize(w.new_empty(rows).normal_(0, 1), dim=0, eps=eps)
+        v = torch.nn.functional.normalize(w.new_empty(cols).normal_(0, 1), dim=0, eps=eps)
+        self.register_buffer('weight_u', u)
+        self.register_buffer('weight_v', v)
+        self.n_power_iterations, self.sn_eps = n_power_iterations, eps
+
+    def forward(self, x, up=0, out_dtype=None):
+        w = ops.SpectralNormFn.apply(self.weight_orig, self.weight_u, self.weight_v,
+                                     self.n_power_iterations if self.training else 0, self.sn_eps)
+        return ops.conv2d(ops.ensure_internal(x), w, self.bias, up, out_dtype)

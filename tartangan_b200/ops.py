@@ -1089,3 +1089,34 @@ def ensure_internal(x):
     if x.dtype == state.act_dtype and _is_nhwc(x):
         return x
     return ToInternal.apply(x, state.act_dtype)
+
+
+class SpectralNormFn(Function):
+    """w / sigma(w) with `n_iter` power-iteration steps updating u, v in place (torch.nn.utils.spectral_norm).
+    Backward treats u, v as constants: g_w = (g - <g, w_out> u v^T) / sigma."""
+
+    @staticmethod
+    def forward(ctx, w, u, v, n_iter, eps):
+        wd = _flat(w.detach())
+        rows, cols = w.shape[0], w[0].numel()
+        w_out = torch.empty_like(wd)
+        sigma = torch.empty(1, dtype=torch.float32, device=w.device)
+        ws = torch.empty(4 + rows + cols, dtype=torch.float32, device=w.device)
+        if n_iter > 0:
+            call('ttg_spectral_norm', ptr(wd), ptr(u), ptr(v), ptr(w_out), ptr(sigma), rows, cols, n_iter, eps, ptr(ws))
+        else:       # eval: sigma = u^T W v with the stored vectors, no update
+            uu, vv = u.clone(), v.clone()
+            call('ttg_spectral_norm_sigma', ptr(wd), ptr(uu), ptr(vv), ptr(w_out), ptr(sigma), rows, cols, ptr(ws))
+        ctx.save_for_backward(w_out, u.clone(), v.clone(), sigma)
+        return w_out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        w_out, u, v, sigma = ctx.saved_tensors
+        g = _flat(g)
+        rows, cols = w_out.shape[0], w_out[0].numel()
+        gw = torch.empty_like(w_out)
+        call('ttg_spectral_norm_bwd', ptr(g), ptr(w_out), ptr(u), ptr(v), ptr(sigma), ptr(gw), rows, cols,
+             ptr(_ws(8, g.device)))
+        return gw, None, None, None, None
