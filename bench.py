@@ -202,17 +202,25 @@ def main():
         hbm, tflops, which = _peaks()
         value = args.batch * world * args.steps / (ms / 1e3)
         e2e_val = args.batch * world * args.steps / e2e_s
-        # dominant kernel = the entry point with the largest share of device time
-        top = by_name[0]
-        conv_like = top['flops'] > 0 and (top['flops'] / max(top['bytes'], 1)) > (tflops * 1e12) / (hbm * 1e9)
-        if conv_like:
+        # dominant kernel = the (entry point, shape) with the largest share of device time
+        fam = by_name[0]
+        cands = [r for r in rows if r['name'] == fam['name'] and r['bytes'] > 0] or [fam]
+        top = max(cands, key=lambda r: r['ms'])
+        per_launch_ms = top['ms'] / max(top['calls'], 1)
+        ai = top['flops'] / max(top['bytes'], 1)
+        if ai > (tflops * 1e12) / (hbm * 1e9):
             achieved = top['flops'] / (top['ms'] / 1e3) / 1e12
             roof = dict(bound='tensor', achieved=achieved, peak=tflops, unit='TFLOP/s', frac=achieved / tflops)
         else:
             achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
             roof = dict(bound='hbm', achieved=achieved, peak=hbm, unit='GB/s', frac=achieved / hbm)
-        roof.update(traffic=None, kernel=top['name'], peak_source=which, launches_per_step=top['calls'],
+        # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel+shape (profiles/)
+        ncu_traffic = {('ttg_conv2d_tc', 'N256 128x128 16->16 k3 up0'): 220.6e6}
+        roof.update(traffic=ncu_traffic.get((top['name'], top.get('key', ''))), kernel=top['name'], shape=top.get('key', ''),
+                    algorithmic_bytes_per_launch=top['bytes'] / max(top['calls'], 1), us_per_launch=per_launch_ms * 1e3,
+                    peak_source=which, launches_per_step=top['calls'],
                     share_of_step=top['ms'] / max(step_ms_prof, 1e-9),
+                    family_share_of_step=fam['ms'] / max(step_ms_prof, 1e-9),
                     step_frac_of_mixed_roofline=(value / world) / ROOFLINE_IMG_S,
                     step_hbm_gbs=(value / world) * MB_PER_IMG / 1e3, step_tflops=(value / world) * GFLOP_PER_IMG / 1e3)
         line = {

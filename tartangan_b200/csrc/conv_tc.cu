@@ -551,6 +551,166 @@ static int launch_conv_tc_persist(const void* x, const void* wp, const float* bi
 
 #define TC_RESIDENT_W_BYTES (80 * 1024)
 
+// ------------------------------------------------------------------ fprop / dgrad, filters too large for shared memory
+// (128->128, 256->256 ...): persistent, warp-specialised, weights STREAMED.  warps 0-3 stage activation tiles
+// (cp.async, NA slots) and run the epilogue; warp 4 issues tcgen05.mma; warp 5 streams the packed filter from L2
+// through a ring of NW 16 KB stages (cp.async) for every tile.  These layers are tensor/L2 bound, not HBM bound.
+#define TC_WSTAGE_BYTES (16 * 1024)
+template <int K, int NA>
+__global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                                const float* __restrict__ bias, void* __restrict__ y,
+                                                                int out_f32, int H, int W, int Cin, int Cout, int up,
+                                                                int total_tiles, int tmem_cols, int chunk_slices) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  constexpr int NW = 4, WD = NW - 2, NACC = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k16n = Cin >> 4, c8n = Cin >> 3;
+  const int total_slices = K * K * k16n;
+  const int nchunks = (total_slices + chunk_slices - 1) / chunk_slices;
+  const uint32_t slice_bytes = (uint32_t)Cout * 32;
+  const uint32_t a_bytes = (uint32_t)c8n * HP * 16;
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + (size_t)NA * a_bytes;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sW + (size_t)NW * TC_WSTAGE_BYTES);
+  uint64_t* aempty = afull + NA;
+  uint64_t* wfull = aempty + NA;
+  uint64_t* wempty = wfull + NW;
+  uint64_t* acc_full = wempty + NW;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_coords = [&](int j, int& n, int& y0, int& x0) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    n = tile / tiles_img;
+    const int t2 = tile - n * tiles_img;
+    y0 = (t2 / tiles_x) * TC_TH;
+    x0 = (t2 % tiles_x) * TC_TW;
+  };
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 128); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_fence_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ activation tiles + epilogue
+    auto stage = [&](int j) {
+      if (j < T) {
+        const int s = j % NA;
+        if (j >= NA) mbar_wait(&aempty[s], (uint32_t)((j / NA) - 1) & 1u);
+        int n, y0, x0;
+        tile_coords(j, n, y0, x0);
+        stage_tile_async<HALO>(sA + (size_t)s * a_bytes, x, n, y0, x0, H, W, Cin, up, 128);
+      }
+      cp_async_commit();
+    };
+    auto epilogue = [&](int j) {
+      const int acc = j % NACC;
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      tc_fence_after_sync();
+      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+    };
+    if (NA > 1) stage(0);
+    for (int it = 0; it < T; ++it) {
+      if (NA > 1) { stage(it + 1); cp_async_wait_group<1>(); }
+      else { stage(it); cp_async_wait_group<0>(); }
+      fence_proxy_async_smem();
+      mbar_arrive(&afull[it % NA]);
+      if (it > 0) epilogue(it - 1);
+    }
+    if (T > 0) epilogue(T - 1);
+    cp_async_wait_all();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
+    long long g = 0;
+    for (int it = 0; it < T; ++it) {
+      const int s = it % NA, acc = it % NACC;
+      mbar_wait(&afull[s], (uint32_t)(it / NA) & 1u);
+      if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
+      const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
+      const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
+      for (int c = 0; c < nchunks; ++c, ++g) {
+        const int ws = (int)(g % NW);
+        mbar_wait(&wfull[ws], (uint32_t)(g / NW) & 1u);
+        tc_fence_after_sync();
+        if (lane == 0) {
+          const uint64_t b0 = umma_desc(smem_u32(sW + (size_t)ws * TC_WSTAGE_BYTES), (uint32_t)Cout * 16, 128);
+          const int first = c * chunk_slices, cnt = min(chunk_slices, total_slices - first);
+          for (int i = 0; i < cnt; ++i) {
+            const int slice = first + i;
+            const int tap = slice / k16n, j = slice - tap * k16n;
+            const int ky = tap / K, kx = tap - ky * K;
+            umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(i * (slice_bytes >> 4)), idesc,
+                      slice > 0 ? 1u : 0u);
+          }
+          umma_commit(&wempty[ws]);
+          if (c == nchunks - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ weight streamer (warp 5, one lane)
+    // cp.async.bulk (TMA 1-D bulk copy): one instruction per 16 KB stage, completion counted in bytes on the
+    // stage's mbarrier, written through the async proxy (no generic->async fence needed), NW stages in flight.
+    if (lane == 0) {
+      const long long G = (long long)T * nchunks;
+      const uint32_t chunk_bytes = (uint32_t)chunk_slices * slice_bytes;
+      const uint32_t sW_addr = smem_u32(sW);
+      for (long long g = 0; g < G; ++g) {
+        const int ws = (int)(g % NW), c = (int)(g % nchunks);
+        if (g >= NW) mbar_wait(&wempty[ws], (uint32_t)((g / NW) - 1) & 1u);
+        const int cnt = min(chunk_slices, total_slices - c * chunk_slices);
+        const uint32_t bytes = (uint32_t)cnt * slice_bytes;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wp) + (size_t)c * chunk_bytes;
+        const uint32_t bar = smem_u32(&wfull[ws]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sW_addr + (uint32_t)ws * TC_WSTAGE_BYTES), "l"(src), "r"(bytes), "r"(bar) : "memory");
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+template <int K, int NA>
+static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* bias, void* y, int out_f32, int H, int W,
+                                    int Cin, int Cout, int up, long long tiles, cudaStream_t st) {
+  const int halo = K / 2, HP = (TC_TW + 2 * halo) * (TC_TH + 2 * halo);
+  const int smem = NA * (Cin / 8) * HP * 16 + 4 * TC_WSTAGE_BYTES + 256;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_ws_kernel<K, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int chunk_slices = TC_WSTAGE_BYTES / (Cout * 32);
+  if (chunk_slices < 1) chunk_slices = 1;
+  const int cols = (int)tmem_cols_for(2 * Cout);
+  long long grid = ttg_num_sms();
+  if (grid > tiles) grid = tiles;
+  conv_tc_stream_ws_kernel<K, NA><<<(unsigned)grid, 192, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
+                                                                    Cout, up, (int)tiles, cols, chunk_slices);
+  TTG_CHECK_LAUNCH("conv2d_tc_stream_ws");
+  return TTG_OK;
+}
+
 static int g_conv_tc_smem[2] = {0, 0};
 
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
@@ -602,6 +762,15 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
     if (ksize == 3) return nbuf == 4 ? TTG_PERSIST(3, 4) : nbuf == 3 ? TTG_PERSIST(3, 3) : TTG_PERSIST(3, 2);
     return nbuf == 4 ? TTG_PERSIST(1, 4) : nbuf == 3 ? TTG_PERSIST(1, 3) : TTG_PERSIST(1, 2);
 #undef TTG_PERSIST
+  }
+  if (!pre_scale && Cout * 32 <= TC_WSTAGE_BYTES) {
+    const int a_bytes = (Cin / 8) * HP * 16;
+    const bool two = 2 * a_bytes + 4 * TC_WSTAGE_BYTES + 256 <= 200 * 1024;
+    const int of32 = dtype_out == TTG_F32;
+    if (ksize == 3) return two ? launch_conv_tc_stream_ws<3, 2>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st)
+                               : launch_conv_tc_stream_ws<3, 1>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st);
+    return two ? launch_conv_tc_stream_ws<1, 2>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st)
+               : launch_conv_tc_stream_ws<1, 1>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st);
   }
   const int ki = ksize == 3 ? 1 : 0;
   if (smem > g_conv_tc_smem[ki]) {

@@ -66,4 +66,30 @@ def main():
         med, best = timeit(fn)
         print(f'bn_act_bwd M{m} C{c}: {med*1e3:.1f} us {m*c*10/med/1e6:.0f} GB/s')
 
-main()
+
+
+def iqn(rows_b, c=128, nq=8):
+    """IQN head + quantile-Huber forward/backward at B rows (asymptotic GB/s at >= 2^20 quantile rows)."""
+    b = rows_b
+    feats = torch.randn(b, c, device='cuda'); taus = torch.rand(b * nq, device='cuda')
+    we = torch.randn(c, 20, device='cuda') * .3; be = torch.zeros(c, device='cuda'); wo = torch.randn(c, device='cuda'); bo = torch.zeros(1, device='cuda')
+    p = torch.empty(b * nq, device='cuda'); tgt = torch.ones(b, device='cuda'); loss = torch.empty((), device='cuda')
+    g = torch.randn(b * nq, device='cuda'); gf = torch.empty(b, c, device='cuda')
+    gwe = torch.empty(c, 20, device='cuda'); gbe = torch.empty(c, device='cuda'); gwo = torch.empty(c, device='cuda'); gbo = torch.empty(1, device='cuda')
+    fwd = lambda: (call('ttg_iqn_head_fwd', ptr(feats), ptr(taus), ptr(we), ptr(be), ptr(wo), ptr(bo), ptr(p), None, b, nq, c, 20),
+                   call('ttg_quantile_huber_fwd', ptr(p), ptr(tgt), ptr(taus), ptr(loss), b, nq, 1.0))
+    bwd = lambda: call('ttg_iqn_head_bwd', ptr(g), ptr(feats), ptr(taus), ptr(we), ptr(be), ptr(wo), ptr(gf), ptr(gwe), ptr(gbe), ptr(gwo), ptr(gbo), b, nq, c, 20)
+    # algorithmic bytes: feats read once per quantile row in the unfused reference = rows*C*4; fused kernel reads feats B*C*4 + taus + writes p
+    med, best = timeit(fwd)
+    nb = b * c * 4 + b * nq * 8
+    print(f'iqn_head+huber fwd B={b} nq={nq} C={c}: {med*1e3:.1f} us  fused bytes {nb/1e6:.1f} MB -> {nb/med/1e6:.0f} GB/s; '
+          f'unfused reference traffic (x.repeat + emb + mix) {(3*b*nq*c*4)/1e6:.0f} MB -> equivalent {(3*b*nq*c*4)/med/1e6:.0f} GB/s')
+    med, best = timeit(bwd)
+    nb = 2 * b * c * 4 + b * nq * 8
+    print(f'iqn_head bwd B={b}: {med*1e3:.1f} us  {nb/med/1e6:.0f} GB/s (fused bytes)')
+
+
+if sys.argv[1] == 'iqn':
+    iqn(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128)
+else:
+    main()
