@@ -551,6 +551,166 @@ static int launch_conv_tc_persist(const void* x, const void* wp, const float* bi
 
 #define TC_RESIDENT_W_BYTES (80 * 1024)
 
+// ------------------------------------------------------------------ fprop / dgrad, TMA-fed (weights resident)
+// Same pipeline as conv_tc_persist_kernel, but the activation halo tile is fetched by ONE
+// cp.async.bulk.tensor (TMA) instruction per tile: a rank-5 tensor map over the NHWC tensor viewed as
+// (8 channels, W, C/8, H, N) with box (8, WH, C/8, HH, 1) lands in shared memory exactly as the
+// [halo row][channel group][halo col] x 16 B image the UMMA descriptors expect, zero-filled outside the
+// image (the conv padding), completion counted in bytes on the slot's mbarrier.  warp 5 = TMA producer,
+// warp 4 = MMA issuer, warps 0-3 = epilogue only.
+#include <cuda.h>
+typedef CUresult (*ttg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static ttg_encode_tiled_fn ttg_get_encode_tiled() {
+  static ttg_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (ttg_encode_tiled_fn)p;
+  }
+  return fn;
+}
+
+template <int K, int NBUF>
+__global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
+                                                          const float* __restrict__ bias, void* __restrict__ y, int out_f32,
+                                                          int H, int W, int Cin, int Cout, int total_tiles, int tmem_cols) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  constexpr int LAG = 2, NACC = 4;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k16n = Cin >> 4, c8n = Cin >> 3;
+  const uint32_t slice_bytes = (uint32_t)Cout * 32;
+  const uint32_t w_bytes = (uint32_t)(K * K * k16n) * slice_bytes;
+  const uint32_t a_bytes = (uint32_t)c8n * HP * 16;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + ((w_bytes + 127) & ~127u);                             // NBUF slots, 128-B aligned for TMA
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + NBUF * (size_t)a_bytes);
+  uint64_t* empty = full + NBUF;
+  uint64_t* acc_full = empty + NBUF;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_coords = [&](int j, int& n, int& y0, int& x0) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    n = tile / tiles_img;
+    const int t2 = tile - n * tiles_img;
+    y0 = (t2 / tiles_x) * TC_TH;
+    x0 = (t2 % tiles_x) * TC_TW;
+  };
+
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_fence_init();
+  }
+  if (warp < 4)
+    for (int i = tid; i < (int)(w_bytes / 16); i += 128)
+      reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ epilogue (LAG tiles behind)
+    for (int j = 0; j < T; ++j) {
+      const int acc = j & (NACC - 1);
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      tc_fence_after_sync();
+      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
+    const uint64_t b0 = umma_desc(smem_u32(sW), (uint32_t)Cout * 16, 128);
+    const uint32_t b_step = slice_bytes >> 4;
+    for (int it = 0; it < T; ++it) {
+      const int s = it % NBUF, acc = it & (NACC - 1);
+      mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+      if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
+        const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
+        uint32_t sl = 0;
+#pragma unroll
+        for (int tap = 0; tap < K * K; ++tap) {
+          const int ky = tap / K, kx = tap % K;
+          for (int j = 0; j < k16n; ++j, ++sl)
+            umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (warp 5, one lane)
+    for (int j = 0; j < T; ++j) {
+      const int s = j % NBUF;
+      if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u);
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      const uint32_t bar = smem_u32(&full[s]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a_bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+          ::"r"(smem_u32(sA + (size_t)s * a_bytes)), "l"(&tmap), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
+          : "memory");
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+template <int K, int NBUF>
+static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
+                              int Cin, int Cout, long long tiles, int w_bytes, int a_bytes, int pcols, cudaStream_t st, bool* used) {
+  *used = false;
+  ttg_encode_tiled_fn enc = ttg_get_encode_tiled();
+  if (!enc) return TTG_OK;
+  constexpr int HALO = K / 2;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int per_sm = (200 * 1024) / smem;
+  if (per_sm > 512 / pcols) per_sm = 512 / pcols;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)ttg_num_sms() * per_sm;
+  if (grid > tiles) grid = tiles;
+  conv_tc_tma_kernel<K, NBUF><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
+                                                                pcols);
+  TTG_CHECK_LAUNCH("conv2d_tc_tma");
+  *used = true;
+  return TTG_OK;
+}
+
 // ------------------------------------------------------------------ fprop / dgrad, filters too large for shared memory
 // (128->128, 256->256 ...): persistent, warp-specialised, weights STREAMED.  warps 0-3 stage activation tiles
 // (cp.async, NA slots) and run the epilogue; warp 4 issues tcgen05.mma; warp 5 streams the packed filter from L2
@@ -712,6 +872,8 @@ static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* 
 }
 
 static int g_conv_tc_smem[2] = {0, 0};
+static int g_use_tma = 1;
+extern "C" int ttg_set_use_tma(int on) { g_use_tma = on; return TTG_OK; }
 
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
 // tensors in memory (equal to Cin / Cout except for the RGB layers).
@@ -754,6 +916,15 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     const int of32 = dtype_out == TTG_F32;
+    if (!padded && !pre_scale && up == 0 && g_use_tma) {
+      bool used = false;
+      const int tcols = (int)tmem_cols_for(4 * Cout);
+      const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
+#define TTG_TMA(KK, NB) launch_conv_tc_tma<KK, NB>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, tiles, w_bytes, a_bytes, tcols, st, &used)
+      const int rc = ksize == 3 ? (deep ? TTG_TMA(3, 4) : TTG_TMA(3, 3)) : (deep ? TTG_TMA(1, 4) : TTG_TMA(1, 3));
+#undef TTG_TMA
+      if (rc != TTG_OK || used) return rc;
+    }
     const bool lean = !padded && !pre_scale && (TC_TW + 2 * halo) * (Cin / 8) <= 128;
 #define TTG_PERSIST(KK, NB) (lean ? launch_conv_tc_persist<KK, NB, true>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, \
                                         pre_shift, slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st)              \

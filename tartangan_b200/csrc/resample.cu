@@ -129,35 +129,40 @@ __device__ __forceinline__ int bil_candidates(int i, int in, int out, int* oidx,
   }
   return cnt;
 }
+// one thread per input pixel: the (<= 3 x 3) contributing outputs and their weights are found once,
+// then every channel vector of the pixel is gathered with them
 template <typename T, int V>
 __global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N, int Hi, int Wi, int C) {
   const int cv = C / V; const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long total = (long long)N * Hi * Wi * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % cv) * V; long long p = i / cv;
-    int ix = (int)(p % Wi); p /= Wi; int iy = (int)(p % Hi); int n = (int)(p / Hi);
+  const long long total = (long long)N * Hi * Wi;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(p % Wi); const long long q = p / Wi; const int iy = (int)(q % Hi); const int n = (int)(q / Hi);
     int oys[4], oxs[4]; float wys[4], wxs[4];
-    int ny = bil_candidates(iy, Hi, Ho, oys, wys), nx = bil_candidates(ix, Wi, Wo, oxs, wxs);
-    float acc[V];
+    const int ny = bil_candidates(iy, Hi, Ho, oys, wys), nx = bil_candidates(ix, Wi, Wo, oxs, wxs);
+    const T* gbase = gy + (long long)n * Ho * Wo * C;
+    T* dst = gx + p * C;
+    for (int v = 0; v < cv; ++v) {
+      float acc[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) acc[j] = 0.f;
-    for (int a = 0; a < ny; ++a)
-      for (int b = 0; b < nx; ++b) {
-        float w = wys[a] * wxs[b];
-        if (w == 0.f) continue;
-        float g[V];
-        Ld<T, V>::ld(gy + (((long long)n * Ho + oys[a]) * Wo + oxs[b]) * C + c, g);
+      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+      for (int a = 0; a < ny; ++a)
+        for (int b = 0; b < nx; ++b) {
+          const float w = wys[a] * wxs[b];
+          float g[V];
+          Ld<T, V>::ld(gbase + ((long long)oys[a] * Wo + oxs[b]) * C + v * V, g);
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] += w * g[j];
-      }
-    Ld<T, V>::st(gx + (((long long)n * Hi + iy) * Wi + ix) * C + c, acc);
+          for (int j = 0; j < V; ++j) acc[j] += w * g[j];
+        }
+      Ld<T, V>::st(dst + v * V, acc);
+    }
   }
 }
 extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  const long long pixels = (long long)N * Hi * Wi;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Hi * Wi * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
-    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_for((long long)N * Hi * Wi * C, 256), 256, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_for(pixels, 128, 16), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_for(pixels, 128, 16), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
   });
   TTG_CHECK_LAUNCH("bilinear_down_bwd");
   return TTG_OK;
