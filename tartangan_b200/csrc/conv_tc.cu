@@ -14,6 +14,7 @@
 // The epilogue reads the fp32 accumulator from TMEM (tcgen05.ld 32x32b), adds the bias and
 // writes NHWC rows (one thread = one pixel = Cout contiguous channels).
 #include "tc_common.cuh"
+#include <string.h>
 
 #define TC_TH 16
 #define TC_TW 8
@@ -1071,11 +1072,13 @@ __global__ void __launch_bounds__(128) conv_wgrad_tc_kernel(const bf16* __restri
 // For Cin <= 80 a unit is a filter column kx with N = 3*Cin: the [row][c8][col] tile layout makes the
 // three vertical taps one uniform-stride B operand, so gy^T (the A operand, mostly padding rows for
 // small Cout) is read 3 instead of 9 times per K step; with Cout <= 64 the MMA uses M = 64.
-template <int K, int NBUF>
-__global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy,
+template <int K, int NBUF, bool TMA>
+__global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gy,
                                                                float* __restrict__ gw, int N, int H, int W, int Cin,
                                                                int Cout, int up, int units_per_group, int fuse,
-                                                               int tmem_cols, int g_bytes, int cin_real, int cout_real) {
+                                                               int tmem_cols, int g_bytes, int cin_real, int cout_real,
+                                                               const __grid_constant__ CUtensorMap tmap_x,
+                                                               const __grid_constant__ CUtensorMap tmap_g) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH, NPIX = TC_TH * TC_TW;
   constexpr int DIST = NBUF > 2 ? NBUF - 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1113,7 +1116,7 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
 
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
-    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 128); mbar_init(&empty[i], (uint32_t)n_issuers); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], TMA ? 1 : 128); mbar_init(&empty[i], (uint32_t)n_issuers); }
     mbar_init(done, (uint32_t)n_issuers);
     mbar_fence_init();
   }
@@ -1159,15 +1162,17 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
       }
       cp_async_commit();
     };
+    if constexpr (!TMA) {
 #pragma unroll
-    for (int d = 0; d < DIST; ++d) stage(d);
-    for (int it = 0; it < T; ++it) {
-      stage(it + DIST);
-      cp_async_wait_group<DIST>();
-      fence_proxy_async_smem();
-      mbar_arrive(&full[it % NBUF]);
+      for (int d = 0; d < DIST; ++d) stage(d);
+      for (int it = 0; it < T; ++it) {
+        stage(it + DIST);
+        cp_async_wait_group<DIST>();
+        fence_proxy_async_smem();
+        mbar_arrive(&full[it % NBUF]);
+      }
+      cp_async_wait_all();
     }
-    cp_async_wait_all();
     if (T > 0) {
       mbar_wait(done, 0);
       tc_fence_after_sync();
@@ -1220,6 +1225,25 @@ __global__ void __launch_bounds__(224) conv_wgrad_tc_ws_kernel(const bf16* __res
       }
       __syncwarp();
     }
+  } else if (TMA && warp == 7 && lane == 0) {
+    // ---- TMA producer: one tensor-map load for the x halo tile, one for the gy tile, per slot
+    for (int j = 0; j < T; ++j) {
+      const int s = j % NBUF;
+      if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u);
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      const uint32_t bar = smem_u32(&full[s]);
+      const uint32_t gbytes_tile = (uint32_t)g8n * NPIX * 16;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + gbytes_tile) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+          ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
+          : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+          ::"r"(smem_u32(sG + (size_t)s * g_bytes)), "l"(&tmap_g), "r"(0), "r"(x0), "r"(y0), "r"(co_base >> 3), "r"(n), "r"(bar)
+          : "memory");
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -1230,14 +1254,41 @@ template <int K, int NBUF>
 static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int up,
                            int upg, int fuse, int cols, int g_bytes, int smem, dim3 grid, int cin_real, int cout_real,
                            cudaStream_t st) {
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_ws_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
-    smem_set = smem;
+  constexpr int HALO = K / 2;
+  CUtensorMap tx, tg;
+  memset(&tx, 0, sizeof(tx)); memset(&tg, 0, sizeof(tg));
+  bool tma = g_use_tma && up == 0 && cin_real == Cin && cout_real == Cout;
+  ttg_encode_tiled_fn enc = tma ? ttg_get_encode_tiled() : nullptr;
+  if (!enc) tma = false;
+  if (tma) {
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t xd[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t xs[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t xb[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    const int g8n = (Cout < 128 ? Cout : 128) / 8;
+    const cuuint64_t gd[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 8), (cuuint64_t)N};
+    const cuuint64_t gs[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, 16, (cuuint64_t)H * W * Cout * 2};
+    const cuuint32_t gb[5] = {8, TC_TW, TC_TH, (cuuint32_t)g8n, 1};
+    CUresult r1 = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xd, xs, xb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(gy), gd, gs, gb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+      return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
   }
-  conv_wgrad_tc_ws_kernel<K, NBUF><<<grid, 224, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
-                                                           fuse, cols, g_bytes, cin_real, cout_real);
+  static int smem_set[2] = {0, 0};
+  if (smem > smem_set[tma ? 1 : 0]) {
+    cudaError_t e = tma ? cudaFuncSetAttribute(conv_wgrad_tc_ws_kernel<K, NBUF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : cudaFuncSetAttribute(conv_wgrad_tc_ws_kernel<K, NBUF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set[tma ? 1 : 0] = smem;
+  }
+  if (tma)
+    conv_wgrad_tc_ws_kernel<K, NBUF, true><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
+                                                                   fuse, cols, g_bytes, cin_real, cout_real, tx, tg);
+  else
+    conv_wgrad_tc_ws_kernel<K, NBUF, false><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
+                                                                    fuse, cols, g_bytes, cin_real, cout_real, tx, tg);
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc_ws");
   return TTG_OK;
 }
