@@ -1094,14 +1094,18 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
   uint64_t* done = empty + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
+  // fuse == 2: SWAPPED orientation for narrow inputs (3*Cin <= 128): A = shifted x with M = (ky, ci) rows,
+  // B = gy^T with N = Cout, one unit per filter column kx.  The 128-row MMA floor is then filled with
+  // 3*Cin useful rows instead of Cout, which cuts the tensor-pipe time of the 16/32-channel layers 3x.
+  const bool swapped = fuse == 2;
   const int units_total = fuse ? K : K * K;
-  const int NU = fuse ? K * Cin : Cin;                  // accumulator columns per unit
+  const int NU = swapped ? Cout : (fuse ? K * Cin : Cin);     // accumulator columns per unit
   const int unit0 = blockIdx.y * units_per_group;
   const int nunits = min(units_per_group, units_total - unit0);
   const int n_issuers = min(3, nunits);
   const int co_base = blockIdx.z * 128;
   const int co_cnt = min(128, Cout - co_base);
-  const bool m64 = Cout <= 64;
+  const bool m64 = swapped ? (K * Cin <= 64) : (Cout <= 64);
   const int g8n = co_cnt >> 3;
   const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
   const int total_tiles = N * tiles_img;
@@ -1178,7 +1182,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       tc_fence_after_sync();
       // accumulator row -> TMEM lane: M=128: row = lane; M=64: rows 16w..16w+15 live in lanes 32w..32w+15
       const int row = m64 ? (warp * 16 + lane) : tid;
-      const bool valid = (m64 ? lane < 16 : true) && row < co_cnt;
+      const bool valid = (m64 ? lane < 16 : true) && row < (swapped ? K * Cin : co_cnt);
       const int co = co_base + row;
       for (int t = 0; t < nunits; ++t) {
         const int u = unit0 + t;
@@ -1186,7 +1190,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NU + c0), r);
           tmem_ld_wait();
-          if (valid) {
+          if (valid && swapped) {                     // row = ky*Cin + ci, column = output channel, unit = kx
+            const int ky = row / Cin, ci = row - ky * Cin;
+            if (ci < cin_real) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < cout_real)
+                  atomicAdd(gw + ((long long)(co_base + c0 + j) * cin_real + ci) * (K * K) + ky * K + u, __uint_as_float(r[j]));
+            }
+          } else if (valid) {
             const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
             const int tap = fuse ? ky * K + u : u;
             if (co < cout_real) {
@@ -1205,7 +1217,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       const int s = it % NBUF;
       mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
       tc_fence_after_sync();
-      if (lane == 0) {
+      if (lane == 0 && swapped) {
+        // A = shifted x (MN-major): M groups = (ky, c8) WH units apart; B = gy^T (MN-major): N groups = co/8
+        const uint64_t a0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * WH) * 16, WH * 16);
+        const uint64_t b0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
+        for (int t = me; t < nunits; t += 3) {
+          const int kx = unit0 + t;
+          const uint32_t dcol = tmem_base + (uint32_t)(t * NU);
+#pragma unroll
+          for (int r = 0; r < TC_TH / 2; ++r)
+            umma_bf16(dcol, a0 + (uint64_t)(2 * r * c8n * WH + kx), b0 + (uint64_t)(2 * r * TC_TW), idesc,
+                      (it == 0 && r == 0) ? 0u : 1u);
+        }
+        umma_commit(&empty[s]);
+        if (it == T - 1) umma_commit(done);
+      } else if (lane == 0) {
         // A = gy^T (MN-major): channel groups SBO = 128 px x 16 B apart, pixels 16 B apart, rows (8 px) LBO apart
         const uint64_t a0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
         // B = shifted x (MN-major): N groups (c8, and ky when fused) WH units apart, halo rows c8n*WH units apart
@@ -1329,9 +1355,12 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
   if (per_sm < 1) per_sm = 1;
   {
     // persistent warp-specialised variant when at least two (x, gy) slots fit in shared memory
-    const int fuse = (ksize == 3 && 3 * Cin <= 256) ? 1 : 0;
+    // measured: the swapped orientation only pays when the input is wider than the output (32->16: 204 -> 175 us);
+    // for Cin <= Cout the MMA count, not the MMA shape, is what bounds these narrow layers
+    const bool swap_ok = ksize == 3 && 3 * Cin <= 128 && Cout <= 128 && Cin > Cout;
+    const int fuse = swap_ok ? 2 : ((ksize == 3 && 3 * Cin <= 256) ? 1 : 0);
     const int units_total = fuse ? 3 : taps;
-    const int NU = fuse ? 3 * Cin : Cin;
+    const int NU = swap_ok ? Cout : (fuse ? 3 * Cin : Cin);
     int upg = 512 / NU;
     if (upg > units_total) upg = units_total;
     const int wgroups = (units_total + upg - 1) / upg;
@@ -1339,7 +1368,9 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
     const int wcols = (int)tmem_cols_for(upg * NU);
     const int x_bytes = (Cin / 8) * HP * 16;
     const int g_bytes = ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
-    const int reach = (Cout <= 64 ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
+    const int reach = swap_ok ? 0 : (Cout <= 64 ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
+    // swapped orientation: the padding rows of the A operand (ky = 3) reach one halo row past the last x slot
+    const int xpad = swap_ok ? 2 * (Cin / 8) * (TC_TW + 2 * halo) * 16 : 0;
     int nbuf = (200 * 1024 - reach) / (x_bytes + g_bytes);
     if (nbuf > 4) nbuf = 4;
     if (nbuf >= 2) {
@@ -1347,7 +1378,7 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
       int body = nbuf * (x_bytes + g_bytes);
       const int need = (nbuf - 1) * g_bytes + reach;
       if (body < need) body = need;
-      const int wsmem = body + 256;
+      const int wsmem = body + xpad + 256;
       if (wper_sm > (220 * 1024) / wsmem) wper_sm = (220 * 1024) / wsmem;
       if (wper_sm > 4) wper_sm = 4;
       if (wper_sm < 1) wper_sm = 1;
