@@ -12,7 +12,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'ttg_b200.h')
-LIB_PATH = os.path.join(_HERE, 'lib', 'libttg_b200.so')
+LIB_PATH = os.environ.get('TTG_B200_LIB') or os.path.join(_HERE, 'lib', 'libttg_b200.so')
 
 F32, BF16 = 0, 1
 _DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16}

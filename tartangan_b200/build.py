@@ -12,6 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libttg_b200.so')
+# development only: extra -D flags / alternative output (variant builds for A/B kernel timing)
+EXTRA_DEFS = os.environ.get('TTG_BUILD_DEFS', '').split()
+VARIANT = os.environ.get('TTG_BUILD_VARIANT', '')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -36,7 +39,7 @@ def is_stale():
 
 
 def _compile_one(src, obj, verbose):
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-c', src, '-o', obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + EXTRA_DEFS + ['-c', src, '-o', obj]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -47,10 +50,11 @@ def _compile_one(src, obj, verbose):
 
 def build(force=False, verbose=False):
     """Compile every csrc/*.cu for sm_100a and link the shared library."""
-    if not force and not is_stale():
+    lib_path = LIB_PATH if not VARIANT else LIB_PATH[:-3] + '_' + VARIANT + '.so'
+    if not VARIANT and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, 'build')
+    obj_dir = os.path.join(HERE, 'build' + ('_' + VARIANT if VARIANT else ''))
     os.makedirs(obj_dir, exist_ok=True)
     srcs = sources()
     hdr_t = max([os.path.getmtime(p) for p in glob.glob(os.path.join(CSRC, '*.cuh'))] + [0])
@@ -65,10 +69,10 @@ def build(force=False, verbose=False):
             log = j.result()
             if verbose and log:
                 print(log)
-    r = subprocess.run([_nvcc(), '-shared', '-o', LIB_PATH] + objs, capture_output=True, text=True)
+    r = subprocess.run([_nvcc(), '-shared', '-o', lib_path] + objs, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == '__main__':

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
       mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
       if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
       tc_fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const int c8n = Cin >> 3;
         const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
         const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
@@ -577,7 +577,8 @@ static ttg_encode_tiled_fn ttg_get_encode_tiled() {
 template <int K, int NBUF>
 __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
-                                                          int H, int W, int Cin, int Cout, int total_tiles, int tmem_cols) {
+                                                          int H, int W, int Cin, int Cout, int total_tiles, int tmem_cols,
+                                                          int mode) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   constexpr int LAG = 2, NACC = 4;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -627,6 +628,23 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       tile_coords(j, n, y0, x0);
       mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
       tc_fence_after_sync();
+      if (mode == 1) {       // TIMING EXPERIMENT: stores as a [N][H][C/8][W][8] layout would issue them
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * Cout);
+        const int gy = y0 + (tid >> 3), gx = x0 + (tid & 7);
+        for (int c0 = 0; c0 < Cout; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (gy < H && gx < W) {
+            uint4 o[2];
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            uint4* dst = reinterpret_cast<uint4*>(y) + (((long long)n * H + gy) * (Cout >> 3) + (c0 >> 3)) * W + gx;
+            dst[0] = o[0]; dst[W] = o[1];
+          }
+        }
+      } else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
@@ -641,7 +659,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
       if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
       tc_fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
         const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
         uint32_t sl = 0;
@@ -656,7 +674,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ------------------------------------------------------------ TMA producer (warp 5, one lane)
     for (int j = 0; j < T; ++j) {
       const int s = j % NBUF;
@@ -665,9 +683,15 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       tile_coords(j, n, y0, x0);
       const uint32_t bar = smem_u32(&full[s]);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a_bytes) : "memory");
+      if (mode == 0)
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
           ::"r"(smem_u32(sA + (size_t)s * a_bytes)), "l"(&tmap), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
+          : "memory");
+      else
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+          ::"r"(smem_u32(sA + (size_t)s * a_bytes)), "l"(&tmap), "r"(mode == 1 ? (x0 - HALO) * 8 : 0), "r"(mode == 1 ? 0 : x0 - HALO), "r"(y0 - HALO), "r"(n), "r"(bar)
           : "memory");
     }
   }
@@ -676,6 +700,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
+static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
 template <int K, int NBUF>
 static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
                               int Cin, int Cout, long long tiles, int w_bytes, int a_bytes, int pcols, cudaStream_t st, bool* used) {
@@ -688,7 +713,22 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+  CUresult r;
+  const int mode = g_use_tma - 1;
+  if (mode == 1) {
+    const cuuint64_t d4[4] = {(cuuint64_t)W * 8, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t s4[3] = {(cuuint64_t)W * 16, (cuuint64_t)(Cin / 8) * W * 16, (cuuint64_t)H * (Cin / 8) * W * 16};
+    const cuuint32_t b4[4] = {(cuuint32_t)(TC_TW + 2 * HALO) * 8, (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), d4, s4, b4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (mode == 2) {
+    const cuuint64_t d4[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t s4[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t b4[4] = {(cuuint32_t)Cin, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), d4, s4, b4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else
+  r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -706,7 +746,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
   conv_tc_tma_kernel<K, NBUF><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
-                                                                pcols);
+                                                                pcols, mode);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
   return TTG_OK;
@@ -797,51 +837,63 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
-    long long g = 0;
+    const uint32_t sl_units = slice_bytes >> 4;
+    uint32_t g = 0;
     for (int it = 0; it < T; ++it) {
       const int s = it % NA, acc = it % NACC;
       mbar_wait(&afull[s], (uint32_t)(it / NA) & 1u);
       if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
       const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
       const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
+      // (tap, k16) walk kept incrementally: no division in the issue loop
+      int j = 0, kx = 0;
+      uint32_t a_row = 0;                 // ky * c8n * WH
+      uint32_t accum = 0;
+      int left = total_slices;
       for (int c = 0; c < nchunks; ++c, ++g) {
-        const int ws = (int)(g % NW);
-        mbar_wait(&wfull[ws], (uint32_t)(g / NW) & 1u);
+        const uint32_t ws = g & (NW - 1);
+        mbar_wait(&wfull[ws], (g / NW) & 1u);
         tc_fence_after_sync();
-        if (lane == 0) {
-          const uint64_t b0 = umma_desc(smem_u32(sW + (size_t)ws * TC_WSTAGE_BYTES), (uint32_t)Cout * 16, 128);
-          const int first = c * chunk_slices, cnt = min(chunk_slices, total_slices - first);
+        {
+          // every lane walks the (tap, k16) indices (they are warp-uniform); one elected lane issues
+          uint64_t b = umma_desc(smem_u32(sW + (size_t)ws * TC_WSTAGE_BYTES), (uint32_t)Cout * 16, 128);
+          const int cnt = min(chunk_slices, left);
+          const bool leader = elect_one();
           for (int i = 0; i < cnt; ++i) {
-            const int slice = first + i;
-            const int tap = slice / k16n, j = slice - tap * k16n;
-            const int ky = tap / K, kx = tap - ky * K;
-            umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(i * (slice_bytes >> 4)), idesc,
-                      slice > 0 ? 1u : 0u);
+            if (leader) umma_bf16(dacc, a0 + (uint64_t)(a_row + (uint32_t)kx + (uint32_t)(2 * j * WH)), b, idesc, accum);
+            accum = 1u;
+            b += sl_units;
+            if (++j == k16n) { j = 0; if (++kx == K) { kx = 0; a_row += (uint32_t)(c8n * WH); } }
           }
-          umma_commit(&wempty[ws]);
-          if (c == nchunks - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+          if (leader) {
+            umma_commit(&wempty[ws]);
+            if (c == nchunks - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+          }
         }
         __syncwarp();
+        left -= chunk_slices;
       }
     }
   } else {
     // ------------------------------------------------------------ weight streamer (warp 5, one lane)
     // cp.async.bulk (TMA 1-D bulk copy): one instruction per 16 KB stage, completion counted in bytes on the
     // stage's mbarrier, written through the async proxy (no generic->async fence needed), NW stages in flight.
-    if (lane == 0) {
-      const long long G = (long long)T * nchunks;
+    if (elect_one()) {
+      const uint32_t G = (uint32_t)T * (uint32_t)nchunks;
       const uint32_t chunk_bytes = (uint32_t)chunk_slices * slice_bytes;
+      const uint32_t last_bytes = (uint32_t)(total_slices - (nchunks - 1) * chunk_slices) * slice_bytes;
       const uint32_t sW_addr = smem_u32(sW);
-      for (long long g = 0; g < G; ++g) {
-        const int ws = (int)(g % NW), c = (int)(g % nchunks);
-        if (g >= NW) mbar_wait(&wempty[ws], (uint32_t)((g / NW) - 1) & 1u);
-        const int cnt = min(chunk_slices, total_slices - c * chunk_slices);
-        const uint32_t bytes = (uint32_t)cnt * slice_bytes;
+      int c = 0;
+      for (uint32_t g = 0; g < G; ++g) {
+        const uint32_t ws = g & (NW - 1);
+        if (g >= NW) mbar_wait(&wempty[ws], ((g / NW) - 1) & 1u);
+        const uint32_t bytes = c == nchunks - 1 ? last_bytes : chunk_bytes;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wp) + (size_t)c * chunk_bytes;
         const uint32_t bar = smem_u32(&wfull[ws]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(sW_addr + (uint32_t)ws * TC_WSTAGE_BYTES), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                     ::"r"(sW_addr + ws * TC_WSTAGE_BYTES), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        if (++c == nchunks) c = 0;
       }
     }
   }
@@ -873,7 +925,6 @@ static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* 
 }
 
 static int g_conv_tc_smem[2] = {0, 0};
-static int g_use_tma = 1;
 extern "C" int ttg_set_use_tma(int on) { g_use_tma = on; return TTG_OK; }
 
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the

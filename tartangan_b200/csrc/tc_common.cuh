@@ -4,21 +4,43 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp; unlike `lane == 0`, ptxas knows the region is single-threaded, so the
+// descriptors stay in uniform registers and no divergence-handling loop is wrapped around UTCHMMA / UTMALDG.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// TTG_MBAR_SUSPEND_NS > 0 adds a suspend-time hint to try_wait (ptxas then emits SYNCS.PHASECHK + NANOSLEEP);
+// 0 (default) uses the plain form (SYNCS.PHASECHK.TRYWAIT: the hardware parks the warp until the phase flips).
+#ifndef TTG_MBAR_SUSPEND_NS
+#define TTG_MBAR_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  // suspend-time hint: the warp sleeps in hardware (up to ~1 us) instead of spinning on issue slots
+#if TTG_MBAR_SUSPEND_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TTG_MBAR_SUSPEND_NS)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU box.
