@@ -18,6 +18,14 @@
 
 #define TC_TH 16
 #define TC_TW 8
+
+// compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
+#include <type_traits>
+#include <utility>
+template <int... Is, typename F>
+__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F&& f) { (f(std::integral_constant<int, Is>{}), ...); }
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) { static_for_impl(std::make_integer_sequence<int, N>{}, f); }
 #define TC_STAGE_BYTES (32 * 1024)
 
 // ------------------------------------------------------------------ weight packing
@@ -392,6 +400,56 @@ __device__ __forceinline__ void conv_tc_epilogue(uint32_t tacc, int warp, int ti
   }
 }
 
+// Coalescing epilogue (bf16 NHWC output, Cout a multiple of 16): every warp stages its 32 pixels x (<= 64 channels)
+// in a private, padded shared-memory strip and writes it back with consecutive lanes on consecutive 16-byte units,
+// so a store instruction covers whole 32-byte sectors / 128-byte lines instead of 16 B out of every pixel.
+//   strip pitch = chunk bytes + 16  ->  both the pixel-major writes and the unit-major reads are conflict free.
+#define TC_EPI_CHUNK 64
+static inline int tc_epi_bytes(int Cout) { return 4 * 32 * ((Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK) * 2 + 16); }
+__device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_t* sE, int warp, int lane, int n, int y0, int x0,
+                                                           int H, int W, int Cout, const float* __restrict__ bias,
+                                                           bf16* __restrict__ y) {
+  const int cc = Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK;     // channels per chunk (16, 32, 48 or 64)
+  const int upp = cc >> 3;                                       // 16-byte units per pixel in a chunk
+  const int pitch = cc * 2 + 16;
+  uint8_t* strip = sE + (size_t)warp * 32 * pitch;
+  const uint32_t strip_addr = smem_u32(strip);
+  for (int c0 = 0; c0 < Cout; c0 += cc) {
+    const int ccur = min(cc, Cout - c0);
+    for (int c1 = 0; c1 < ccur; c1 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + c1), r);
+      tmem_ld_wait();
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
+        if (bias) { f0 += bias[c0 + c1 + 2 * j]; f1 += bias[c0 + c1 + 2 * j + 1]; }
+        __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+        o[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      const uint32_t d = strip_addr + (uint32_t)(lane * pitch + c1 * 2);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 16), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+    }
+    __syncwarp();
+    const int up_cur = ccur >> 3;
+    const int units = 32 * up_cur;
+    const int sh = (up_cur & (up_cur - 1)) == 0 ? __ffs(up_cur) - 1 : -1;
+    for (int u = lane; u < units; u += 32) {
+      const int p = sh >= 0 ? (u >> sh) : u / up_cur, j = u - p * up_cur;
+      const int gy = y0 + warp * 4 + (p >> 3), gx = x0 + (p & 7);
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(strip_addr + (uint32_t)(p * pitch + j * 16)));
+      if (gy < H && gx < W)
+        *reinterpret_cast<uint4*>(y + (((long long)n * H + gy) * W + gx) * Cout + c0 + j * 8) = v;
+    }
+    __syncwarp();
+  }
+  (void)upp;
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -485,6 +543,10 @@ __global__ void __launch_bounds__(160) conv_tc_persist_kernel(const bf16* __rest
       tile_coords(j, n, y0, x0);
       mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
       tc_fence_after_sync();
+      if (!out_f32 && (LEAN || cout_real == Cout))
+        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
+                                   Cout, bias, reinterpret_cast<bf16*>(y));
+      else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32, LEAN ? 0 : cout_real);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
@@ -644,7 +706,10 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
             dst[0] = o[0]; dst[W] = o[1];
           }
         }
-      } else
+      } else if (!out_f32)
+        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
+                                   Cout, bias, reinterpret_cast<bf16*>(y));
+      else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
@@ -732,7 +797,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256;
+  const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256 + tc_epi_bytes(Cout);
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -757,23 +822,77 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
 // (cp.async, NA slots) and run the epilogue; warp 4 issues tcgen05.mma; warp 5 streams the packed filter from L2
 // through a ring of NW 16 KB stages (cp.async) for every tile.  These layers are tensor/L2 bound, not HBM bound.
 #define TC_WSTAGE_BYTES (16 * 1024)
-template <int K, int NA>
+#ifdef TTG_TRACE
+// development build only: per-event clock64() stamps of CTA 0 (role, index, t0, t1)
+__device__ long long ttg_trace_buf[16 * 256 * 2];
+__device__ __forceinline__ void ttg_trace(int role, int idx, long long t0, long long t1) {
+  if (blockIdx.x != 0 || idx >= 256) return;
+  ttg_trace_buf[(role * 256 + idx) * 2] = t0;          // fire-and-forget stores: no round trip in the traced path
+  ttg_trace_buf[(role * 256 + idx) * 2 + 1] = t1;
+}
+extern "C" int ttg_trace_read(long long* host, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host, ttg_trace_buf, sizeof(ttg_trace_buf));
+  if (reset) { static long long z[16 * 256 * 2]; cudaMemcpyToSymbol(ttg_trace_buf, z, sizeof(z)); }
+  return 16 * 256;
+}
+#define TTG_T0() long long t0__ = clock64()
+#define TTG_T1(role, idx) ttg_trace(role, idx, t0__, clock64())
+#else
+#define TTG_T0()
+#define TTG_T1(role, idx)
+#endif
+// accumulate flag as an immediate: with compile-time channel counts every descriptor of a tile is base + constant
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+
+// One chunk (= one weight stage) of the statically unrolled MMA sequence of a 3x3 tile.
+template <int CIN, int COUT, int CHUNK, int C, int I = 0>
+__device__ __forceinline__ void stream_issue_chunk(uint32_t dacc, uint64_t a0, uint64_t b, uint32_t idesc) {
+  constexpr int K16N = CIN / 16, C8N = CIN / 8, WH = TC_TW + 2, TOTAL = 9 * K16N;
+  constexpr int slice = C * CHUNK + I;
+  if constexpr (I < CHUNK && slice < TOTAL) {
+    constexpr int tap = slice / K16N, j = slice % K16N, ky = tap / 3, kx = tap % 3;
+    constexpr uint32_t aoff = (uint32_t)(ky * C8N * WH + kx + 2 * j * WH);
+    umma_bf16_imm<(slice > 0)>(dacc, a0 + (uint64_t)aoff, b + (uint64_t)(I * (COUT * 32 / 16)), idesc);
+    stream_issue_chunk<CIN, COUT, CHUNK, C, I + 1>(dacc, a0, b, idesc);
+  }
+}
+
+// CIN / COUT > 0: 3x3 layer with compile-time channel counts (lean, fully unrolled issue sequence);
+// CIN == 0: any supported layer, runtime walk.
+template <int K, int NA, bool TMA_A, int CIN, int COUT>
 __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
                                                                 const float* __restrict__ bias, void* __restrict__ y,
-                                                                int out_f32, int H, int W, int Cin, int Cout, int up,
-                                                                int total_tiles, int tmem_cols, int chunk_slices) {
+                                                                int out_f32, int H, int W, int Cin_rt, int Cout_rt, int up,
+                                                                int total_tiles, int tmem_cols, int chunk_slices_rt,
+                                                                const __grid_constant__ CUtensorMap tmap) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
-  constexpr int NW = 4, WD = NW - 2, NACC = 2;
+  constexpr bool STATIC = CIN > 0;
+  // weight ring: the issuing thread pays ~400 cycles of fixed cost per stage (mbarrier wait, fences, commit), so the
+  // static variant uses 32 KB stages (8 MMAs of 128x128x16 = 512 tensor cycles per stage)
+  constexpr int NW = STATIC ? 3 : 4, WSB = STATIC ? 2 * TC_WSTAGE_BYTES : TC_WSTAGE_BYTES, NACC = 2;
+  constexpr int APIECES = K == 3 ? 6 : 4, AROWS = HH / APIECES;      // activation tile = APIECES tensor-map loads
+  static_assert(!STATIC || K == 3, "static channel counts: 3x3 only");
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cin = STATIC ? CIN : Cin_rt, Cout = STATIC ? COUT : Cout_rt;
   const int k16n = Cin >> 4, c8n = Cin >> 3;
   const int total_slices = K * K * k16n;
+  const int chunk_slices = STATIC ? WSB / (COUT > 0 ? COUT * 32 : 1) : chunk_slices_rt;
   const int nchunks = (total_slices + chunk_slices - 1) / chunk_slices;
   const uint32_t slice_bytes = (uint32_t)Cout * 32;
   const uint32_t a_bytes = (uint32_t)c8n * HP * 16;
   uint8_t* sA = smem;
   uint8_t* sW = smem + (size_t)NA * a_bytes;
-  uint64_t* afull = reinterpret_cast<uint64_t*>(sW + (size_t)NW * TC_WSTAGE_BYTES);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(sW + (size_t)NW * WSB);
   uint64_t* aempty = afull + NA;
   uint64_t* wfull = aempty + NA;
   uint64_t* wempty = wfull + NW;
@@ -792,7 +911,7 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
   };
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
-    for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], 128); mbar_init(&aempty[i], 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], TMA_A ? 1 : 128); mbar_init(&aempty[i], 1); }
     for (int i = 0; i < NW; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     mbar_fence_init();
@@ -818,82 +937,150 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
       const int acc = j % NACC;
       int n, y0, x0;
       tile_coords(j, n, y0, x0);
-      mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      { TTG_T0(); mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u); if (tid == 0) { TTG_T1(5, j); } }
       tc_fence_after_sync();
-      conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
+      TTG_T0();
+      if (!out_f32)
+        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(afull) + 256, warp, lane, n, y0, x0, H, W,
+                                   Cout, bias, reinterpret_cast<bf16*>(y));
+      else
+        conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
+      if (tid == 0) { TTG_T1(6, j); }
     };
-    if (NA > 1) stage(0);
-    for (int it = 0; it < T; ++it) {
-      if (NA > 1) { stage(it + 1); cp_async_wait_group<1>(); }
-      else { stage(it); cp_async_wait_group<0>(); }
-      fence_proxy_async_smem();
-      mbar_arrive(&afull[it % NA]);
-      if (it > 0) epilogue(it - 1);
+    if constexpr (TMA_A) {
+      for (int j = 0; j < T; ++j) epilogue(j);          // tiles arrive by TMA (warp 5)
+    } else {
+      // tile `it` is published BEFORE the loads of tile it+1 are issued, so the MMAs of a tile never wait for
+      // the (instruction-heavy) staging of its successor
+      stage(0);
+      for (int it = 0; it < T; ++it) {
+        cp_async_wait_group<0>();
+        fence_proxy_async_smem();
+        mbar_arrive(&afull[it % NA]);
+        if (NA > 1) stage(it + 1);
+        if (it > 0) epilogue(it - 1);
+        if (NA == 1) stage(it + 1);
+      }
+      if (T > 0) epilogue(T - 1);
+      cp_async_wait_all();
     }
-    if (T > 0) epilogue(T - 1);
-    cp_async_wait_all();
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
+    // The issuing thread is a single in-order instruction stream: every instruction between two UTCHMMAs is
+    // exposed latency, so the static variant folds all descriptor arithmetic into immediates.
     const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
     const uint32_t sl_units = slice_bytes >> 4;
+    const uint64_t bdesc0 = umma_desc(smem_u32(sW), (uint32_t)Cout * 16, 128);
     uint32_t g = 0;
     for (int it = 0; it < T; ++it) {
       const int s = it % NA, acc = it % NACC;
-      mbar_wait(&afull[s], (uint32_t)(it / NA) & 1u);
-      if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
+      { TTG_T0(); mbar_wait(&afull[s], (uint32_t)(it / NA) & 1u); if (lane == 0) { TTG_T1(2, it); } }
+      { TTG_T0(); if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u); if (lane == 0) { TTG_T1(3, it); } }
       const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
       const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
-      // (tap, k16) walk kept incrementally: no division in the issue loop
-      int j = 0, kx = 0;
-      uint32_t a_row = 0;                 // ky * c8n * WH
-      uint32_t accum = 0;
-      int left = total_slices;
-      for (int c = 0; c < nchunks; ++c, ++g) {
-        const uint32_t ws = g & (NW - 1);
-        mbar_wait(&wfull[ws], (g / NW) & 1u);
-        tc_fence_after_sync();
-        {
-          // every lane walks the (tap, k16) indices (they are warp-uniform); one elected lane issues
-          uint64_t b = umma_desc(smem_u32(sW + (size_t)ws * TC_WSTAGE_BYTES), (uint32_t)Cout * 16, 128);
-          const int cnt = min(chunk_slices, left);
-          const bool leader = elect_one();
-          for (int i = 0; i < cnt; ++i) {
-            if (leader) umma_bf16(dacc, a0 + (uint64_t)(a_row + (uint32_t)kx + (uint32_t)(2 * j * WH)), b, idesc, accum);
-            accum = 1u;
-            b += sl_units;
-            if (++j == k16n) { j = 0; if (++kx == K) { kx = 0; a_row += (uint32_t)(c8n * WH); } }
-          }
-          if (leader) {
+      if constexpr (STATIC) {
+        constexpr int CHUNK = WSB / (COUT * 32);
+        static_assert(CHUNK >= 1, "stage smaller than one K slice");
+        constexpr int NCH = (9 * (CIN / 16) + CHUNK - 1) / CHUNK;
+        auto chunk = [&](auto cc) {
+          constexpr int C = decltype(cc)::value;
+          const uint32_t ws = (g + C) % NW;
+          { TTG_T0(); mbar_wait(&wfull[ws], ((g + C) / NW) & 1u); if (lane == 0) { TTG_T1(1, (int)(g + C)); } }
+          tc_fence_after_sync();
+          if (elect_one()) {
+            TTG_T0();
+            stream_issue_chunk<CIN, COUT, CHUNK, C>(dacc, a0, bdesc0 + (uint64_t)(ws * (WSB >> 4)), idesc);
+            TTG_T1(7, (int)(g + C));
+            { TTG_T0();
             umma_commit(&wempty[ws]);
-            if (c == nchunks - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+            if constexpr (C == NCH - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+            TTG_T1(8, (int)(g + C)); }
           }
+          __syncwarp();
+        };
+        static_for<NCH>(chunk);
+        g += NCH;
+      } else {
+        // runtime (tap, k16) walk kept incrementally: no division in the issue loop
+        int j = 0, kx = 0;
+        uint32_t a_row = 0;               // ky * c8n * WH
+        uint32_t accum = 0;
+        int left = total_slices;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t ws = g % NW;
+          mbar_wait(&wfull[ws], (g / NW) & 1u);
+          tc_fence_after_sync();
+          {
+            // every lane walks the indices (they are warp-uniform); one elected lane issues
+            uint64_t b = bdesc0 + (uint64_t)(ws * (WSB >> 4));
+            const int cnt = min(chunk_slices, left);
+            const bool leader = elect_one();
+            for (int i = 0; i < cnt; ++i) {
+              if (leader) umma_bf16(dacc, a0 + (uint64_t)(a_row + (uint32_t)kx + (uint32_t)(2 * j * WH)), b, idesc, accum);
+              accum = 1u;
+              b += sl_units;
+              if (++j == k16n) { j = 0; if (++kx == K) { kx = 0; a_row += (uint32_t)(c8n * WH); } }
+            }
+            if (leader) {
+              umma_commit(&wempty[ws]);
+              if (c == nchunks - 1) { umma_commit(&aempty[s]); umma_commit(&acc_full[acc]); }
+            }
+          }
+          __syncwarp();
+          left -= chunk_slices;
         }
-        __syncwarp();
-        left -= chunk_slices;
       }
     }
   } else {
-    // ------------------------------------------------------------ weight streamer (warp 5, one lane)
-    // cp.async.bulk (TMA 1-D bulk copy): one instruction per 16 KB stage, completion counted in bytes on the
-    // stage's mbarrier, written through the async proxy (no generic->async fence needed), NW stages in flight.
+    // ------------------------------------------------------------ producer (warp 5, one lane)
+    // weights: cp.async.bulk (TMA 1-D bulk copy), one instruction per 16 KB stage, completion counted in bytes on
+    // the stage's mbarrier, NW stages in flight; activation halo tiles (TMA_A): one tensor-map load per tile.
     if (elect_one()) {
       const uint32_t G = (uint32_t)T * (uint32_t)nchunks;
       const uint32_t chunk_bytes = (uint32_t)chunk_slices * slice_bytes;
       const uint32_t last_bytes = (uint32_t)(total_slices - (nchunks - 1) * chunk_slices) * slice_bytes;
       const uint32_t sW_addr = smem_u32(sW);
-      int c = 0;
+      // An activation tile is fetched as APIECES row groups: the TMA engine serves requests in order and a halo tile is
+      // thousands of 16-byte rows, so one big load would stall the weight stream queued behind it.  The pieces of tile
+      // t+1 are slipped in between the weight stages of tile t (all pieces complete_tx on the slot's barrier).
+      auto issue_a_piece = [&](int j, int piece) {
+        const int s = j % NA;
+        int n, y0, x0;
+        tile_coords(j, n, y0, x0);
+        const uint32_t bar = smem_u32(&afull[s]);
+        if (piece == 0) {
+          if (j >= NA) mbar_wait(&aempty[s], (uint32_t)((j / NA) - 1) & 1u);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a_bytes) : "memory");
+        }
+        const uint32_t dst = smem_u32(sA + (size_t)s * a_bytes) + (uint32_t)(piece * AROWS * c8n * WH * 16);
+        asm volatile(
+            "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+            ::"r"(dst), "l"(&tmap), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO + piece * AROWS), "r"(n), "r"(bar)
+            : "memory");
+      };
+      // pieces of the next tile start once the ring has turned over (its slot is then known to be free: NA == 2),
+      // or after the last stage when there is a single activation slot
+      const int c_first = NA > 1 ? min(NW, nchunks - 1) : nchunks - 1;
+      if (TMA_A && T > 0)
+        for (int pc = 0; pc < APIECES; ++pc) issue_a_piece(0, pc);
+      int c = 0, tile = 0, piece = 0;
       for (uint32_t g = 0; g < G; ++g) {
-        const uint32_t ws = g & (NW - 1);
-        if (g >= NW) mbar_wait(&wempty[ws], ((g / NW) - 1) & 1u);
+        const uint32_t ws = g % NW;
+        { TTG_T0(); if (g >= NW) mbar_wait(&wempty[ws], ((g / NW) - 1) & 1u); TTG_T1(4, (int)g); }
         const uint32_t bytes = c == nchunks - 1 ? last_bytes : chunk_bytes;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wp) + (size_t)c * chunk_bytes;
         const uint32_t bar = smem_u32(&wfull[ws]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(sW_addr + ws * TC_WSTAGE_BYTES), "l"(src), "r"(bytes), "r"(bar) : "memory");
-        if (++c == nchunks) c = 0;
+                     ::"r"(sW_addr + ws * WSB), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        if (TMA_A && tile + 1 < T && c >= c_first) {
+          if (piece < APIECES) issue_a_piece(tile + 1, piece++);
+          if (c == nchunks - 1)
+            while (piece < APIECES) issue_a_piece(tile + 1, piece++);
+        }
+        if (++c == nchunks) { c = 0; ++tile; piece = 0; }
       }
     }
   }
@@ -902,24 +1089,45 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
-template <int K, int NA>
-static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* bias, void* y, int out_f32, int H, int W,
+template <int K, int NA, int CIN, int COUT>
+static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
                                     int Cin, int Cout, int up, long long tiles, cudaStream_t st) {
-  const int halo = K / 2, HP = (TC_TW + 2 * halo) * (TC_TH + 2 * halo);
-  const int smem = NA * (Cin / 8) * HP * 16 + 4 * TC_WSTAGE_BYTES + 256;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_stream_ws_kernel<K, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
-    smem_set = smem;
+  constexpr int HALO = K / 2;
+  const int HP = (TC_TW + 2 * HALO) * (TC_TH + 2 * HALO);
+  constexpr int NW = CIN > 0 ? 3 : 4, WSB = CIN > 0 ? 2 * TC_WSTAGE_BYTES : TC_WSTAGE_BYTES;
+  constexpr int APIECES = K == 3 ? 6 : 4;
+  const int smem = NA * (Cin / 8) * HP * 16 + NW * WSB + 256 + tc_epi_bytes(Cout);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  ttg_encode_tiled_fn enc = (g_use_tma && up == 0) ? ttg_get_encode_tiled() : nullptr;
+  if (enc) {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)((TC_TH + 2 * HALO) / APIECES), 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  int chunk_slices = TC_WSTAGE_BYTES / (Cout * 32);
+  static int smem_set[2] = {0, 0};
+  if (smem > smem_set[enc ? 1 : 0]) {
+    cudaError_t e = enc ? cudaFuncSetAttribute(conv_tc_stream_ws_kernel<K, NA, true, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : cudaFuncSetAttribute(conv_tc_stream_ws_kernel<K, NA, false, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    smem_set[enc ? 1 : 0] = smem;
+  }
+  int chunk_slices = WSB / (Cout * 32);
   if (chunk_slices < 1) chunk_slices = 1;
   const int cols = (int)tmem_cols_for(2 * Cout);
   long long grid = ttg_num_sms();
   if (grid > tiles) grid = tiles;
-  conv_tc_stream_ws_kernel<K, NA><<<(unsigned)grid, 192, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin,
-                                                                    Cout, up, (int)tiles, cols, chunk_slices);
+  if (enc)
+    conv_tc_stream_ws_kernel<K, NA, true, CIN, COUT><<<(unsigned)grid, 192, smem, st>>>(
+        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap);
+  else
+    conv_tc_stream_ws_kernel<K, NA, false, CIN, COUT><<<(unsigned)grid, 192, smem, st>>>(
+        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap);
   TTG_CHECK_LAUNCH("conv2d_tc_stream_ws");
   return TTG_OK;
 }
@@ -961,7 +1169,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
   if (w_bytes <= TC_RESIDENT_W_BYTES) {
     const int a_bytes = (Cin / 8) * HP * 16;
     const int nbuf = a_bytes <= 12 * 1024 ? 4 : (a_bytes <= 24 * 1024 ? 3 : 2);
-    const int psmem = w_bytes + nbuf * a_bytes + 256;
+    const int psmem = w_bytes + nbuf * a_bytes + 256 + tc_epi_bytes(Cout);
     const int pcols = (int)tmem_cols_for(4 * Cout);
     int per_sm = (200 * 1024) / psmem;
     if (per_sm > 512 / pcols) per_sm = 512 / pcols;
@@ -988,12 +1196,24 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
   }
   if (!pre_scale && Cout * 32 <= TC_WSTAGE_BYTES) {
     const int a_bytes = (Cin / 8) * HP * 16;
-    const bool two = 2 * a_bytes + 4 * TC_WSTAGE_BYTES + 256 <= 200 * 1024;
+    const bool two = 2 * a_bytes + 4 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 200 * 1024;
     const int of32 = dtype_out == TTG_F32;
-    if (ksize == 3) return two ? launch_conv_tc_stream_ws<3, 2>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st)
-                               : launch_conv_tc_stream_ws<3, 1>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st);
-    return two ? launch_conv_tc_stream_ws<1, 2>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st)
-               : launch_conv_tc_stream_ws<1, 1>(x, wp, bias, y, of32, H, W, Cin, Cout, up, tiles, st);
+#define TTG_STREAM(KK, NAA, CI, CO) launch_conv_tc_stream_ws<KK, NAA, CI, CO>(x, wp, bias, y, of32, N, H, W, Cin, Cout, up, tiles, st)
+    const bool two32 = 2 * a_bytes + 6 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 224 * 1024;
+    const bool one32 = a_bytes + 6 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 224 * 1024;
+    if (ksize == 3 && two32) {
+      if (Cin == 128 && Cout == 128) return TTG_STREAM(3, 2, 128, 128);
+      if (Cin == 128 && Cout == 64) return TTG_STREAM(3, 2, 128, 64);
+      if (Cin == 64 && Cout == 128) return TTG_STREAM(3, 2, 64, 128);
+      if (Cin == 128 && Cout == 256) return TTG_STREAM(3, 2, 128, 256);
+    }
+    if (ksize == 3 && !two32 && one32) {
+      if (Cin == 256 && Cout == 256) return TTG_STREAM(3, 1, 256, 256);
+      if (Cin == 256 && Cout == 128) return TTG_STREAM(3, 1, 256, 128);
+    }
+    if (ksize == 3) return two ? TTG_STREAM(3, 2, 0, 0) : TTG_STREAM(3, 1, 0, 0);
+    return two ? TTG_STREAM(1, 2, 0, 0) : TTG_STREAM(1, 1, 0, 0);
+#undef TTG_STREAM
   }
   const int ki = ksize == 3 ? 1 : 0;
   if (smem > g_conv_tc_smem[ki]) {
