@@ -636,15 +636,37 @@ static ttg_encode_tiled_fn ttg_get_encode_tiled() {
   return fn;
 }
 
-template <int K, int NBUF>
+// accumulate flag as an immediate: with a compile-time input channel count every A descriptor of a tile is base + constant
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// all K*K*CIN/16 MMAs of one tile, statically unrolled (weights resident: B advances by b_step per slice)
+template <int K, int CIN, int SL = 0>
+__device__ __forceinline__ void resident_issue_tile(uint32_t dacc, uint64_t a0, uint64_t b, uint32_t b_step, uint32_t idesc) {
+  constexpr int K16N = CIN / 16, C8N = CIN / 8, WH = TC_TW + 2 * (K / 2);
+  if constexpr (SL < K * K * K16N) {
+    constexpr int tap = SL / K16N, j = SL % K16N, ky = tap / K, kx = tap % K;
+    umma_bf16_imm<(SL > 0)>(dacc, a0 + (uint64_t)(ky * C8N * WH + kx + 2 * j * WH), b, idesc);
+    resident_issue_tile<K, CIN, SL + 1>(dacc, a0, b + b_step, b_step, idesc);
+  }
+}
+
+template <int K, int NBUF, int CIN>
 __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
-                                                          int H, int W, int Cin, int Cout, int total_tiles, int tmem_cols,
+                                                          int H, int W, int Cin_rt, int Cout, int total_tiles, int tmem_cols,
                                                           int mode) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
-  constexpr int LAG = 2, NACC = 4;
+  constexpr int NACC = 4;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Cin = CIN > 0 ? CIN : Cin_rt;
   const int k16n = Cin >> 4, c8n = Cin >> 3;
   const uint32_t slice_bytes = (uint32_t)Cout * 32;
   const uint32_t w_bytes = (uint32_t)(K * K * k16n) * slice_bytes;
@@ -727,12 +749,16 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       if (elect_one()) {
         const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
         const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
-        uint32_t sl = 0;
+        if constexpr (CIN > 0) {
+          resident_issue_tile<K, CIN>(dacc, a0, b0, b_step, idesc);
+        } else {
+          uint32_t sl = 0;
 #pragma unroll
-        for (int tap = 0; tap < K * K; ++tap) {
-          const int ky = tap / K, kx = tap % K;
-          for (int j = 0; j < k16n; ++j, ++sl)
-            umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
+          for (int tap = 0; tap < K * K; ++tap) {
+            const int ky = tap / K, kx = tap % K;
+            for (int j = 0; j < k16n; ++j, ++sl)
+              umma_bf16(dacc, a0 + (uint64_t)((ky * c8n * WH + kx) + 2 * j * WH), b0 + (uint64_t)(sl * b_step), idesc, sl > 0 ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
         umma_commit(&acc_full[acc]);
@@ -766,7 +792,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
 }
 
 static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
-template <int K, int NBUF>
+template <int K, int NBUF, int CIN>
 static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
                               int Cin, int Cout, long long tiles, int w_bytes, int a_bytes, int pcols, cudaStream_t st, bool* used) {
   *used = false;
@@ -800,7 +826,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256 + tc_epi_bytes(Cout);
   static int smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     smem_set = smem;
   }
@@ -810,7 +836,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
-  conv_tc_tma_kernel<K, NBUF><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
+  conv_tc_tma_kernel<K, NBUF, CIN><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
                                                                 pcols, mode);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
@@ -842,17 +868,6 @@ extern "C" int ttg_trace_read(long long* host, int reset) {
 #define TTG_T0()
 #define TTG_T1(role, idx)
 #endif
-// accumulate flag as an immediate: with compile-time channel counts every descriptor of a tile is base + constant
-template <bool ACC>
-__device__ __forceinline__ void umma_bf16_imm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  if constexpr (ACC)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
-  else
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
-}
-
 // One chunk (= one weight stage) of the statically unrolled MMA sequence of a 3x3 tile.
 template <int CIN, int COUT, int CHUNK, int C, int I = 0>
 __device__ __forceinline__ void stream_issue_chunk(uint32_t dacc, uint64_t a0, uint64_t b, uint32_t idesc) {
@@ -1180,8 +1195,12 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
       bool used = false;
       const int tcols = (int)tmem_cols_for(4 * Cout);
       const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
-#define TTG_TMA(KK, NB) launch_conv_tc_tma<KK, NB>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, tiles, w_bytes, a_bytes, tcols, st, &used)
-      const int rc = ksize == 3 ? (deep ? TTG_TMA(3, 4) : TTG_TMA(3, 3)) : (deep ? TTG_TMA(1, 4) : TTG_TMA(1, 3));
+#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, tiles, w_bytes, a_bytes, tcols, st, &used)
+      int rc;
+      if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 4, 16) : Cin == 32 ? TTG_TMA(3, 4, 32) : Cin == 64 ? TTG_TMA(3, 3, 64)
+                                     : (deep ? TTG_TMA(3, 4, 0) : TTG_TMA(3, 3, 0));
+      else rc = Cin == 16 ? TTG_TMA(1, 4, 16) : Cin == 32 ? TTG_TMA(1, 4, 32) : Cin == 64 ? TTG_TMA(1, 3, 64)
+                          : (deep ? TTG_TMA(1, 4, 0) : TTG_TMA(1, 3, 0));
 #undef TTG_TMA
       if (rc != TTG_OK || used) return rc;
     }
