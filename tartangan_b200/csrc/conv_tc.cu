@@ -1468,9 +1468,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       cp_async_wait_all();
     }
     if (T > 0) {
-      mbar_wait(done, 0);
+      { TTG_T0(); mbar_wait(done, 0); if (tid == 0) { TTG_T1(9, 0); } }
       tc_fence_after_sync();
-      // accumulator row -> TMEM lane: M=128: row = lane; M=64: rows 16w..16w+15 live in lanes 32w..32w+15
+      TTG_T0();
+      // accumulator row -> TMEM lane: M=128: row = lane; M=64: rows 16w..16w+15 live in lanes 32w..32w+15.
+      // The partial sums go to a PACKED fp32 image with 16 consecutive accumulator columns contiguous, so a thread
+      // issues four 16-byte vector reductions per TMEM load instead of sixteen scattered scalar atomics:
+      //   normal / fused : gwp[tap][co][ci]      (columns = ci)
+      //   swapped        : gwp[tap][ci][co]      (columns = co)
+      // ttg_wgrad_unpack_kernel turns it into OIHW.
       const int row = m64 ? (warp * 16 + lane) : tid;
       const bool valid = (m64 ? lane < 16 : true) && row < (swapped ? K * Cin : co_cnt);
       const int co = co_base + row;
@@ -1480,34 +1486,38 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NU + c0), r);
           tmem_ld_wait();
-          if (valid && swapped) {                     // row = ky*Cin + ci, column = output channel, unit = kx
+          if (!valid) continue;
+          float* dst;
+          if (swapped) {                              // row = ky*Cin + ci, column = output channel, unit = kx
             const int ky = row / Cin, ci = row - ky * Cin;
-            if (ci < cin_real) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < cout_real)
-                  atomicAdd(gw + ((long long)(co_base + c0 + j) * cin_real + ci) * (K * K) + ky * K + u, __uint_as_float(r[j]));
-            }
-          } else if (valid) {
+            dst = gw + ((long long)(ky * K + u) * Cin + ci) * Cout + co_base + c0;
+          } else {
             const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
             const int tap = fuse ? ky * K + u : u;
-            if (co < cout_real) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (ci0 + j < cin_real) atomicAdd(gw + ((long long)co * cin_real + ci0 + j) * (K * K) + tap, __uint_as_float(r[j]));
-            }
+            dst = gw + ((long long)tap * Cout + co) * Cin + ci0;
           }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3])
+                         : "memory");
         }
       }
+      if (tid == 0) { TTG_T1(10, 0); }
     }
   } else if (warp - 4 < n_issuers) {
     const int me = warp - 4;
     const uint32_t idesc = umma_idesc_bf16(m64 ? 64 : 128, NU, 1, 1);
     for (int it = 0; it < T; ++it) {
       const int s = it % NBUF;
-      mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+      { TTG_T0(); mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u); if (lane == 0 && me == 0) { TTG_T1(11, it); } }
       tc_fence_after_sync();
-      if (lane == 0 && swapped) {
+      TTG_T0();
+      // K steps that only cover rows below the image (tiles taller than an 8x8 feature map) are skipped
+      int n_, y0_, x0_;
+      tile_coords(it, n_, y0_, x0_);
+      const int rmax = min(TC_TH / 2, (H - y0_ + 1) >> 1);
+      const bool leader = elect_one();
+      if (leader && swapped) {
         // A = shifted x (MN-major): M groups = (ky, c8) WH units apart; B = gy^T (MN-major): N groups = co/8
         const uint64_t a0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * WH) * 16, WH * 16);
         const uint64_t b0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
@@ -1516,12 +1526,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
           const uint32_t dcol = tmem_base + (uint32_t)(t * NU);
 #pragma unroll
           for (int r = 0; r < TC_TH / 2; ++r)
-            umma_bf16(dcol, a0 + (uint64_t)(2 * r * c8n * WH + kx), b0 + (uint64_t)(2 * r * TC_TW), idesc,
-                      (it == 0 && r == 0) ? 0u : 1u);
+            if (r < rmax)
+              umma_bf16(dcol, a0 + (uint64_t)(2 * r * c8n * WH + kx), b0 + (uint64_t)(2 * r * TC_TW), idesc,
+                        (it == 0 && r == 0) ? 0u : 1u);
         }
         umma_commit(&empty[s]);
         if (it == T - 1) umma_commit(done);
-      } else if (lane == 0) {
+      } else if (leader) {
         // A = gy^T (MN-major): channel groups SBO = 128 px x 16 B apart, pixels 16 B apart, rows (8 px) LBO apart
         const uint64_t a0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
         // B = shifted x (MN-major): N groups (c8, and ky when fused) WH units apart, halo rows c8n*WH units apart
@@ -1533,19 +1544,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
           const uint64_t bt = b0 + (uint64_t)(ky * c8n * WH + kx);
 #pragma unroll
           for (int r = 0; r < TC_TH / 2; ++r)
-            umma_bf16(dcol, a0 + (uint64_t)(2 * r * TC_TW), bt + (uint64_t)(2 * r * c8n * WH), idesc,
-                      (it == 0 && r == 0) ? 0u : 1u);
+            if (r < rmax)
+              umma_bf16(dcol, a0 + (uint64_t)(2 * r * TC_TW), bt + (uint64_t)(2 * r * c8n * WH), idesc,
+                        (it == 0 && r == 0) ? 0u : 1u);
         }
         umma_commit(&empty[s]);
         if (it == T - 1) umma_commit(done);
+        if (me == 0) { TTG_T1(12, it); }
       }
       __syncwarp();
     }
-  } else if (TMA && warp == 7 && lane == 0) {
+  } else if (TMA && warp == 7 && elect_one()) {
     // ---- TMA producer: one tensor-map load for the x halo tile, one for the gy tile, per slot
     for (int j = 0; j < T; ++j) {
       const int s = j % NBUF;
-      if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u);
+      { TTG_T0(); if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u); TTG_T1(13, j); }
       int n, y0, x0;
       tile_coords(j, n, y0, x0);
       const uint32_t bar = smem_u32(&full[s]);
@@ -1611,7 +1624,19 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
 
 static int g_wgrad_tc_smem[2] = {0, 0};
 
-extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int, int, int) { return 16; }
+// packed partial-sum image -> OIHW fp32 (layout 0: gwp[tap][co][ci], 1: gwp[tap][ci][co]; padded sizes CoutP x CinP)
+__global__ void ttg_wgrad_unpack_kernel(const float* __restrict__ gwp, float* __restrict__ gw, int Cout, int Cin, int CoutP, int CinP,
+                                        int taps, int layout) {
+  const int total = Cout * Cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);
+    gw[i] = layout == 0 ? gwp[((long long)tap * CoutP + co) * CinP + ci] : gwp[((long long)tap * CinP + ci) * CoutP + co];
+  }
+}
+static inline int ttg_pad16(int c) { return c <= 8 ? 16 : c; }
+extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize) {
+  return sizeof(float) * (size_t)ttg_pad16(Cin) * ttg_pad16(Cout) * ksize * ksize + 16;
+}
 
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                       int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
@@ -1621,8 +1646,9 @@ extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int
 }
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                       int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
-  (void)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_wgrad_tc: workspace must be 16-byte aligned");
+  float* gwp = reinterpret_cast<float*>(workspace);
   const bool padded = cin_real != Cin || cout_real != Cout;
   TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || cout_real <= 8)),
               "conv2d_wgrad_tc: channel padding supports <= 8 real channels");
@@ -1675,12 +1701,18 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
       long long wsplits = (long long)ttg_num_sms() * wper_sm / (wgroups * halves);
       if (wsplits < 1) wsplits = 1;
       if (wsplits > tiles) wsplits = tiles;
-      cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st);
+      cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
-#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gw, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, st)
-      if (ksize == 3) return nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
-      return nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
+#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, st)
+      int rc;
+      if (ksize == 3) rc = nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
+      else rc = nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
 #undef TTG_WG
+      if (rc != TTG_OK) return rc;
+      const int total = cout_real * cin_real * taps;
+      ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0);
+      TTG_CHECK_LAUNCH("conv2d_wgrad_unpack");
+      return TTG_OK;
     }
   }
   TTG_REQUIRE(!padded, "conv2d_wgrad_tc: padded layers must fit the persistent kernel");

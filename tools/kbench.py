@@ -46,7 +46,7 @@ def main():
         else:
             gy = ops.empty_nhwc(n, cout, h, w, bf, 'cuda'); gy.normal_()
             gw = torch.empty(cout, cin, k, k, device='cuda')
-            ws = torch.empty(16, device='cuda')
+            ws = torch.empty(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k) // 4 + 4, device='cuda')
             fn = lambda: call('ttg_conv2d_wgrad_tc', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, 0, ptr(ws))
         med, best = timeit(fn, reps)
         print(f'{kind} N{n} {h}x{w} {cin}->{cout} k{k}: median {med*1e3:.1f} us  best {best*1e3:.1f} us  '
