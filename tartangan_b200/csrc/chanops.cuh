@@ -132,19 +132,23 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
 //   template <int V> struct P;  load<V>(c0, P&);  apply<V>(const float* v, int j, const P<V>&, float* o)
 // When the grid stride keeps every thread on the same channel group (`invariant`), the per-channel
 // parameters are loaded once per thread instead of once per element.
+// `reverse`: walk the tensor from its end.  A map pass that follows a reduction over the same tensors then starts
+// with the part of them the reduction touched last, i.e. the part that is still resident in the 126 MB L2.
 template <typename T, int V, class Op>
-__global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, int C, int invariant) {
+__global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, int C, int invariant, int reverse) {
   constexpr int U = 2;                             // vectors in flight per thread
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   typename Op::template P<V> prm;
-  if (invariant && i0 < nvec) op.template load<V>((int)((i0 * V) % C), prm);
+  const long long last = nvec - 1;
+  if (invariant && i0 < nvec) op.template load<V>((int)(((reverse ? last - i0 : i0) * V) % C), prm);
   for (; i0 < nvec; i0 += U * stride) {
     float v[U][Op::NIN][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
+      const long long ii = i0 + u * stride;
+      const long long i = reverse ? last - ii : ii;
+      if (ii < nvec) {
 #pragma unroll
         for (int t = 0; t < Op::NIN; ++t) {
           if constexpr (V == 1) v[u][t][0] = to_f(op.in[t][i]);
@@ -154,8 +158,9 @@ __global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, in
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < nvec) {
+      const long long ii = i0 + u * stride;
+      const long long i = reverse ? last - ii : ii;
+      if (ii < nvec) {
         const long long base = i * V;
         if (!invariant) op.template load<V>((int)(base % C), prm);
         float o[Op::NOUT][V];
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, in
 }
 
 template <typename T, class Op>
-static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStream_t st) {
+static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStream_t st, int reverse = 0) {
   const void* ptrs[Op::NIN + Op::NOUT];
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
   for (int i = 0; i < Op::NOUT; ++i) ptrs[Op::NIN + i] = op.out[i];
@@ -189,11 +194,11 @@ static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStre
     long long nvec = n / V;
     int grid = ttg_grid_for(nvec, 256 * 2);
     int inv = ((long long)grid * 256 * V) % C == 0;
-    chan_map_kernel<T, V, Op><<<grid, 256, 0, st>>>(op, nvec, C, inv);
+    chan_map_kernel<T, V, Op><<<grid, 256, 0, st>>>(op, nvec, C, inv, reverse);
   } else {
     int grid = ttg_grid_for(n, 256 * 4);
     int inv = ((long long)grid * 256) % C == 0;
-    chan_map_kernel<T, 1, Op><<<grid, 256, 0, st>>>(op, n, C, inv);
+    chan_map_kernel<T, 1, Op><<<grid, 256, 0, st>>>(op, n, C, inv, reverse);
   }
   TTG_CHECK_LAUNCH(name);
   return TTG_OK;
