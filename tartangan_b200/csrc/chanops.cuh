@@ -115,12 +115,12 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN) && C / Vec<T>::N <= 256) {
     constexpr int V = Vec<T>::N;
     int rpi = 256 / (C / V);
-    int grid = ttg_grid_for(M, rpi * 4, 8);
+    int grid = ttg_grid_occ(chan_reduce_kernel<T, V, Op>, M, rpi * 4, 256, smem);
     chan_reduce_kernel<T, V, Op><<<grid, 256, smem, st>>>(op, M, C, out);
   } else {
     if (C > 256) return ttg_set_error(TTG_ERR_UNSUPPORTED, "%s: C=%d needs C%%%d==0 and 16B alignment", name, C, Vec<T>::N);
     int rpi = 256 / C;
-    int grid = ttg_grid_for(M, rpi * 8, 4);
+    int grid = ttg_grid_occ(chan_reduce_kernel<T, 1, Op>, M, rpi * 8, 256, smem);
     chan_reduce_kernel<T, 1, Op><<<grid, 256, smem, st>>>(op, M, C, out);
   }
   TTG_CHECK_LAUNCH(name);
@@ -192,11 +192,11 @@ static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStre
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN + Op::NOUT)) {
     constexpr int V = Vec<T>::N;
     long long nvec = n / V;
-    int grid = ttg_grid_for(nvec, 256 * 2);
+    int grid = ttg_grid_occ(chan_map_kernel<T, V, Op>, nvec, 256 * 2);
     int inv = ((long long)grid * 256 * V) % C == 0;
     chan_map_kernel<T, V, Op><<<grid, 256, 0, st>>>(op, nvec, C, inv, reverse);
   } else {
-    int grid = ttg_grid_for(n, 256 * 4);
+    int grid = ttg_grid_occ(chan_map_kernel<T, 1, Op>, n, 256 * 4);
     int inv = ((long long)grid * 256) % C == 0;
     chan_map_kernel<T, 1, Op><<<grid, 256, 0, st>>>(op, n, C, inv, reverse);
   }

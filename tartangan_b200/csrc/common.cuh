@@ -50,6 +50,31 @@ static inline int ttg_grid_for(long long work_items, int per_block, int max_wave
   return (int)b;
 }
 
+// Grid for a grid-stride kernel: enough blocks for the work, at most ONE full wave at the kernel's real occupancy
+// (a fixed "8 blocks per SM" cap leaves a ragged second wave when registers limit a kernel to 5-6 blocks per SM).
+#include <mutex>
+#include <unordered_map>
+static inline int ttg_blocks_per_sm(const void* fn, int block, size_t smem) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, int> cache;
+  const unsigned long long key = (unsigned long long)(uintptr_t)fn ^ ((unsigned long long)block << 48) ^ ((unsigned long long)smem << 20);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, block, smem) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 4; }
+  cache[key] = n;
+  return n;
+}
+template <class Kern>
+static inline int ttg_grid_occ(Kern kernel, long long work_items, int per_block, int block = 256, size_t smem = 0) {
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)ttg_num_sms() * ttg_blocks_per_sm((const void*)kernel, block, smem);
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 // ---------------------------------------------------------------- device side
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }

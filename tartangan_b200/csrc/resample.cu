@@ -44,8 +44,8 @@ __global__ void pool2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, 
 extern "C" int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, x, y)) { pool2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
-    else { pool2_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
+    if (vec2_ok<T>(C, x, y)) { pool2_kernel<T, Vec<T>::N><<<ttg_grid_occ(pool2_kernel<T, Vec<T>::N>, (long long)N * Ho * Wo * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
+    else { pool2_kernel<T, 1><<<ttg_grid_occ(pool2_kernel<T, 1>, (long long)N * Ho * Wo * C, 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
   });
   TTG_CHECK_LAUNCH("pool2_sum");
   return TTG_OK;
@@ -69,8 +69,8 @@ __global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int
 extern "C" int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, x, y)) { upsample2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Hi * Wi * 4 * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
-    else { upsample2_kernel<T, 1><<<ttg_grid_for((long long)N * Hi * Wi * 4 * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
+    if (vec2_ok<T>(C, x, y)) { upsample2_kernel<T, Vec<T>::N><<<ttg_grid_occ(upsample2_kernel<T, Vec<T>::N>, (long long)N * Hi * Wi * 4 * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
+    else { upsample2_kernel<T, 1><<<ttg_grid_occ(upsample2_kernel<T, 1>, (long long)N * Hi * Wi * 4 * C, 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
   });
   TTG_CHECK_LAUNCH("upsample2");
   return TTG_OK;
@@ -107,8 +107,8 @@ extern "C" int ttg_bilinear_down_fwd(const void* x, void* y, int N, int Hi, int 
   cudaStream_t st = (cudaStream_t)stream;
   TTG_REQUIRE(Hi % 2 == 0 && Wi % 2 == 0, "bilinear_down: odd input size %dx%d", Hi, Wi);
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, x, y)) { bilinear_down_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * (Hi / 2) * (Wi / 2) * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
-    else { bilinear_down_kernel<T, 1><<<ttg_grid_for((long long)N * (Hi / 2) * (Wi / 2) * C, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
+    if (vec2_ok<T>(C, x, y)) { bilinear_down_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_kernel<T, Vec<T>::N>, (long long)N * (Hi / 2) * (Wi / 2) * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
+    else { bilinear_down_kernel<T, 1><<<ttg_grid_occ(bilinear_down_kernel<T, 1>, (long long)N * (Hi / 2) * (Wi / 2) * C, 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C); }
   });
   TTG_CHECK_LAUNCH("bilinear_down_fwd");
   return TTG_OK;
@@ -161,8 +161,8 @@ extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, in
   cudaStream_t st = (cudaStream_t)stream;
   const long long pixels = (long long)N * Hi * Wi;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_for(pixels, 128, 16), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
-    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_for(pixels, 128, 16), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, Vec<T>::N>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, 1>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
   });
   TTG_CHECK_LAUNCH("bilinear_down_bwd");
   return TTG_OK;
@@ -188,8 +188,8 @@ extern "C" int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho,
   cudaStream_t st = (cudaStream_t)stream;
   TTG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "add_up2: odd output size");
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { add_up2_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 512), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
-    else { add_up2_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 1024), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
+    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { add_up2_kernel<T, Vec<T>::N><<<ttg_grid_occ(add_up2_kernel<T, Vec<T>::N>, (long long)N * Ho * Wo * (C / Vec<T>::N), 512, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
+    else { add_up2_kernel<T, 1><<<ttg_grid_occ(add_up2_kernel<T, 1>, (long long)N * Ho * Wo * C, 1024, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C); }
   });
   TTG_CHECK_LAUNCH("add_up2");
   return TTG_OK;
@@ -218,8 +218,8 @@ __global__ void pool2_add_kernel(const T* __restrict__ h, const T* __restrict__ 
 extern "C" int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { pool2_add_kernel<T, Vec<T>::N><<<ttg_grid_for((long long)N * Ho * Wo * (C / Vec<T>::N), 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
-    else { pool2_add_kernel<T, 1><<<ttg_grid_for((long long)N * Ho * Wo * C, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
+    if (vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) { pool2_add_kernel<T, Vec<T>::N><<<ttg_grid_occ(pool2_add_kernel<T, Vec<T>::N>, (long long)N * Ho * Wo * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
+    else { pool2_add_kernel<T, 1><<<ttg_grid_occ(pool2_add_kernel<T, 1>, (long long)N * Ho * Wo * C, 256, 256), 256, 0, st>>>((const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale); }
   });
   TTG_CHECK_LAUNCH("pool2_add");
   return TTG_OK;
@@ -241,8 +241,8 @@ extern "C" int ttg_axpby(const void* a, const void* b, void* out, long long n, f
   if (n == 0) return TTG_OK;
   TTG_DISPATCH(dtype, {
     bool vec = n % Vec<T>::N == 0 && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15);
-    if (vec) axpby_kernel<T, Vec<T>::N><<<ttg_grid_for(n / Vec<T>::N, 512), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n / Vec<T>::N, alpha, beta);
-    else axpby_kernel<T, 1><<<ttg_grid_for(n, 1024), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, alpha, beta);
+    if (vec) axpby_kernel<T, Vec<T>::N><<<ttg_grid_occ(axpby_kernel<T, Vec<T>::N>, n / Vec<T>::N, 512, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n / Vec<T>::N, alpha, beta);
+    else axpby_kernel<T, 1><<<ttg_grid_occ(axpby_kernel<T, 1>, n, 1024, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, alpha, beta);
   });
   TTG_CHECK_LAUNCH("axpby");
   return TTG_OK;
@@ -255,7 +255,7 @@ __global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict_
 }
 extern "C" int ttg_scale_f32(const float* x, float* out, long long n, float host_scale, const float* dev_scale, void* stream) {
   if (n == 0) return TTG_OK;
-  scale_f32_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, out, n, host_scale, dev_scale);
+  scale_f32_kernel<<<ttg_grid_occ(scale_f32_kernel, n, 1024, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, host_scale, dev_scale);
   TTG_CHECK_LAUNCH("scale_f32");
   return TTG_OK;
 }
@@ -285,7 +285,7 @@ __global__ void spatial_bcast_kernel(const float* __restrict__ g, T* __restrict_
 }
 extern "C" int ttg_spatial_bcast(const float* g, void* gx, int N, int HW, int C, int dtype, void* stream) {
   long long total = (long long)N * HW * C;
-  TTG_DISPATCH(dtype, { spatial_bcast_kernel<T><<<ttg_grid_for(total, 1024), 256, 0, (cudaStream_t)stream>>>(g, (T*)gx, total, HW, C); });
+  TTG_DISPATCH(dtype, { spatial_bcast_kernel<T><<<ttg_grid_occ(spatial_bcast_kernel<T>, total, 1024, 256), 256, 0, (cudaStream_t)stream>>>(g, (T*)gx, total, HW, C); });
   TTG_CHECK_LAUNCH("spatial_bcast");
   return TTG_OK;
 }
@@ -310,12 +310,12 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
   }
 }
 extern "C" int ttg_nchw_to_nhwc(const float* x, void* y, int N, int C, int HW, int dtype, void* stream) {
-  TTG_DISPATCH(dtype, { nchw_to_nhwc_kernel<T><<<ttg_grid_for((long long)N * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, N, C, HW); });
+  TTG_DISPATCH(dtype, { nchw_to_nhwc_kernel<T><<<ttg_grid_occ(nchw_to_nhwc_kernel<T>, (long long)N * HW, 256, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, N, C, HW); });
   TTG_CHECK_LAUNCH("nchw_to_nhwc");
   return TTG_OK;
 }
 extern "C" int ttg_nhwc_to_nchw(const void* x, float* y, int N, int C, int HW, int dtype, void* stream) {
-  TTG_DISPATCH(dtype, { nhwc_to_nchw_kernel<T><<<ttg_grid_for((long long)N * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, N, C, HW); });
+  TTG_DISPATCH(dtype, { nhwc_to_nchw_kernel<T><<<ttg_grid_occ(nhwc_to_nchw_kernel<T>, (long long)N * HW, 256, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, N, C, HW); });
   TTG_CHECK_LAUNCH("nhwc_to_nchw");
   return TTG_OK;
 }
@@ -347,13 +347,13 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __rest
 }
 extern "C" int ttg_tanh_fwd(const float* x, float* y, long long n, void* stream) {
   if (n == 0) return TTG_OK;
-  tanh_fwd_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  tanh_fwd_kernel<<<ttg_grid_occ(tanh_fwd_kernel, n, 1024, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
   TTG_CHECK_LAUNCH("tanh_fwd");
   return TTG_OK;
 }
 extern "C" int ttg_tanh_bwd(const float* y, const float* g, float* gx, long long n, void* stream) {
   if (n == 0) return TTG_OK;
-  tanh_bwd_kernel<<<ttg_grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(y, g, gx, n);
+  tanh_bwd_kernel<<<ttg_grid_occ(tanh_bwd_kernel, n, 1024, 256), 256, 0, (cudaStream_t)stream>>>(y, g, gx, n);
   TTG_CHECK_LAUNCH("tanh_bwd");
   return TTG_OK;
 }
