@@ -69,6 +69,11 @@ int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias, void* y, 
                      const float* pre_shift, float slope, void* stream);
 int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                            int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
+/* 8-channel staging copies of the <= 8-channel (RGB) bf16 tensors: y8[p][0..7] = x[p][0..c_real-1], 0...  With
+ * cin_real / cout_real == 8 (Cin / Cout == 16) the _ex entry points above read / write such tensors through the
+ * same TMA tiles and 16-byte stores as the wide layers (missing channel groups are zero-filled by the TMA engine). */
+int ttg_pad_channels8(const void* x, void* y8, long long npix, int c_real, void* stream);
+int ttg_unpad_channels8(const void* y8, void* y, long long npix, int c_real, void* stream);
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
                         int up, void* workspace, void* stream);
 size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);

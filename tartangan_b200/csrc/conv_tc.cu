@@ -406,9 +406,27 @@ __device__ __forceinline__ void conv_tc_epilogue(uint32_t tacc, int warp, int ti
 //   strip pitch = chunk bytes + 16  ->  both the pixel-major writes and the unit-major reads are conflict free.
 #define TC_EPI_CHUNK 64
 static inline int tc_epi_bytes(int Cout) { return 4 * 32 * ((Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK) * 2 + 16); }
+// `Cout` = channels stored per pixel (row pitch of y): the accumulator width, or 8 for the 8-channel staging tensors
+// of the RGB layers (accumulator columns 8..15 are padding and are dropped).
 __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_t* sE, int warp, int lane, int n, int y0, int x0,
                                                            int H, int W, int Cout, const float* __restrict__ bias,
                                                            bf16* __restrict__ y) {
+  if (Cout == 8) {                       // one 16-byte unit per pixel: lanes are already on consecutive units
+    uint32_t r[16];
+    tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16), r);
+    tmem_ld_wait();
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0 = __uint_as_float(r[2 * j]), f1 = __uint_as_float(r[2 * j + 1]);
+      if (bias) { f0 += bias[2 * j]; f1 += bias[2 * j + 1]; }
+      __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const int gy = y0 + warp * 4 + (lane >> 3), gx = x0 + (lane & 7);
+    if (gy < H && gx < W) *reinterpret_cast<uint4*>(y + (((long long)n * H + gy) * W + gx) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    return;
+  }
   const int cc = Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK;     // channels per chunk (16, 32, 48 or 64)
   const int upp = cc >> 3;                                       // 16-byte units per pixel in a chunk
   const int pitch = cc * 2 + 16;
@@ -661,7 +679,7 @@ template <int K, int NBUF, int CIN>
 __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
                                                           int H, int W, int Cin_rt, int Cout, int total_tiles, int tmem_cols,
-                                                          int mode) {
+                                                          int mode, int cstore) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   constexpr int NACC = 4;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -730,7 +748,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
         }
       } else if (!out_f32)
         conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
-                                   Cout, bias, reinterpret_cast<bf16*>(y));
+                                   cstore, bias, reinterpret_cast<bf16*>(y));
       else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
@@ -794,14 +812,17 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
 static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
 template <int K, int NBUF, int CIN>
 static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
-                              int Cin, int Cout, long long tiles, int w_bytes, int a_bytes, int pcols, cudaStream_t st, bool* used) {
+                              int Cin, int Cout, int cin_mem, int cstore, long long tiles, int w_bytes, int a_bytes, int pcols,
+                              cudaStream_t st, bool* used) {
   *used = false;
   ttg_encode_tiled_fn enc = ttg_get_encode_tiled();
   if (!enc) return TTG_OK;
   constexpr int HALO = K / 2;
   CUtensorMap tmap;
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t gstr[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  // cin_mem = channels per pixel in memory (Cin, or 8 for the RGB staging tensors: the box still asks for Cin / 8
+  // channel groups and the groups that do not exist are zero-filled by the TMA engine, like the spatial halo)
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)(cin_mem / 8), (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {(cuuint64_t)cin_mem * 2, 16, (cuuint64_t)W * cin_mem * 2, (cuuint64_t)H * W * cin_mem * 2};
   const cuuint32_t box[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r;
@@ -837,7 +858,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
   conv_tc_tma_kernel<K, NBUF, CIN><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
-                                                                pcols, mode);
+                                                                pcols, mode, cstore);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
   return TTG_OK;
@@ -1156,8 +1177,12 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
                                 int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
                                 const float* pre_scale, const float* pre_shift, float slope, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const bool padded = cin_real != Cin || cout_real != Cout;
+  // 8-channel staging tensors (ttg_pad_channels8) ride the TMA path: not "padded" in the scalar-access sense
+  const bool in8 = cin_real == 8 && Cin == 16, out8 = cout_real == 8 && Cout == 16;
+  const bool padded = (cin_real != Cin && !in8) || (cout_real != Cout && !out8);
   TTG_REQUIRE(cin_real >= 1 && cin_real <= Cin && cout_real >= 1 && cout_real <= Cout, "conv2d_tc: bad real channel counts");
+  TTG_REQUIRE(!(in8 || out8) || (!pre_scale && up == 0 && g_use_tma && dtype_out == TTG_BF16 && ttg_get_encode_tiled() != nullptr),
+              "conv2d_tc: 8-channel staging tensors need the TMA path (bf16 output, no upsample / prologue)");
   TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || (cout_real <= 16 && Cout == 16)) && !pre_scale),
               "conv2d_tc: channel padding supports <= 8 real input channels / Cout padded to 16, without prologue");
   TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize %d unsupported", ksize);
@@ -1195,7 +1220,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
       bool used = false;
       const int tcols = (int)tmem_cols_for(4 * Cout);
       const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
-#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, tiles, w_bytes, a_bytes, tcols, st, &used)
+#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, st, &used)
       int rc;
       if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 4, 16) : Cin == 32 ? TTG_TMA(3, 4, 32) : Cin == 64 ? TTG_TMA(3, 3, 64)
                                      : (deep ? TTG_TMA(3, 4, 0) : TTG_TMA(3, 3, 0));
@@ -1586,17 +1611,18 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
   constexpr int HALO = K / 2;
   CUtensorMap tx, tg;
   memset(&tx, 0, sizeof(tx)); memset(&tg, 0, sizeof(tg));
-  bool tma = g_use_tma && up == 0 && cin_real == Cin && cout_real == Cout;
+  const bool in8 = cin_real == 8 && Cin == 16, out8 = cout_real == 8 && Cout == 16;
+  bool tma = g_use_tma && up == 0 && (cin_real == Cin || in8) && (cout_real == Cout || out8);
   ttg_encode_tiled_fn enc = tma ? ttg_get_encode_tiled() : nullptr;
   if (!enc) tma = false;
   if (tma) {
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const cuuint64_t xd[5] = {8, (cuuint64_t)W, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t xs[4] = {(cuuint64_t)Cin * 2, 16, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint64_t xd[5] = {8, (cuuint64_t)W, (cuuint64_t)(cin_real / 8), (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t xs[4] = {(cuuint64_t)cin_real * 2, 16, (cuuint64_t)W * cin_real * 2, (cuuint64_t)H * W * cin_real * 2};
     const cuuint32_t xb[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
     const int g8n = (Cout < 128 ? Cout : 128) / 8;
-    const cuuint64_t gd[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cout / 8), (cuuint64_t)N};
-    const cuuint64_t gs[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, 16, (cuuint64_t)H * W * Cout * 2};
+    const cuuint64_t gd[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(cout_real / 8), (cuuint64_t)N};
+    const cuuint64_t gs[4] = {(cuuint64_t)cout_real * 2, (cuuint64_t)W * cout_real * 2, 16, (cuuint64_t)H * W * cout_real * 2};
     const cuuint32_t gb[5] = {8, TC_TW, TC_TH, (cuuint32_t)g8n, 1};
     CUresult r1 = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xd, xs, xb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1650,6 +1676,8 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
   TTG_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_wgrad_tc: workspace must be 16-byte aligned");
   float* gwp = reinterpret_cast<float*>(workspace);
   const bool padded = cin_real != Cin || cout_real != Cout;
+  TTG_REQUIRE(!(cin_real == 8 && Cin == 16) && !(cout_real == 8 && Cout == 16) || (up == 0 && g_use_tma && ttg_get_encode_tiled() != nullptr),
+              "conv2d_wgrad_tc: 8-channel staging tensors need the TMA path");
   TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || cout_real <= 8)),
               "conv2d_wgrad_tc: channel padding supports <= 8 real channels");
   TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad_tc: ksize %d unsupported", ksize);
@@ -1734,5 +1762,45 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
   else
     conv_wgrad_tc_kernel<1><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc");
+  return TTG_OK;
+}
+
+// ------------------------------------------------------------------ 8-channel staging of the RGB tensors
+// The image-like tensors (3 channels: D's first conv input, the image gradient, G's output conv) are copied into
+// 8-channel pixels (channels >= c_real zero) so that the tensor-core kernels fetch / store them with the same TMA
+// tiles and 16-byte stores as every other layer; the copy costs one extra pass over a tensor that is 5x smaller than
+// its 16-channel neighbour.
+__global__ void pad_channels8_kernel(const unsigned short* __restrict__ x, uint4* __restrict__ y, long long npix, int c_real) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const unsigned short* src = x + p * c_real;
+    for (int c = 0; c < c_real; ++c) w[c >> 1] |= (uint32_t)src[c] << (16 * (c & 1));
+    y[p] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+__global__ void unpad_channels8_kernel(const uint4* __restrict__ y8, unsigned short* __restrict__ y, long long npix, int c_real) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = y8[p];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    unsigned short* dst = y + p * c_real;
+    for (int c = 0; c < c_real; ++c) dst[c] = (unsigned short)(w[c >> 1] >> (16 * (c & 1)));
+  }
+}
+extern "C" int ttg_pad_channels8(const void* x, void* y8, long long npix, int c_real, void* stream) {
+  TTG_REQUIRE(c_real >= 1 && c_real <= 8 && npix >= 0, "pad_channels8: 1..8 channels");
+  TTG_REQUIRE((reinterpret_cast<uintptr_t>(y8) & 15) == 0, "pad_channels8: destination must be 16-byte aligned");
+  if (npix == 0) return TTG_OK;
+  pad_channels8_kernel<<<ttg_grid_occ(pad_channels8_kernel, npix, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const unsigned short*)x, (uint4*)y8, npix, c_real);
+  TTG_CHECK_LAUNCH("pad_channels8");
+  return TTG_OK;
+}
+extern "C" int ttg_unpad_channels8(const void* y8, void* y, long long npix, int c_real, void* stream) {
+  TTG_REQUIRE(c_real >= 1 && c_real <= 8 && npix >= 0, "unpad_channels8: 1..8 channels");
+  TTG_REQUIRE((reinterpret_cast<uintptr_t>(y8) & 15) == 0, "unpad_channels8: source must be 16-byte aligned");
+  if (npix == 0) return TTG_OK;
+  unpad_channels8_kernel<<<ttg_grid_occ(unpad_channels8_kernel, npix, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)y8, (unsigned short*)y, npix, c_real);
+  TTG_CHECK_LAUNCH("unpad_channels8");
   return TTG_OK;
 }

@@ -162,6 +162,14 @@ def _packed(w, mode, kind):
     return wp
 
 
+def _pad8(x):
+    """8-channel staging copy (channels >= C zero) of a bf16 NHWC tensor with C < 8 channels."""
+    n, c, h, w = x.shape
+    y = empty_nhwc(n, 8, h, w, x.dtype, x.device)
+    call('ttg_pad_channels8', ptr(x), ptr(y), n * h * w, c)
+    return y
+
+
 def _pad16(c):
     """Channel counts <= 8 (the RGB layers) are zero-padded to 16 inside the tensor-core kernels."""
     return 16 if c <= 8 else c
@@ -184,8 +192,14 @@ def _conv_raw(x, w, bias, mode, up, out_dtype=None):
     y = empty_nhwc(n, c_out_eff, h, wd_, out_dtype, x.device)
     if _tc_ok(x.dtype, cin, cout) and out_dtype in (torch.bfloat16, torch.float32):
         wp = _packed(w, mode, 'tc')
-        call('ttg_conv2d_tc_ex', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, _pad16(c_in_eff), _pad16(c_out_eff),
-             c_in_eff, c_out_eff, k, up, dtype_code(out_dtype), None, None, 1.0)
+        # RGB layers: stage the <= 8-channel tensor as 8-channel pixels so the layer runs on the TMA kernels
+        stage8 = up == 0 and out_dtype == torch.bfloat16
+        xin, cin_mem = (_pad8(x), 8) if (stage8 and c_in_eff < 8) else (x, c_in_eff)
+        yout, cout_mem = (empty_nhwc(n, 8, h, wd_, out_dtype, x.device), 8) if (stage8 and c_out_eff < 8) else (y, c_out_eff)
+        call('ttg_conv2d_tc_ex', ptr(xin), ptr(wp), ptr(bias), ptr(yout), n, h, wd_, _pad16(c_in_eff), _pad16(c_out_eff),
+             cin_mem, cout_mem, k, up, dtype_code(out_dtype), None, None, 1.0)
+        if yout is not y:
+            call('ttg_unpad_channels8', ptr(yout), ptr(y), n * h * wd_, c_out_eff)
     else:
         wp = _packed(w, mode, 'direct')
         call('ttg_conv2d_direct', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, up,
@@ -254,8 +268,18 @@ class ConvWgradFn(Function):
         gw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
         if _tc_ok(x.dtype, cin, cout) and gy.dtype == torch.bfloat16:
             ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
-            call('ttg_conv2d_wgrad_tc_ex', ptr(x), ptr(gy), ptr(gw), n, h, w, _pad16(cin), _pad16(cout), cin, cout, k, up,
-                 ptr(ws))
+            if up == 0 and (cin < 8 or cout < 8):
+                # RGB layers: 8-channel staging copies of the narrow operand(s); the extra rows / columns of the
+                # 8-channel weight gradient are zero and are dropped
+                xin, cin_mem = (_pad8(x), 8) if cin < 8 else (x, cin)
+                gin, cout_mem = (_pad8(gy), 8) if cout < 8 else (gy, cout)
+                gw8 = torch.empty((cout_mem, cin_mem, k, k), dtype=torch.float32, device=x.device)
+                call('ttg_conv2d_wgrad_tc_ex', ptr(xin), ptr(gin), ptr(gw8), n, h, w, _pad16(cin), _pad16(cout), cin_mem,
+                     cout_mem, k, up, ptr(ws))
+                gw.copy_(gw8[:cout, :cin])
+            else:
+                call('ttg_conv2d_wgrad_tc_ex', ptr(x), ptr(gy), ptr(gw), n, h, w, _pad16(cin), _pad16(cout), cin, cout, k,
+                     up, ptr(ws))
         else:
             call('ttg_conv2d_wgrad_direct', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up,
                  dtype_code(x.dtype), dtype_code(gy.dtype))

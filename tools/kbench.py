@@ -51,6 +51,17 @@ def main():
         med, best = timeit(fn, reps)
         print(f'{kind} N{n} {h}x{w} {cin}->{cout} k{k}: median {med*1e3:.1f} us  best {best*1e3:.1f} us  '
               f'{nbytes/med/1e6:.0f} GB/s  {flops/med/1e9:.1f} TFLOP/s')
+    elif kind == 'rgb':
+        # RGB layers through the Python operator (pad8 staging + TMA kernels): fprop 3->16, dgrad 16->3, wgrad 3->16
+        n, h, w, k = a[:4]
+        x3 = ops.empty_nhwc(n, 3, h, w, bf, 'cuda'); x3.normal_()
+        g16 = ops.empty_nhwc(n, 16, h, w, bf, 'cuda'); g16.normal_()
+        wt = torch.randn(16, 3, k, k, device='cuda') * 0.05
+        for name, fn in (('fprop 3->16', lambda: ops._conv_raw(x3, wt, None, 0, 0)),
+                         ('dgrad 16->3', lambda: ops._conv_raw(g16, wt, None, 1, 0)),
+                         ('wgrad 3->16', lambda: ops.ConvWgradFn.apply(x3, g16, k, 0))):
+            med, best = timeit(fn)
+            print(f'rgb {name} N{n} {h}x{w} k{k}: median {med*1e3:.1f} us best {best*1e3:.1f} us')
     elif kind == 'bn':
         m, c = a[:2]
         x = torch.randn(m, c, device='cuda').to(bf)
