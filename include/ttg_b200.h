@@ -72,6 +72,11 @@ int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int 
 /* 8-channel staging copies of the <= 8-channel (RGB) bf16 tensors: y8[p][0..7] = x[p][0..c_real-1], 0...  With
  * cin_real / cout_real == 8 (Cin / Cout == 16) the _ex entry points above read / write such tensors through the
  * same TMA tiles and 16-byte stores as the wide layers (missing channel groups are zero-filled by the TMA engine). */
+/* every conv filter of a model (views of one flat fp32 parameter buffer) packed in one launch; table rows of 9
+ * int64 {src offset (floats), dst offset (bytes), Cout, Cin, CoutP, CinP, ksize, mode, first block}, 256 threads per
+ * block, one element per thread; padded destination images must have been zeroed once. */
+int ttg_pack_weights_multi(const float* flat, void* packed, const long long* table, int n_entries, int total_blocks,
+                           void* stream);
 int ttg_pad_channels8(const void* x, void* y8, long long npix, int c_real, void* stream);
 int ttg_unpad_channels8(const void* y8, void* y, long long npix, int c_real, void* stream);
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,

@@ -1804,3 +1804,41 @@ extern "C" int ttg_unpad_channels8(const void* y8, void* y, long long npix, int 
   TTG_CHECK_LAUNCH("unpad_channels8");
   return TTG_OK;
 }
+
+// ------------------------------------------------------------------ all filters of a model in one launch
+// table: n_entries rows of 9 int64: {src offset (floats), dst offset (bytes), Cout, Cin, CoutP, CinP, k, mode,
+// first block}; blocks [first block, next first block) pack entry e.  Replaces ~50 pack_weight launches per step
+// (every filter, both operand orientations) by one launch after each optimiser update.
+__global__ void pack_weights_multi_kernel(const float* __restrict__ flat, unsigned char* __restrict__ packed,
+                                          const long long* __restrict__ table, int n_entries) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && (long long)blockIdx.x >= table[(e + 1) * 9 + 8]) ++e;
+    s_e = e;
+  }
+  __syncthreads();
+  const long long* t = table + (long long)s_e * 9;
+  const float* w = flat + t[0];
+  bf16* wp = reinterpret_cast<bf16*>(packed + t[1]);
+  const int Cout = (int)t[2], Cin = (int)t[3], CoutP = (int)t[4], CinP = (int)t[5], k = (int)t[6], mode = (int)t[7];
+  const int i = (int)((long long)blockIdx.x - t[8]) * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * k * k) return;
+  const int kx = i % k, ky = (i / k) % k, ci = (i / (k * k)) % Cin, co = i / (k * k * Cin);
+  const bf16 v = __float2bfloat16_rn(w[i]);
+  if (mode == 0) {
+    const int tap = ky * k + kx;
+    wp[(((long long)tap * (CinP / 8) + ci / 8) * CoutP + co) * 8 + (ci % 8)] = v;
+  } else {
+    const int tap = (k - 1 - ky) * k + (k - 1 - kx);
+    wp[(((long long)tap * (CoutP / 8) + co / 8) * CinP + ci) * 8 + (co % 8)] = v;
+  }
+}
+extern "C" int ttg_pack_weights_multi(const float* flat, void* packed, const long long* table, int n_entries,
+                                      int total_blocks, void* stream) {
+  TTG_REQUIRE(n_entries >= 0 && total_blocks >= 0, "pack_weights_multi: bad table");
+  if (n_entries == 0 || total_blocks == 0) return TTG_OK;
+  pack_weights_multi_kernel<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(flat, (unsigned char*)packed, table, n_entries);
+  TTG_CHECK_LAUNCH("pack_weights_multi");
+  return TTG_OK;
+}

@@ -92,6 +92,19 @@ class FusedAdam(torch.optim.Optimizer):
              g['lr'], g['betas'][0], g['betas'][1], g['eps'], self.ema_lr, ptr(self._step))
         for p in flat.params:       # invalidate packed-weight caches (ops._packed)
             p._ttg_epoch = getattr(p, '_ttg_epoch', 0) + 1
+        if self.ema_target is not None:      # the fused EMA rewrote the target model's parameters as well
+            for p in self.ema_target.params:
+                p._ttg_epoch = getattr(p, '_ttg_epoch', 0) + 1
+        self.repack()
+
+    def repack(self):
+        """Refresh the packed conv-filter images of the optimised model in one launch (ops.PackedModel)."""
+        from . import ops
+        flat = self._ensure_flat()
+        pm = getattr(self, '_packed_model', None)
+        if pm is None or pm.flat is not flat:
+            pm = self._packed_model = ops.PackedModel(flat)
+        pm.repack()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)

@@ -232,7 +232,9 @@ class GanTrainer(Trainer):
         for opt, (m_, v_, s_) in zip((self.optimizer_d, self.optimizer_g), opt_saved):
             opt._m.copy_(m_); opt._v.copy_(v_); opt._step.copy_(s_)
         torch.set_rng_state(rng)
-        ops.state.pack_generation += 1          # every packed weight is re-packed (and captured) at first use
+        ops.state.pack_generation += 1          # invalidate every per-tensor packed-weight cache ...
+        for opt in (self.optimizer_d, self.optimizer_g):
+            opt.repack()                        # ... and refill them (eagerly) from the shared buffers the graphs read
         # route z / tau draws to the static buffers while capturing
         if nt:
             self.d.to_output.iqn.tau_source = self._static_taus
