@@ -72,6 +72,13 @@ int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int 
 /* 8-channel staging copies of the <= 8-channel (RGB) bf16 tensors: y8[p][0..7] = x[p][0..c_real-1], 0...  With
  * cin_real / cout_real == 8 (Cin / Cout == 16) the _ex entry points above read / write such tensors through the
  * same TMA tiles and 16-byte stores as the wide layers (missing channel groups are zero-filled by the TMA engine). */
+/* conv (bf16 NHWC, channels multiples of 16, no upsample) that also returns the BatchNorm statistics of its output:
+ * sums[0..Cout) = sum over pixels, sums[Cout..2Cout) = sum of squares (fp64; of the bf16 values written).  Replaces the
+ * first pass of native_batch_norm over the conv output (conv -> BatchNorm2d pairs: generator.py:41-43,
+ * discriminator.py:63-65).  ttg_bn_finalize turns the sums into mean / invstd / running statistics. */
+int ttg_conv2d_tc_stats_supported(int Cin, int Cout, int ksize);
+int ttg_conv2d_tc_stats(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                        int ksize, double* sums, void* stream);
 /* every conv filter of a model (views of one flat fp32 parameter buffer) packed in one launch; table rows of 9
  * int64 {src offset (floats), dst offset (bytes), Cout, Cin, CoutP, CinP, ksize, mode, first block}, 256 threads per
  * block, one element per thread; padded destination images must have been zeroed once. */
@@ -91,6 +98,8 @@ size_t ttg_bn_workspace_bytes(int C);
 int ttg_bn_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* invstd,
                  float* running_mean, float* running_var, long long* num_batches, void* workspace,
                  long long count_mult, int dtype, void* stream);
+int ttg_bn_finalize(const double* sums, long long M, int C, float eps, float momentum, float* mean, float* invstd,
+                    float* running_mean, float* running_var, long long* num_batches, long long count_mult, void* stream);
 int ttg_bn_eval_stats(const float* running_mean, const float* running_var, float eps, int C, float* mean,
                       float* invstd, void* stream);
 int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const float* mean, const float* invstd,

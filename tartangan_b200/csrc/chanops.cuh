@@ -4,6 +4,15 @@
 // grid sized in multiples of the SM count (grid-stride loops).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
+
+// Vector width per (dtype, Op): 16-byte vectors unless the Op asks for 4-element bf16 vectors (`BF16_V = 4`).
+// Measured on B200 (bn_act_bwd, M = 4 Mi, C = 16): 8 channels per thread (80 / 105 registers, 3 / 2 blocks per SM)
+// 182 us; 4 channels per thread (60 / 63 registers, 4 blocks per SM) 203 us -> every op keeps 16-byte vectors.
+template <class Op, class = void> struct OpBf16V { static constexpr int value = 8; };
+template <class Op> struct OpBf16V<Op, std::void_t<decltype(Op::BF16_V)>> { static constexpr int value = Op::BF16_V; };
+template <typename T, class Op> struct ChanV { static constexpr int value = Vec<T>::N; };
+template <class Op> struct ChanV<bf16, Op> { static constexpr int value = OpBf16V<Op>::value; };
 
 // Op concept for reductions:
 //   static constexpr int NIN, NACC;   const T* in[NIN];
@@ -26,7 +35,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
   if (rsub < rpi) {
     typename Op::template P<V> prm;
     op.template load<V>(g * V, prm);
-    constexpr int U = 2;                           // rows in flight per thread
+    constexpr int U = 2;                           // rows in flight per thread (4 measured slower: registers)
     const long long rstep = (long long)gridDim.x * rpi;
     long long r0 = (long long)blockIdx.x * rpi + rsub;
     for (; r0 + (U - 1) * rstep < M; r0 += U * rstep) {
@@ -37,7 +46,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
 #pragma unroll
         for (int t = 0; t < Op::NIN; ++t) {
           if constexpr (V == 1) v[u][t][0] = to_f(op.in[t][base]);
-          else { Vec<T> q; q.load(op.in[t] + base); q.unpack(v[u][t]); }
+          else { VecN<T, V> q; q.load(op.in[t] + base); q.unpack(v[u][t]); }
         }
       }
 #pragma unroll
@@ -60,7 +69,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
 #pragma unroll
       for (int t = 0; t < Op::NIN; ++t) {
         if constexpr (V == 1) v[t][0] = to_f(op.in[t][base]);
-        else { Vec<T> q; q.load(op.in[t] + base); q.unpack(v[t]); }
+        else { VecN<T, V> q; q.load(op.in[t] + base); q.unpack(v[t]); }
       }
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -98,8 +107,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
   for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], (double)s_acc[i]);
 }
 
-template <typename T> static inline bool ttg_vec_ok(int C, const void* const* ptrs, int n) {
-  if (C % Vec<T>::N) return false;
+template <typename T> static inline bool ttg_vec_ok(int C, const void* const* ptrs, int n, int vec = Vec<T>::N) {
+  if (C % vec) return false;
   for (int i = 0; i < n; ++i)
     if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return false;
   return true;
@@ -112,8 +121,9 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
   const void* ptrs[Op::NIN];
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
   size_t smem = sizeof(float) * Op::NACC * C;
-  if (ttg_vec_ok<T>(C, ptrs, Op::NIN) && C / Vec<T>::N <= 256) {
-    constexpr int V = Vec<T>::N;
+  constexpr int VV = ChanV<T, Op>::value;
+  if (ttg_vec_ok<T>(C, ptrs, Op::NIN, VV) && C / VV <= 256) {
+    constexpr int V = VV;
     int rpi = 256 / (C / V);
     int grid = ttg_grid_occ(chan_reduce_kernel<T, V, Op>, M, rpi * 4, 256, smem);
     chan_reduce_kernel<T, V, Op><<<grid, 256, smem, st>>>(op, M, C, out);
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, in
 #pragma unroll
         for (int t = 0; t < Op::NIN; ++t) {
           if constexpr (V == 1) v[u][t][0] = to_f(op.in[t][i]);
-          else { Vec<T> q; q.load(op.in[t] + i * V); q.unpack(v[u][t]); }
+          else { VecN<T, V> q; q.load(op.in[t] + i * V); q.unpack(v[u][t]); }
         }
       }
     }
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, in
 #pragma unroll
         for (int t = 0; t < Op::NOUT; ++t) {
           if constexpr (V == 1) op.out[t][base] = from_f<T>(o[t][0]);
-          else { Vec<T> q; q.pack(o[t]); q.store(op.out[t] + base); }
+          else { VecN<T, V> q; q.pack(o[t]); q.store(op.out[t] + base); }
         }
       }
     }
@@ -189,8 +199,8 @@ static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStre
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
   for (int i = 0; i < Op::NOUT; ++i) ptrs[Op::NIN + i] = op.out[i];
   if (n == 0) return TTG_OK;
-  if (ttg_vec_ok<T>(C, ptrs, Op::NIN + Op::NOUT)) {
-    constexpr int V = Vec<T>::N;
+  if (ttg_vec_ok<T>(C, ptrs, Op::NIN + Op::NOUT, ChanV<T, Op>::value)) {
+    constexpr int V = ChanV<T, Op>::value;
     long long nvec = n / V;
     int grid = ttg_grid_occ(chan_map_kernel<T, V, Op>, nvec, 256 * 2);
     int inv = ((long long)grid * 256 * V) % C == 0;

@@ -109,6 +109,27 @@ template <> struct Vec<bf16> {
   }
 };
 
+// N-element vectors (N chosen per kernel: 16-byte vectors by default, 8-byte bf16 vectors for register-heavy ops)
+template <typename T, int N> struct VecN;
+template <> struct VecN<float, 4> : Vec<float> {};
+template <> struct VecN<bf16, 8> : Vec<bf16> {};
+template <> struct VecN<bf16, 4> {
+  static constexpr int N = 4;
+  uint2 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint2*>(p) = raw; }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ __forceinline__ void pack(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -405,12 +405,41 @@ __device__ __forceinline__ void conv_tc_epilogue(uint32_t tacc, int warp, int ti
 // so a store instruction covers whole 32-byte sectors / 128-byte lines instead of 16 B out of every pixel.
 //   strip pitch = chunk bytes + 16  ->  both the pixel-major writes and the unit-major reads are conflict free.
 #define TC_EPI_CHUNK 64
-static inline int tc_epi_bytes(int Cout) { return 4 * 32 * ((Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK) * 2 + 16); }
+static inline int tc_epi_strip_bytes(int Cout) { return 4 * 32 * ((Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK) * 2 + 16); }
+// strips + per-CTA BatchNorm statistics accumulators (sum, sum of squares: 2 x Cout floats)
+static inline int tc_epi_bytes(int Cout) { return tc_epi_strip_bytes(Cout) + 2 * Cout * 4; }
+__device__ __forceinline__ int tc_epi_strip_bytes_dev(int Cout) { return 4 * 32 * ((Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK) * 2 + 16); }
+
+// Sum of 16 per-lane values over the 32 lanes of a warp, for all 16 values at once (butterfly that halves the
+// number of values a lane carries at every exchange: 8+4+2+1+1 shuffles instead of 16 x 5).  On return v[0] holds the
+// warp total of value index ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1).
+__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float keep = (lane & 16) ? v[j + 8] : v[j], send = (lane & 16) ? v[j] : v[j + 8];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float keep = (lane & 8) ? v[j + 4] : v[j], send = (lane & 8) ? v[j] : v[j + 4];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float keep = (lane & 4) ? v[j + 2] : v[j], send = (lane & 4) ? v[j] : v[j + 2];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float keep = (lane & 2) ? v[1] : v[0], send = (lane & 2) ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
 // `Cout` = channels stored per pixel (row pitch of y): the accumulator width, or 8 for the 8-channel staging tensors
 // of the RGB layers (accumulator columns 8..15 are padding and are dropped).
 __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_t* sE, int warp, int lane, int n, int y0, int x0,
                                                            int H, int W, int Cout, const float* __restrict__ bias,
-                                                           bf16* __restrict__ y) {
+                                                           bf16* __restrict__ y, float* s_stats = nullptr) {
   if (Cout == 8) {                       // one 16-byte unit per pixel: lanes are already on consecutive units
     uint32_t r[16];
     tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16), r);
@@ -449,6 +478,22 @@ __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_
       const uint32_t d = strip_addr + (uint32_t)(lane * pitch + c1 * 2);
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 16), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+      if (s_stats) {
+        // BatchNorm statistics of the tensor being written (the bf16-rounded values, pixels inside the image only)
+        const bool inside = (y0 + warp * 4 + (lane >> 3)) < H && (x0 + (lane & 7)) < W;
+        float v[16], q[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] = inside ? __uint_as_float(o[j] << 16) : 0.f;
+          v[2 * j + 1] = inside ? __uint_as_float(o[j] & 0xffff0000u) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) q[j] = v[j] * v[j];
+        warp_reduce16(v, lane);
+        warp_reduce16(q, lane);
+        const int ch = c0 + c1 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        atomicAdd(&s_stats[(lane & 1) ? Cout + ch : ch], (lane & 1) ? q[0] : v[0]);
+      }
     }
     __syncwarp();
     const int up_cur = ccur >> 3;
@@ -679,7 +724,7 @@ template <int K, int NBUF, int CIN>
 __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
                                                           int H, int W, int Cin_rt, int Cout, int total_tiles, int tmem_cols,
-                                                          int mode, int cstore) {
+                                                          int mode, int cstore, double* __restrict__ stats) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   constexpr int NACC = 4;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -707,6 +752,9 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
     x0 = (t2 % tiles_x) * TC_TW;
   };
 
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256 + tc_epi_strip_bytes_dev(Cout));
+  if (stats)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -748,7 +796,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
         }
       } else if (!out_f32)
         conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
-                                   cstore, bias, reinterpret_cast<bf16*>(y));
+                                   cstore, bias, reinterpret_cast<bf16*>(y), stats ? s_stats : nullptr);
       else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
@@ -807,13 +855,15 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (stats)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
 }
 
 static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
 template <int K, int NBUF, int CIN>
 static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
                               int Cin, int Cout, int cin_mem, int cstore, long long tiles, int w_bytes, int a_bytes, int pcols,
-                              cudaStream_t st, bool* used) {
+                              double* stats, cudaStream_t st, bool* used) {
   *used = false;
   ttg_encode_tiled_fn enc = ttg_get_encode_tiled();
   if (!enc) return TTG_OK;
@@ -858,7 +908,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
   conv_tc_tma_kernel<K, NBUF, CIN><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
-                                                                pcols, mode, cstore);
+                                                                pcols, mode, cstore, stats);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
   return TTG_OK;
@@ -909,7 +959,8 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
                                                                 const float* __restrict__ bias, void* __restrict__ y,
                                                                 int out_f32, int H, int W, int Cin_rt, int Cout_rt, int up,
                                                                 int total_tiles, int tmem_cols, int chunk_slices_rt,
-                                                                const __grid_constant__ CUtensorMap tmap) {
+                                                                const __grid_constant__ CUtensorMap tmap,
+                                                                double* __restrict__ stats) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   constexpr bool STATIC = CIN > 0;
   // weight ring: the issuing thread pays ~400 cycles of fixed cost per stage (mbarrier wait, fences, commit), so the
@@ -945,6 +996,9 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
     y0 = (t2 / tiles_x) * TC_TH;
     x0 = (t2 % tiles_x) * TC_TW;
   };
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(afull) + 256 + tc_epi_strip_bytes_dev(Cout));
+  if (stats)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&afull[i], TMA_A ? 1 : 128); mbar_init(&aempty[i], 1); }
@@ -978,7 +1032,7 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
       TTG_T0();
       if (!out_f32)
         conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(afull) + 256, warp, lane, n, y0, x0, H, W,
-                                   Cout, bias, reinterpret_cast<bf16*>(y));
+                                   Cout, bias, reinterpret_cast<bf16*>(y), stats ? s_stats : nullptr);
       else
         conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
@@ -1123,11 +1177,13 @@ __global__ void __launch_bounds__(192) conv_tc_stream_ws_kernel(const bf16* __re
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (stats)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
 }
 
 template <int K, int NA, int CIN, int COUT>
 static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
-                                    int Cin, int Cout, int up, long long tiles, cudaStream_t st) {
+                                    int Cin, int Cout, int up, long long tiles, double* stats, cudaStream_t st) {
   constexpr int HALO = K / 2;
   const int HP = (TC_TW + 2 * HALO) * (TC_TH + 2 * HALO);
   constexpr int NW = CIN > 0 ? 3 : 4, WSB = CIN > 0 ? 2 * TC_WSTAGE_BYTES : TC_WSTAGE_BYTES;
@@ -1160,10 +1216,10 @@ static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* 
   if (grid > tiles) grid = tiles;
   if (enc)
     conv_tc_stream_ws_kernel<K, NA, true, CIN, COUT><<<(unsigned)grid, 192, smem, st>>>(
-        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap);
+        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap, stats);
   else
     conv_tc_stream_ws_kernel<K, NA, false, CIN, COUT><<<(unsigned)grid, 192, smem, st>>>(
-        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap);
+        (const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, up, (int)tiles, cols, chunk_slices, tmap, stats);
   TTG_CHECK_LAUNCH("conv2d_tc_stream_ws");
   return TTG_OK;
 }
@@ -1173,9 +1229,11 @@ extern "C" int ttg_set_use_tma(int on) { g_use_tma = on; return TTG_OK; }
 
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
 // tensors in memory (equal to Cin / Cout except for the RGB layers).
-extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
-                                int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
-                                const float* pre_scale, const float* pre_shift, float slope, void* stream) {
+// stats (optional): double[2 * Cout], zeroed by the caller; receives sum / sum of squares per output channel of the
+// tensor written (BatchNorm statistics of the next layer, see ttg_conv2d_tc_stats).
+static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                          int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
+                          const float* pre_scale, const float* pre_shift, float slope, double* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // 8-channel staging tensors (ttg_pad_channels8) ride the TMA path: not "padded" in the scalar-access sense
   const bool in8 = cin_real == 8 && Cin == 16, out8 = cout_real == 8 && Cout == 16;
@@ -1220,7 +1278,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
       bool used = false;
       const int tcols = (int)tmem_cols_for(4 * Cout);
       const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
-#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, st, &used)
+#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, stats, st, &used)
       int rc;
       if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 4, 16) : Cin == 32 ? TTG_TMA(3, 4, 32) : Cin == 64 ? TTG_TMA(3, 3, 64)
                                      : (deep ? TTG_TMA(3, 4, 0) : TTG_TMA(3, 3, 0));
@@ -1229,6 +1287,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
 #undef TTG_TMA
       if (rc != TTG_OK || used) return rc;
     }
+    TTG_REQUIRE(stats == nullptr, "conv2d_tc: output statistics need the TMA kernels (bf16 output, no upsample / prologue / padding)");
     const bool lean = !padded && !pre_scale && (TC_TW + 2 * halo) * (Cin / 8) <= 128;
 #define TTG_PERSIST(KK, NB) (lean ? launch_conv_tc_persist<KK, NB, true>(x, wp, bias, y, of32, H, W, Cin, Cout, up, pre_scale, \
                                         pre_shift, slope, tiles, psmem, pcols, per_sm, cin_real, cout_real, st)              \
@@ -1242,7 +1301,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
     const int a_bytes = (Cin / 8) * HP * 16;
     const bool two = 2 * a_bytes + 4 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 200 * 1024;
     const int of32 = dtype_out == TTG_F32;
-#define TTG_STREAM(KK, NAA, CI, CO) launch_conv_tc_stream_ws<KK, NAA, CI, CO>(x, wp, bias, y, of32, N, H, W, Cin, Cout, up, tiles, st)
+#define TTG_STREAM(KK, NAA, CI, CO) launch_conv_tc_stream_ws<KK, NAA, CI, CO>(x, wp, bias, y, of32, N, H, W, Cin, Cout, up, tiles, stats, st)
     const bool two32 = 2 * a_bytes + 6 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 224 * 1024;
     const bool one32 = a_bytes + 6 * TC_WSTAGE_BYTES + 256 + tc_epi_bytes(Cout) <= 224 * 1024;
     if (ksize == 3 && two32) {
@@ -1259,6 +1318,7 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
     return two ? TTG_STREAM(1, 2, 0, 0) : TTG_STREAM(1, 1, 0, 0);
 #undef TTG_STREAM
   }
+  TTG_REQUIRE(stats == nullptr, "conv2d_tc: output statistics are not available on the generic streaming kernel");
   const int ki = ksize == 3 ? 1 : 0;
   if (smem > g_conv_tc_smem[ki]) {
     cudaError_t e = ksize == 3
@@ -1276,6 +1336,29 @@ extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias
                                                          Cin, Cout, up, pre_scale, pre_shift, slope, stage_slices, nstages, cols);
   TTG_CHECK_LAUNCH("conv2d_tc");
   return TTG_OK;
+}
+
+extern "C" int ttg_conv2d_tc_ex(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                                int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
+                                const float* pre_scale, const float* pre_shift, float slope, void* stream) {
+  return conv2d_tc_core(x, wp, bias, y, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, dtype_out, pre_scale, pre_shift, slope,
+                        nullptr, stream);
+}
+// conv + BatchNorm statistics of its output in one pass: sums[0..Cout) = sum_pixels y, sums[Cout..2Cout) = sum y^2
+// (fp64, of the bf16 values written).  The epilogue reduces the tile it holds in registers, so the statistics pass of
+// the following nn.BatchNorm2d (native_batch_norm's first read of the tensor) disappears.
+extern "C" int ttg_conv2d_tc_stats_supported(int Cin, int Cout, int ksize) {
+  if (!g_use_tma || ttg_get_encode_tiled() == nullptr) return 0;
+  if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16 || Cin > 256 || Cout > 256 || (ksize != 1 && ksize != 3)) return 0;
+  const int w_bytes = ksize * ksize * (Cin / 16) * Cout * 32;
+  return w_bytes <= TC_RESIDENT_W_BYTES || Cout * 32 <= TC_WSTAGE_BYTES;
+}
+extern "C" int ttg_conv2d_tc_stats(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
+                                   int Cout, int ksize, double* sums, void* stream) {
+  TTG_REQUIRE(sums != nullptr, "conv2d_tc_stats: sums is required");
+  TTG_REQUIRE(ttg_conv2d_tc_stats_supported(Cin, Cout, ksize), "conv2d_tc_stats: unsupported layer %d -> %d k%d", Cin, Cout, ksize);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)Cout, (cudaStream_t)stream);
+  return conv2d_tc_core(x, wp, bias, y, N, H, W, Cin, Cout, Cin, Cout, ksize, 0, TTG_BF16, nullptr, nullptr, 1.f, sums, stream);
 }
 
 extern "C" int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,

@@ -57,6 +57,17 @@ extern "C" int ttg_bn_stats(const void* x, long long M, int C, float eps, float 
   return TTG_OK;
 }
 
+// statistics already accumulated by the producer of x (ttg_conv2d_tc_stats): sums = {sum x, sum x^2} in fp64
+extern "C" int ttg_bn_finalize(const double* sums, long long M, int C, float eps, float momentum, float* mean, float* invstd,
+                               float* running_mean, float* running_var, long long* num_batches, long long count_mult,
+                               void* stream) {
+  TTG_REQUIRE(M > 0 && C > 0 && count_mult >= 1 && sums != nullptr, "bn_finalize: empty input");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, M, count_mult, C, eps, momentum, mean, invstd,
+                                                                       running_mean, running_var, num_batches);
+  TTG_CHECK_LAUNCH("bn_finalize");
+  return TTG_OK;
+}
+
 // eval-mode helper: mean/invstd from running statistics.
 __global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, int C, float* mean, float* invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;

@@ -22,8 +22,8 @@ class Conv2d(nn.Conv2d):
             raise NotImplementedError('tartangan_b200.Conv2d supports kernel 1 or 3, stride 1, padding k//2 '
                                       f'(got k={self.kernel_size}, stride={self.stride}, padding={self.padding})')
 
-    def forward(self, x, up=0, out_dtype=None):
-        return ops.conv2d(ops.ensure_internal(x), self.weight, self.bias, up, out_dtype)
+    def forward(self, x, up=0, out_dtype=None, stats=False):
+        return ops.conv2d(ops.ensure_internal(x), self.weight, self.bias, up, out_dtype, stats)
 
 
 class BatchNorm2d(nn.BatchNorm2d):
@@ -121,8 +121,10 @@ def run_layers(layers, x, up_first=False):
             i += 2
         elif isinstance(m, nn.Identity):
             i += 1
-        elif pending_up and isinstance(m, Conv2d):
-            x = m(x, up=1)
+        elif isinstance(m, Conv2d):
+            # a conv that feeds a train-mode BatchNorm reduces that layer's batch statistics in its epilogue
+            feeds_bn = isinstance(nxt, BatchNorm2d) and (nxt.training or nxt.running_mean is None)
+            x = m(x, up=1 if pending_up else 0, stats=feeds_bn)
             pending_up = False
             i += 1
         elif pending_up and not isinstance(m, LeakyReLU):
@@ -155,7 +157,7 @@ class SpectralNormConv2d(Conv2d):
         self.register_buffer('weight_v', v)
         self.n_power_iterations, self.sn_eps = n_power_iterations, eps
 
-    def forward(self, x, up=0, out_dtype=None):
+    def forward(self, x, up=0, out_dtype=None, stats=False):
         w = ops.SpectralNormFn.apply(self.weight_orig, self.weight_u, self.weight_v,
                                      self.n_power_iterations if self.training else 0, self.sn_eps)
-        return ops.conv2d(ops.ensure_internal(x), w, self.bias, up, out_dtype)
+        return ops.conv2d(ops.ensure_internal(x), w, self.bias, up, out_dtype, stats)

@@ -11,6 +11,8 @@ Activation tensors keep the reference's logical NCHW shape but live in NHWC memo
 (``torch.channels_last`` strides); their dtype (fp32 or bf16) is the precision mode.
 PyTorch is used for allocation, streams and autograd bookkeeping only.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -26,6 +28,7 @@ class _State:
     use_tc = True                  # tensor-core conv kernels when shapes allow
     launches = 0                   # kernels launched through the C ABI (bench counter)
     pack_generation = 0            # bumped to invalidate every packed-weight cache (CUDA-graph capture)
+    producer_stats = None          # (weakref(tensor), float64 sums) left by conv2d(..., stats=True) for bn_act
 
 
 state = _State()
@@ -218,8 +221,16 @@ def _tc_ok(dtype, cin, cout):
     return state.use_tc and dtype == torch.bfloat16 and ok(cin) and ok(cout)
 
 
-def _conv_raw(x, w, bias, mode, up, out_dtype=None):
-    """y = conv(x) with w packed in `mode` (0 fprop: w is OIHW; 1 dgrad: roles swapped)."""
+def conv_stats_ok(w, up, dtype):
+    """True when conv2d(..., stats=True) can return the BatchNorm statistics of its output from the conv epilogue."""
+    cout, cin, k, _ = w.shape
+    return (not up and dtype == torch.bfloat16 and state.use_tc and cin % 16 == 0 and cout % 16 == 0
+            and bool(_lib.lib.ttg_conv2d_tc_stats_supported(cin, cout, k)))
+
+
+def _conv_raw(x, w, bias, mode, up, out_dtype=None, stats=None):
+    """y = conv(x) with w packed in `mode` (0 fprop: w is OIHW; 1 dgrad: roles swapped).
+    stats: optional float64[2*Cout] that receives sum / sum of squares of the output (fprop, TMA kernels only)."""
     x = nhwc(x)
     n, cx, hi, wi = x.shape
     cout, cin, k, _ = w.shape
@@ -230,6 +241,9 @@ def _conv_raw(x, w, bias, mode, up, out_dtype=None):
     y = empty_nhwc(n, c_out_eff, h, wd_, out_dtype, x.device)
     if _tc_ok(x.dtype, cin, cout) and out_dtype in (torch.bfloat16, torch.float32):
         wp = _packed(w, mode, 'tc')
+        if stats is not None:
+            call('ttg_conv2d_tc_stats', ptr(x), ptr(wp), ptr(bias), ptr(y), n, h, wd_, c_in_eff, c_out_eff, k, ptr(stats))
+            return y
         # RGB layers: stage the <= 8-channel tensor as 8-channel pixels so the layer runs on the TMA kernels
         stage8 = up == 0 and out_dtype == torch.bfloat16
         xin, cin_mem = (_pad8(x), 8) if (stage8 and c_in_eff < 8) else (x, c_in_eff)
@@ -249,10 +263,10 @@ class Conv2dFn(Function):
     """nn.Conv2d(k in {1,3}, padding=k//2) with optional nearest x2 upsample of the input folded in."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, up, out_dtype):
+    def forward(ctx, x, w, bias, up, out_dtype, stats=None):
         ctx.save_for_backward(x, w)
         ctx.up, ctx.has_bias, ctx.in_dtype = up, bias is not None, x.dtype
-        return _conv_raw(x, w, bias, 0, up, out_dtype)
+        return _conv_raw(x, w, bias, 0, up, out_dtype, stats)
 
     @staticmethod
     def backward(ctx, gy):
@@ -267,7 +281,7 @@ class Conv2dFn(Function):
                 gw = ConvWgradFn.apply(x, gy, w.shape[2], ctx.up)
             if ctx.has_bias and ctx.needs_input_grad[2]:
                 gb = ChannelSumFn.apply(gy)
-        return gx, gw, gb, None, None
+        return gx, gw, gb, None, None, None
 
 
 class ConvDgradFn(Function):
@@ -334,13 +348,28 @@ class ConvWgradFn(Function):
         return g_x, g_gy, None, None
 
 
-def conv2d(x, w, bias=None, up=0, out_dtype=None):
+def conv2d(x, w, bias=None, up=0, out_dtype=None, stats=False):
     if up and x.dtype == torch.bfloat16 and _tc_ok(x.dtype, w.shape[1], w.shape[0]):
         # tensor-core path: materialise the nearest x2 upsample (one streaming pass) so that fprop AND wgrad fetch
         # their tiles with TMA; measured 2-3x faster than gathering (y>>1, x>>1) with cp.async inside the conv
         # (32->16 @128^2: 197 us -> ~105 us).  The fp32 path keeps the upsample folded into the conv.
         x, up = upsample2(x), 0
+    if stats and conv_stats_ok(w, up, x.dtype) and out_dtype in (None, torch.bfloat16):
+        # the conv epilogue also accumulates the BatchNorm statistics of y; bn_act() picks them up (same tensor object)
+        sums = torch.empty(2 * w.shape[0], dtype=torch.float64, device=x.device)
+        y = Conv2dFn.apply(x, w, bias, up, out_dtype, sums)
+        state.producer_stats = (weakref.ref(y), sums)
+        return y
     return Conv2dFn.apply(x, w, bias, up, out_dtype)
+
+
+def take_producer_stats(x):
+    """Statistics left by the kernel that produced x (or None).  Consumed at most once, and only by the very tensor
+    object they were computed for."""
+    ps, state.producer_stats = state.producer_stats, None
+    if ps is not None and ps[0]() is x:
+        return ps[1]
+    return None
 
 
 class ChannelSumFn(Function):
@@ -378,14 +407,18 @@ class BnActFn(Function):
     """lrelu(batch_norm(x)) with batch statistics (train) or running statistics (eval)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, training, momentum, eps, slope, count_mult=1):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, num_batches, training, momentum, eps, slope, count_mult=1,
+                sums=None):
         x = nhwc(x)
         n, c, h, w = x.shape
         m = n * h * w
         dev = x.device
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
-        if training:
+        if training and sums is not None:       # statistics already reduced by the producing conv's epilogue
+            call('ttg_bn_finalize', ptr(sums), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
+                 ptr(running_var), ptr(num_batches), count_mult)
+        elif training:
             ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
             call('ttg_bn_stats', ptr(x), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
                  ptr(running_var), ptr(num_batches), ptr(ws), count_mult, dtype_code(x.dtype))
@@ -407,7 +440,7 @@ class BnActFn(Function):
         gx, ggamma, gbeta = BnActBwdFn.apply(x, ga, gamma, beta, mean, invstd, ctx.slope)
         if state.inputs_only:
             ggamma = gbeta = None
-        return gx, ggamma, gbeta, None, None, None, None, None, None, None, None
+        return gx, ggamma, gbeta, None, None, None, None, None, None, None, None, None
 
 
 class BnActBwdFn(Function):
@@ -450,10 +483,11 @@ def bn_act(x, bn, slope=SLOPE, count_mult=1):
     """x -> lrelu(bn(x)) for an nn.BatchNorm2d-compatible module `bn` (or identity norm if None).
     count_mult=4: x is the low-resolution source of a nearest x2 upsample; statistics are identical,
     only the unbiased running-variance correction uses the upsampled element count."""
+    sums = take_producer_stats(x)
     if bn is None:
         return leaky_relu(x, slope)
     return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                         bn.training or bn.running_mean is None, bn.momentum, bn.eps, slope, count_mult)
+                         bn.training or bn.running_mean is None, bn.momentum, bn.eps, slope, count_mult, sums)
 
 
 class LeakyReluFn(Function):
