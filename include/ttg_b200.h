@@ -131,6 +131,13 @@ int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C
 /* fused residual joins: h + nearest_up2(skip) (generator.py:58-62) and avg_pool2(h) + skip (discriminator.py:67,95) */
 int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, int dtype, void* stream);
 int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream);
+/* residual joins that also return the BatchNorm statistics of the tensor they write (sums: double[2C] = sum, sum of
+ * squares of the rounded outputs; bf16, C % 8 == 0); the next block starts with nn.BatchNorm2d (generator.py:38,
+ * discriminator.py:60, 132, 153) */
+int ttg_join_stats_supported(int C);
+int ttg_add_up2_stats(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, double* sums, int dtype, void* stream);
+int ttg_pool2_add_stats(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, double* sums,
+                        int dtype, void* stream);
 int ttg_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int dtype, void* stream);
 int ttg_scale_f32(const float* x, float* out, long long n, float host_scale, const float* dev_scale, void* stream);
 int ttg_spatial_sum(const void* x, float* out, int N, int HW, int C, int dtype, void* stream);

@@ -168,11 +168,43 @@ extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, in
   return TTG_OK;
 }
 
+// BatchNorm statistics of the tensor a join kernel writes (sum / sum of squares per channel of the ROUNDED values):
+// every thread owns one fixed 8-channel group (256 % (C/8) == 0), keeps 16 partial sums in registers, lanes of the
+// same group are combined with shuffles, then one shared atomic per (warp, channel) and one fp64 atomic per
+// (block, channel).  The residual blocks' outputs feed the next block's BatchNorm (generator.py:38, discriminator.py:60).
+template <typename T> __device__ __forceinline__ float ttg_rounded(float v) { return to_f(from_f<T>(v)); }
+template <int V>
+__device__ __forceinline__ void join_stats_flush(float (&sa)[V], float (&sq)[V], int cv, int C, double* __restrict__ stats) {
+  extern __shared__ float s_join[];            // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_join[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x % cv;
+  const bool pow2 = (cv & (cv - 1)) == 0 && cv <= 32;
+  if (pow2) {
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      for (int o = 16; o >= cv; o >>= 1) {
+        sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], o);
+        sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
+      }
+  }
+  if (!pow2 || (threadIdx.x & 31) < cv) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) { atomicAdd(&s_join[g * V + j], sa[j]); atomicAdd(&s_join[C + g * V + j], sq[j]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&stats[i], (double)s_join[i]);
+}
+
 // out[n,oy,ox,c] = h[n,oy,ox,c] + s[n,oy/2,ox/2,c]   (residual add with the nearest-upsampled skip folded in)
-template <typename T, int V>
-__global__ void add_up2_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C) {
+template <typename T, int V, bool STATS = false>
+__global__ void add_up2_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C,
+                               double* __restrict__ stats = nullptr) {
   const int cv = C / V; const int Hi = Ho / 2, Wi = Wo / 2;
   const long long total = (long long)N * Ho * Wo * cv;
+  float sa[V], sq[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) sa[j] = sq[j] = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % cv) * V; long long p = i / cv;
     int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
@@ -182,7 +214,30 @@ __global__ void add_up2_kernel(const T* __restrict__ h, const T* __restrict__ s,
 #pragma unroll
     for (int j = 0; j < V; ++j) a[j] += b[j];
     Ld<T, V>::st(y + i * V, a);
+    if constexpr (STATS) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const float r = ttg_rounded<T>(a[j]); sa[j] += r; sq[j] += r * r; }
+    }
   }
+  if constexpr (STATS) join_stats_flush<V>(sa, sq, cv, C, stats);
+}
+// join + BatchNorm statistics of its output (sums: double[2C], see join_stats_flush); 16-byte vector path only
+extern "C" int ttg_join_stats_supported(int C) { return C % 8 == 0 && 256 % (C / 8) == 0 && C <= 256; }
+extern "C" int ttg_add_up2_stats(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, double* sums, int dtype,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "add_up2: odd output size");
+  TTG_REQUIRE(sums != nullptr && ttg_join_stats_supported(C), "add_up2_stats: unsupported channel count %d", C);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st);
+  TTG_DISPATCH(dtype, {
+    TTG_REQUIRE((vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) && Vec<T>::N == 8, "add_up2_stats: bf16, 16-byte aligned tensors");
+    constexpr int V = 8;
+    const size_t smem = sizeof(float) * 2 * C;
+    add_up2_kernel<T, V, true><<<ttg_grid_occ(add_up2_kernel<T, V, true>, (long long)N * Ho * Wo * (C / V), 512, 256, smem), 256, smem, st>>>(
+        (const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, sums);
+  });
+  TTG_CHECK_LAUNCH("add_up2_stats");
+  return TTG_OK;
 }
 extern "C" int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -196,10 +251,14 @@ extern "C" int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho,
 }
 
 // out[n,oy,ox,c] = scale * sum_{2x2} h + s[n,oy,ox,c]   (AvgPool2d(2) of the conv path + skip, one pass)
-template <typename T, int V>
-__global__ void pool2_add_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C, float scale) {
+template <typename T, int V, bool STATS = false>
+__global__ void pool2_add_kernel(const T* __restrict__ h, const T* __restrict__ s, T* __restrict__ y, int N, int Ho, int Wo, int C, float scale,
+                                 double* __restrict__ stats = nullptr) {
   const int cv = C / V; const int Wi = Wo * 2;
   const long long total = (long long)N * Ho * Wo * cv;
+  float sa[V], sq[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) sa[j] = sq[j] = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % cv) * V; long long p = i / cv;
     int ox = (int)(p % Wo); p /= Wo; int oy = (int)(p % Ho); int n = (int)(p / Ho);
@@ -213,7 +272,27 @@ __global__ void pool2_add_kernel(const T* __restrict__ h, const T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = (acc[j] + a[j] + b[j]) * scale + sk[j];
     Ld<T, V>::st(y + i * V, acc);
+    if constexpr (STATS) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { const float r = ttg_rounded<T>(acc[j]); sa[j] += r; sq[j] += r * r; }
+    }
   }
+  if constexpr (STATS) join_stats_flush<V>(sa, sq, cv, C, stats);
+}
+extern "C" int ttg_pool2_add_stats(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, double* sums,
+                                   int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(sums != nullptr && ttg_join_stats_supported(C), "pool2_add_stats: unsupported channel count %d", C);
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st);
+  TTG_DISPATCH(dtype, {
+    TTG_REQUIRE((vec2_ok<T>(C, h, s) && vec2_ok<T>(C, y, y)) && Vec<T>::N == 8, "pool2_add_stats: bf16, 16-byte aligned tensors");
+    constexpr int V = 8;
+    const size_t smem = sizeof(float) * 2 * C;
+    pool2_add_kernel<T, V, true><<<ttg_grid_occ(pool2_add_kernel<T, V, true>, (long long)N * Ho * Wo * (C / V), 256, 256, smem), 256, smem, st>>>(
+        (const T*)h, (const T*)s, (T*)y, N, Ho, Wo, C, scale, sums);
+  });
+  TTG_CHECK_LAUNCH("pool2_add_stats");
+  return TTG_OK;
 }
 extern "C" int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

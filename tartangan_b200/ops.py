@@ -28,7 +28,7 @@ class _State:
     use_tc = True                  # tensor-core conv kernels when shapes allow
     launches = 0                   # kernels launched through the C ABI (bench counter)
     pack_generation = 0            # bumped to invalidate every packed-weight cache (CUDA-graph capture)
-    producer_stats = None          # (weakref(tensor), float64 sums) left by conv2d(..., stats=True) for bn_act
+    producer_stats = None          # (tensor, float64 sums) left by a producer kernel (conv / residual join) for bn_act
 
 
 state = _State()
@@ -358,18 +358,25 @@ def conv2d(x, w, bias=None, up=0, out_dtype=None, stats=False):
         # the conv epilogue also accumulates the BatchNorm statistics of y; bn_act() picks them up (same tensor object)
         sums = torch.empty(2 * w.shape[0], dtype=torch.float64, device=x.device)
         y = Conv2dFn.apply(x, w, bias, up, out_dtype, sums)
-        state.producer_stats = (weakref.ref(y), sums)
+        state.producer_stats = (y, sums)
         return y
     return Conv2dFn.apply(x, w, bias, up, out_dtype)
 
 
 def take_producer_stats(x):
-    """Statistics left by the kernel that produced x (or None).  Consumed at most once, and only by the very tensor
-    object they were computed for."""
+    """Statistics left by the kernel that produced x (or None).  Consumed at most once (by the first bn_act after the
+    producer) and only for the same memory: the producer's output is kept alive until then, so its address cannot
+    have been recycled for another tensor."""
     ps, state.producer_stats = state.producer_stats, None
-    if ps is not None and ps[0]() is x:
+    if ps is not None and ps[0].data_ptr() == x.data_ptr() and ps[0].shape == x.shape and ps[0].dtype == x.dtype \
+            and ps[0].stride() == x.stride():
         return ps[1]
     return None
+
+
+def _join_stats_ok(t):
+    return (t.dtype == torch.bfloat16 and t.dim() == 4
+            and bool(_lib.lib.ttg_join_stats_supported(t.shape[1])))
 
 
 class ChannelSumFn(Function):
@@ -575,40 +582,58 @@ class AddUp2Fn(Function):
     """h + nearest_up2(s): the generator's residual join with the upsample of the skip folded in."""
 
     @staticmethod
-    def forward(ctx, h, s):
+    def forward(ctx, h, s, sums=None):
         h, s = nhwc(h), nhwc(s)
         n, c, ho, wo = h.shape
         y = _empty_like(h)
-        call('ttg_add_up2', ptr(h), ptr(s), ptr(y), n, ho, wo, c, dtype_code(h.dtype))
+        if sums is not None:
+            call('ttg_add_up2_stats', ptr(h), ptr(s), ptr(y), n, ho, wo, c, ptr(sums), dtype_code(h.dtype))
+        else:
+            call('ttg_add_up2', ptr(h), ptr(s), ptr(y), n, ho, wo, c, dtype_code(h.dtype))
         return y
 
     @staticmethod
     def backward(ctx, g):
-        return g, Pool2Fn.apply(g, 1.0)
+        return g, Pool2Fn.apply(g, 1.0), None
 
 
 class Pool2AddFn(Function):
     """scale * pool2sum(h) + s: the discriminator's residual join with AvgPool2d(2) folded in."""
 
     @staticmethod
-    def forward(ctx, h, s, scale):
+    def forward(ctx, h, s, scale, sums=None):
         ctx.scale = scale
         h, s = nhwc(h), nhwc(s)
         n, c, ho, wo = s.shape
         y = _empty_like(s)
-        call('ttg_pool2_add', ptr(h), ptr(s), ptr(y), n, ho, wo, c, scale, dtype_code(h.dtype))
+        if sums is not None:
+            call('ttg_pool2_add_stats', ptr(h), ptr(s), ptr(y), n, ho, wo, c, scale, ptr(sums), dtype_code(h.dtype))
+        else:
+            call('ttg_pool2_add', ptr(h), ptr(s), ptr(y), n, ho, wo, c, scale, dtype_code(h.dtype))
         return y
 
     @staticmethod
     def backward(ctx, g):
-        return Up2Fn.apply(g, ctx.scale), g, None
+        return Up2Fn.apply(g, ctx.scale), g, None, None
 
 
-def add_up2(h, s):
+def add_up2(h, s, stats=True):
+    """stats: also reduce the BatchNorm statistics of the result (the next block / the output layer starts with a
+    BatchNorm over exactly this tensor); bn_act() picks them up."""
+    if stats and _join_stats_ok(h):
+        sums = torch.empty(2 * h.shape[1], dtype=torch.float64, device=h.device)
+        y = AddUp2Fn.apply(h, s, sums)
+        state.producer_stats = (y, sums)
+        return y
     return AddUp2Fn.apply(h, s)
 
 
-def avg_pool2_add(h, s):
+def avg_pool2_add(h, s, stats=True):
+    if stats and _join_stats_ok(s):
+        sums = torch.empty(2 * s.shape[1], dtype=torch.float64, device=s.device)
+        y = Pool2AddFn.apply(h, s, 0.25, sums)
+        state.producer_stats = (y, sums)
+        return y
     return Pool2AddFn.apply(h, s, 0.25)
 
 
