@@ -107,6 +107,197 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
   for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], (double)s_acc[i]);
 }
 
+
+// ====================================================================================================================
+// Bulk-copy (TMA 1-D) pipelined variants for bf16 tensors.  The register-fed kernels above keep at most
+// 2 x NIN 16-byte loads per thread in flight, and the per-channel coefficients cost them most of their occupancy
+// (80-180 registers), so they stall at 45-60 % of HBM bandwidth.  Here one producer lane streams 8 KB chunks of every
+// input tensor into a 4-stage shared-memory ring with cp.async.bulk (bytes in flight per SM no longer depend on
+// registers or occupancy); the 8 consumer warps read the ring with LDS.128, apply the same Op, and write results
+// with coalesced 16-byte stores.
+// Requirements: bf16, 16-byte aligned, (C / 8) a power of two <= 32  ->  a thread always sees the same 8 channels.
+#include "tc_common.cuh"
+#define CB_STAGES 4
+#define CB_UNITS 512                      // 16-byte units per tensor per stage (8 KB)
+#define CB_THREADS 288                    // 8 consumer warps + 1 producer warp
+
+template <class Op>
+__device__ __forceinline__ void cb_producer(const Op& op, uint8_t* ring, uint64_t* full, uint64_t* empty, long long nvec,
+                                            long long nchunks) {
+  if (!elect_one()) return;
+  int it = 0;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % CB_STAGES;
+    if (it >= CB_STAGES) mbar_wait(&empty[s], (uint32_t)((it / CB_STAGES) - 1) & 1u);
+    const long long off = c * CB_UNITS;
+    const uint32_t units = (uint32_t)min((long long)CB_UNITS, nvec - off);
+    const uint32_t bytes = units * 16u;
+    const uint32_t bar = smem_u32(&full[s]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * Op::NIN) : "memory");
+#pragma unroll
+    for (int t = 0; t < Op::NIN; ++t) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(op.in[t]) + off * 16;
+      const uint32_t dst = smem_u32(ring + ((size_t)s * Op::NIN + t) * CB_UNITS * 16);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+  }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(CB_THREADS) chan_map_bulk_kernel(Op op, long long nvec, int C) {
+  extern __shared__ __align__(128) uint8_t cb_smem[];
+  uint8_t* ring = cb_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16);
+  uint64_t* empty = full + CB_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int i = 0; i < CB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
+  if (warp == 8) { cb_producer(op, ring, full, empty, nvec, nchunks); return; }
+  typename Op::template P<8> prm;
+  op.template load<8>((tid % (C >> 3)) * 8, prm);
+  int it = 0;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int s = it % CB_STAGES;
+    const long long off = c * CB_UNITS;
+    const int units = (int)min((long long)CB_UNITS, nvec - off);
+    mbar_wait(&full[s], (uint32_t)(it / CB_STAGES) & 1u);
+#pragma unroll
+    for (int k = 0; k < CB_UNITS / 256; ++k) {
+      const int u = tid + 256 * k;
+      if (u < units) {
+        float v[Op::NIN][8], o[Op::NOUT][8];
+#pragma unroll
+        for (int t = 0; t < Op::NIN; ++t) {
+          Vec<bf16> q;
+          q.raw = *reinterpret_cast<const uint4*>(ring + (((size_t)s * Op::NIN + t) * CB_UNITS + u) * 16);
+          q.unpack(v[t]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float vin[Op::NIN], vout[Op::NOUT];
+#pragma unroll
+          for (int t = 0; t < Op::NIN; ++t) vin[t] = v[t][j];
+          op.template apply<8>(vin, j, prm, vout);
+#pragma unroll
+          for (int t = 0; t < Op::NOUT; ++t) o[t][j] = vout[t];
+        }
+#pragma unroll
+        for (int t = 0; t < Op::NOUT; ++t) { Vec<bf16> q; q.pack(o[t]); q.store(op.out[t] + (off + u) * 8); }
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+  }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(CB_THREADS) chan_reduce_bulk_kernel(Op op, long long nvec, int C, double* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t cb_smem[];
+  uint8_t* ring = cb_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16);
+  uint64_t* empty = full + CB_STAGES;
+  float* s_acc = reinterpret_cast<float*>(empty + CB_STAGES);          // [NACC][C]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < Op::NACC * C; i += blockDim.x) s_acc[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < CB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const long long nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
+  const int groups = C >> 3, g = tid % groups;
+  if (warp == 8) {
+    cb_producer(op, ring, full, empty, nvec, nchunks);
+  } else {
+    float a[Op::NACC][8];
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[k][j] = 0.f;
+    typename Op::template P<8> prm;
+    op.template load<8>(g * 8, prm);
+    int it = 0;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+      const int s = it % CB_STAGES;
+      const int units = (int)min((long long)CB_UNITS, nvec - c * CB_UNITS);
+      mbar_wait(&full[s], (uint32_t)(it / CB_STAGES) & 1u);
+#pragma unroll
+      for (int k = 0; k < CB_UNITS / 256; ++k) {
+        const int u = tid + 256 * k;
+        if (u < units) {
+          float v[Op::NIN][8];
+#pragma unroll
+          for (int t = 0; t < Op::NIN; ++t) {
+            Vec<bf16> q;
+            q.raw = *reinterpret_cast<const uint4*>(ring + (((size_t)s * Op::NIN + t) * CB_UNITS + u) * 16);
+            q.unpack(v[t]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float vin[Op::NIN], acc[Op::NACC];
+#pragma unroll
+            for (int t = 0; t < Op::NIN; ++t) vin[t] = v[t][j];
+#pragma unroll
+            for (int k2 = 0; k2 < Op::NACC; ++k2) acc[k2] = a[k2][j];
+            op.template acc<8>(vin, j, prm, acc);
+#pragma unroll
+            for (int k2 = 0; k2 < Op::NACC; ++k2) a[k2][j] = acc[k2];
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+    }
+    // lanes that own the same channel group are combined with shuffles, then one shared atomic per (warp, channel)
+#pragma unroll
+    for (int k = 0; k < Op::NACC; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = a[k][j];
+        for (int o = 16; o >= groups; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        a[k][j] = t;
+      }
+    if ((tid & 31) < groups) {
+#pragma unroll
+      for (int k = 0; k < Op::NACC; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[k * C + g * 8 + j], a[k][j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], (double)s_acc[i]);
+}
+
+static int g_chan_bulk = 1;      // development switch (ttg_set_chan_bulk)
+template <typename T, class Op> static inline bool cb_ok(int C, const void* const* ptrs, int n, long long nelem) {
+  if (!g_chan_bulk || !std::is_same<T, bf16>::value) return false;
+  const int groups = C >> 3;
+  if (C % 8 || groups < 1 || groups > 32 || (groups & (groups - 1)) || nelem % 8) return false;
+  for (int i = 0; i < n; ++i)
+    if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return false;
+  return nelem >= 8LL * CB_UNITS * 148;            // small tensors: the register kernels (less fixed cost)
+}
+template <class Kern> static inline int cb_grid(Kern kernel, long long nchunks, size_t smem, int* err) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> done;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find((const void*)kernel);
+    if (it == done.end() || it->second < smem) {
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { *err = 1; return 1; }
+      done[(const void*)kernel] = smem;
+    }
+  }
+  long long cap = (long long)ttg_num_sms() * ttg_blocks_per_sm((const void*)kernel, CB_THREADS, smem);
+  long long b = nchunks < cap ? nchunks : cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 template <typename T> static inline bool ttg_vec_ok(int C, const void* const* ptrs, int n, int vec = Vec<T>::N) {
   if (C % vec) return false;
   for (int i = 0; i < n; ++i)
@@ -120,6 +311,18 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
   cudaMemsetAsync(out, 0, sizeof(double) * Op::NACC * C, st);
   const void* ptrs[Op::NIN];
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (cb_ok<T, Op>(C, ptrs, Op::NIN, M * C)) {
+      const long long nvec = M * C / 8, nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
+      const size_t bsmem = (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16 + 2 * CB_STAGES * 8 + sizeof(float) * Op::NACC * C;
+      int err = 0;
+      const int grid = cb_grid(chan_reduce_bulk_kernel<Op>, nchunks, bsmem, &err);
+      if (err) return ttg_set_error(TTG_ERR_CUDA, "%s: shared memory attribute", name);
+      chan_reduce_bulk_kernel<Op><<<grid, CB_THREADS, bsmem, st>>>(op, nvec, C, out);
+      TTG_CHECK_LAUNCH(name);
+      return TTG_OK;
+    }
+  }
   size_t smem = sizeof(float) * Op::NACC * C;
   constexpr int VV = ChanV<T, Op>::value;
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN, VV) && C / VV <= 256) {
@@ -199,6 +402,18 @@ static int launch_chan_map(const char* name, Op op, long long n, int C, cudaStre
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
   for (int i = 0; i < Op::NOUT; ++i) ptrs[Op::NIN + i] = op.out[i];
   if (n == 0) return TTG_OK;
+  if constexpr (std::is_same<T, bf16>::value) {
+    if (!reverse && cb_ok<T, Op>(C, ptrs, Op::NIN + Op::NOUT, n)) {
+      const long long nvec = n / 8, nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
+      const size_t bsmem = (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16 + 2 * CB_STAGES * 8;
+      int err = 0;
+      const int grid = cb_grid(chan_map_bulk_kernel<Op>, nchunks, bsmem, &err);
+      if (err) return ttg_set_error(TTG_ERR_CUDA, "%s: shared memory attribute", name);
+      chan_map_bulk_kernel<Op><<<grid, CB_THREADS, bsmem, st>>>(op, nvec, C);
+      TTG_CHECK_LAUNCH(name);
+      return TTG_OK;
+    }
+  }
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN + Op::NOUT, ChanV<T, Op>::value)) {
     constexpr int V = ChanV<T, Op>::value;
     long long nvec = n / V;

@@ -516,9 +516,6 @@ __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Warp-specialised persistent kernel: warps 0-3 stage tiles (cp.async, NBUF-deep ring) and run the
 // epilogue; warp 4 only issues tcgen05.mma.  Hand-offs are mbarriers (full/empty per activation slot,
