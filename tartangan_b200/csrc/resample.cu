@@ -6,7 +6,7 @@
 //   residual add (generator.py:62, discriminator.py:95), sum over H,W
 //   (discriminator.py:143,166), NCHW fp32 <-> NHWC conversions at the module
 //   boundary, tanh (generator.py:126).
-#include "common.cuh"
+#include "chanops.cuh"
 
 template <typename T, int V> struct Ld {
   static __device__ __forceinline__ void ld(const T* p, float* f) {
@@ -315,9 +315,21 @@ __global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T
     Ld<T, V>::st(o + i * V, x);
   }
 }
+struct AxpbyNoParams { template <int V> struct P {}; template <int V> __device__ __forceinline__ void load(int, P<V>&) const {} };
+template <typename T> struct AxpbyOp : AxpbyNoParams {
+  static constexpr int NIN = 2, NOUT = 1;
+  const T* in[2]; T* out[1]; float alpha, beta;
+  template <int V> __device__ __forceinline__ void apply(const float* v, int, const P<V>&, float* o) const { o[0] = alpha * v[0] + beta * v[1]; }
+};
 extern "C" int ttg_axpby(const void* a, const void* b, void* out, long long n, float alpha, float beta, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) return TTG_OK;
+  if (dtype == TTG_BF16 && n % 8 == 0 &&
+      !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    // large bf16 tensors (gradient fan-in adds): the bulk-copy pipelined map of chanops.cuh
+    AxpbyOp<bf16> op; op.in[0] = (const bf16*)a; op.in[1] = (const bf16*)b; op.out[0] = (bf16*)out; op.alpha = alpha; op.beta = beta;
+    return launch_chan_map<bf16>("axpby", op, n, 8, st);
+  }
   TTG_DISPATCH(dtype, {
     bool vec = n % Vec<T>::N == 0 && !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15);
     if (vec) axpby_kernel<T, Vec<T>::N><<<ttg_grid_occ(axpby_kernel<T, Vec<T>::N>, n / Vec<T>::N, 512, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n / Vec<T>::N, alpha, beta);

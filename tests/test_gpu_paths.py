@@ -1,0 +1,186 @@
+"""GPU parity of the round-1 fast paths that the small-shape operator tests do not reach:
+
+* bulk-copy (TMA 1-D) pipelined channel kernels  -> tensors above the size threshold (chanops.cuh: cb_ok)
+* streaming conv kernel with compile-time channel counts (128 -> 128, 128 -> 64, 64 -> 128) and wgrad at those sizes
+* conv epilogue / residual-join BatchNorm statistics (ttg_conv2d_tc_stats, ttg_*_stats, ttg_bn_finalize)
+* 8-channel staging of the RGB layers (ttg_pad_channels8 / ttg_unpad_channels8)
+* all filters of a model packed in one launch (ttg_pack_weights_multi)
+
+Oracle: the same op in PyTorch fp32 on the CPU (operands rounded to bf16 where the kernel rounds them).
+Tolerances: bf16 outputs 2e-2 relative L2; fp32 reductions 2e-3 relative.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-6))
+
+
+def _internal(x):
+    from tartangan_b200 import ops
+    return ops.to_internal(x.cuda(), BF)
+
+
+@pytest.fixture(autouse=True)
+def _bf16_mode():
+    import tartangan_b200 as tb
+    tb.set_precision('bf16')
+    yield
+    tb.set_precision('bf16')
+
+
+# ------------------------------------------------------------------ bulk-pipelined BatchNorm kernels
+@pytest.mark.parametrize('c,hw,n', [(16, 64, 16), (64, 32, 12), (128, 16, 24), (256, 8, 48)])
+def test_bn_act_large_fwd_bwd_double(c, hw, n):
+    """Sizes above the bulk-kernel threshold (>= 148 * 512 * 8 elements); forward, backward and double backward."""
+    from tartangan_b200 import ops
+    from tartangan_b200.models.layers import BatchNorm2d
+    torch.manual_seed(3)
+    assert n * c * hw * hw >= 8 * 512 * 148
+    x = (torch.randn(n, c, hw, hw) * 1.3 + 0.2).to(BF).float().requires_grad_()
+    ref = torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+    bn = BatchNorm2d(c).cuda()
+    bn.load_state_dict(ref.state_dict())
+    y = F.leaky_relu(ref(x), 0.2)
+    g = torch.randn_like(y).to(BF).float()
+    gx, = torch.autograd.grad(y, x, g, create_graph=True)
+    v = torch.randn_like(x).to(BF).float()
+    ggx, = torch.autograd.grad((gx * v).sum(), x)
+
+    xd = x.detach().cuda().requires_grad_()
+    yd = ops.bn_act(ops.to_internal(xd, BF), bn, 0.2)
+    assert rel_l2(yd, y) < 2e-2
+    gxd, = torch.autograd.grad(yd, xd, _internal(g), create_graph=True)
+    assert rel_l2(gxd, gx) < 2e-2
+    ggxd, = torch.autograd.grad(ops.DotFn.apply(ops.to_internal(gxd, BF), _internal(v)), xd)
+    assert rel_l2(ggxd, ggx) < 4e-2
+    assert rel_l2(bn.running_mean, ref.running_mean) < 2e-3 and rel_l2(bn.running_var, ref.running_var) < 2e-3
+
+
+def test_axpby_and_channel_sum_large():
+    from tartangan_b200 import ops
+    torch.manual_seed(4)
+    a, b = torch.randn(8, 32, 64, 64).to(BF), torch.randn(8, 32, 64, 64).to(BF)
+    out = ops.AxpbyFn.apply(_internal(a.float()), _internal(b.float()), 1.0, 0.5)
+    assert rel_l2(out, a.float() + 0.5 * b.float()) < 1e-2
+    s = ops.ChannelSumFn.apply(_internal(a.float()))
+    want = a.float().sum(dim=(0, 2, 3))
+    assert float((s.cpu() - want).abs().max() / want.abs().max()) < 2e-3
+
+
+# ------------------------------------------------------------------ streaming / static conv kernels
+@pytest.mark.parametrize('cin,cout,hw,n', [(128, 128, 16, 6), (128, 128, 8, 10), (128, 64, 16, 6), (64, 128, 16, 6),
+                                           (64, 64, 32, 3), (32, 32, 32, 5), (16, 16, 64, 2)])
+def test_conv_static_kernels(cin, cout, hw, n):
+    """fprop, dgrad and wgrad at the channel counts that select the compile-time (static) kernels; more tiles than
+    SMs in the persistent loops for the small-channel cases."""
+    from tartangan_b200 import ops
+    torch.manual_seed(5)
+    x = torch.randn(n, cin, hw, hw).to(BF).float().requires_grad_()
+    w = (torch.randn(cout, cin, 3, 3) / math.sqrt(cin * 9)).requires_grad_()
+    b = torch.randn(cout, requires_grad=True)
+    wq = w.detach().to(BF).float().requires_grad_()
+    y = F.conv2d(x, wq, b, padding=1)
+    gy = torch.randn_like(y).to(BF).float()
+    gx, gw, gb = torch.autograd.grad(y, (x, wq, b), gy)
+    xd, wd, bd = x.detach().cuda().requires_grad_(), w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+    yd = ops.conv2d(ops.to_internal(xd, BF), wd, bd)
+    assert rel_l2(yd, y) < 1e-2
+    gxd, gwd, gbd = torch.autograd.grad(yd, (xd, wd, bd), _internal(gy))
+    assert rel_l2(gxd, gx) < 1e-2 and rel_l2(gwd, gw) < 1e-2 and rel_l2(gbd, gb) < 1e-2
+
+
+# ------------------------------------------------------------------ producer statistics
+@pytest.mark.parametrize('cin,cout,hw,n,k', [(16, 16, 32, 4, 3), (32, 64, 20, 3, 3), (128, 128, 16, 4, 3), (64, 32, 16, 2, 1)])
+def test_conv_epilogue_statistics(cin, cout, hw, n, k):
+    from tartangan_b200 import ops
+    torch.manual_seed(6)
+    x = _internal(torch.randn(n, cin, hw, hw))
+    w = (torch.randn(cout, cin, k, k) / math.sqrt(cin * k * k)).cuda()
+    b = torch.randn(cout).cuda()
+    assert ops.conv_stats_ok(w, 0, BF)
+    y = ops.conv2d(x, w, b, stats=True)
+    pending = ops.state.producer_stats
+    assert pending is not None and pending[0].data_ptr() == y.data_ptr()
+    sums = ops.take_producer_stats(y)
+    assert sums is not None and ops.take_producer_stats(y) is None          # consumed once
+    yf = y.float().cpu()
+    want = torch.cat([yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))]).double()
+    got = sums.cpu()
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-4       # statistics of the STORED bf16 values
+    y_plain = ops.conv2d(x, w, b)
+    assert torch.equal(y_plain, y)                                          # same conv, bit for bit
+
+
+def test_bn_consumes_producer_statistics():
+    """conv(stats) -> bn_act and join(stats) -> bn_act give the same result as the two-pass BatchNorm."""
+    from tartangan_b200 import ops
+    from tartangan_b200.models.layers import BatchNorm2d
+    torch.manual_seed(7)
+    x = _internal(torch.randn(4, 32, 16, 16))
+    w = (torch.randn(32, 32, 3, 3) / 17.0).cuda()
+    bn1, bn2 = BatchNorm2d(32).cuda(), BatchNorm2d(32).cuda()
+    a1 = ops.bn_act(ops.conv2d(x, w, None, stats=True), bn1, 0.2)
+    a2 = ops.bn_act(ops.conv2d(x, w, None), bn2, 0.2)
+    assert rel_l2(a1, a2) < 1e-3 and rel_l2(bn1.running_var, bn2.running_var) < 1e-4
+    h, s = _internal(torch.randn(4, 32, 16, 16)), _internal(torch.randn(4, 32, 8, 8))
+    for join, args in ((ops.add_up2, (h, s)), (ops.avg_pool2_add, (h, s))):
+        bn1, bn2 = BatchNorm2d(32).cuda(), BatchNorm2d(32).cuda()
+        a1 = ops.bn_act(join(*args, stats=True), bn1, 0.2)
+        a2 = ops.bn_act(join(*args, stats=False), bn2, 0.2)
+        assert rel_l2(a1, a2) < 1e-3 and rel_l2(bn1.running_mean, bn2.running_mean) < 1e-4
+
+
+def test_stale_producer_statistics_are_dropped():
+    from tartangan_b200 import ops
+    from tartangan_b200.models.layers import BatchNorm2d
+    torch.manual_seed(8)
+    x = _internal(torch.randn(2, 16, 16, 16))
+    w = (torch.randn(16, 16, 3, 3) / 12.0).cuda()
+    ops.conv2d(x, w, None, stats=True)                   # statistics pending for a tensor nobody normalises
+    other = _internal(torch.randn(2, 16, 16, 16) * 3 + 1)
+    bn = BatchNorm2d(16).cuda()
+    ref = torch.nn.BatchNorm2d(16)
+    got = ops.bn_act(other, bn, 0.2)
+    want = F.leaky_relu(ref(other.float().cpu()), 0.2)
+    assert rel_l2(got, want) < 2e-2 and ops.state.producer_stats is None
+
+
+# ------------------------------------------------------------------ RGB staging, multi-pack
+def test_pad_unpad_channels8_roundtrip():
+    from tartangan_b200 import ops
+    from tartangan_b200._lib import call, ptr
+    torch.manual_seed(9)
+    x = _internal(torch.randn(3, 3, 9, 7))
+    x8 = ops._pad8(x)
+    assert x8.shape == (3, 8, 9, 7) and torch.equal(x8[:, :3], x) and float(x8[:, 3:].abs().max()) == 0.0
+    back = ops.empty_nhwc(3, 3, 9, 7, BF, 'cuda')
+    call('ttg_unpad_channels8', ptr(x8), ptr(back), 3 * 9 * 7, 3)
+    assert torch.equal(back, x)
+
+
+def test_pack_weights_multi_matches_single_pack():
+    from tartangan_b200 import ops
+    from tartangan_b200.optim import FlatParams
+    torch.manual_seed(10)
+    shapes = [(16, 3, 3, 3), (32, 16, 3, 3), (32, 16, 1, 1), (3, 16, 1, 1), (64, 64, 3, 3)]
+    params = [torch.nn.Parameter(torch.randn(*s, device='cuda')) for s in shapes] + \
+             [torch.nn.Parameter(torch.randn(7, device='cuda'))]
+    singles = {(i, m): ops._packed(p, m, 'tc').clone() for i, p in enumerate(params[:-1]) for m in (0, 1)}
+    flat = FlatParams(params)
+    pm = ops.PackedModel(flat)
+    pm.repack()
+    for i, p in enumerate(params[:-1]):
+        for m in (0, 1):
+            assert torch.equal(ops._packed(p, m, 'tc'), singles[(i, m)]), (i, m)
