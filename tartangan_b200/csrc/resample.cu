@@ -41,8 +41,18 @@ __global__ void pool2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, 
     Ld<T, V>::st(y + (((long long)n * Ho + oy) * Wo + ox) * C + c, s);
   }
 }
+__global__ void pool2_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, unsigned total, unsigned Wo, unsigned cv, float scale);
+static inline bool ttg_bf16x8_ok(int dtype, int C, const void* a, const void* b, long long items);
 extern "C" int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (ttg_bf16x8_ok(dtype, C, x, y, (long long)N * Ho * Wo * (C / 8) * 4)) {
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    if (total == 0) return TTG_OK;
+    pool2_bf16x8_kernel<<<ttg_grid_occ(pool2_bf16x8_kernel, total, 256, 256), 256, 0, st>>>(
+        (const uint4*)x, (uint4*)y, (unsigned)total, (unsigned)Wo, (unsigned)(C / 8), scale);
+    TTG_CHECK_LAUNCH("pool2_sum");
+    return TTG_OK;
+  }
   TTG_DISPATCH(dtype, {
     if (vec2_ok<T>(C, x, y)) { pool2_kernel<T, Vec<T>::N><<<ttg_grid_occ(pool2_kernel<T, Vec<T>::N>, (long long)N * Ho * Wo * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
     else { pool2_kernel<T, 1><<<ttg_grid_occ(pool2_kernel<T, 1>, (long long)N * Ho * Wo * C, 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Ho, Wo, C, scale); }
@@ -66,8 +76,69 @@ __global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int
     Ld<T, V>::st(y + (((long long)n * Ho + oy) * Wo + ox) * C + c, a);
   }
 }
+// bf16 fast path: one thread = one 16-byte INPUT unit -> four 16-byte stores (the 2x2 replicas), 32-bit index
+// arithmetic, two units in flight per thread.  (The generic kernel spends ~300 instructions per unit on 64-bit
+// div/mod and re-reads every input unit four times.)
+__device__ __forceinline__ uint4 ttg_scale_bf16x8(uint4 v, float scale) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); h[i] = __floats2bfloat162_rn(f.x * scale, f.y * scale); }
+  return v;
+}
+__global__ void __launch_bounds__(256) upsample2_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, unsigned total,
+                                                               unsigned Wi, unsigned cv, float scale) {
+  const unsigned stride = gridDim.x * blockDim.x, rowo = 2u * Wi * cv;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2u * stride) {
+    const unsigned i1 = i0 + stride;
+    const bool two = i1 < total;
+    uint4 v0 = x[i0], v1 = two ? x[i1] : make_uint4(0u, 0u, 0u, 0u);
+    if (scale != 1.f) { v0 = ttg_scale_bf16x8(v0, scale); if (two) v1 = ttg_scale_bf16x8(v1, scale); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const unsigned i = u ? i1 : i0;
+      const uint4 v = u ? v1 : v0;
+      const unsigned c8 = i % cv, p = i / cv, xi = p % Wi, q = p / Wi;          // q = n * Hi + yi
+      uint4* o = y + ((size_t)q * 2u * rowo + (size_t)(2u * xi) * cv + c8);
+      o[0] = v; o[cv] = v; o[rowo] = v; o[rowo + cv] = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) pool2_bf16x8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, unsigned total,
+                                                           unsigned Wo, unsigned cv, float scale) {
+  const unsigned stride = gridDim.x * blockDim.x, rowi = 2u * Wo * cv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const unsigned c8 = i % cv, p = i / cv, xo = p % Wo, q = p / Wo;              // q = n * Ho + oy
+    const uint4* src = x + ((size_t)q * 2u * rowi + (size_t)(2u * xo) * cv + c8);
+    const uint4 a = src[0], b = src[cv], c = src[rowi], d = src[rowi + cv];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&b);
+    const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+    const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&d);
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __bfloat1622float2(ha[j]), fb = __bfloat1622float2(hb[j]), fc = __bfloat1622float2(hc[j]), fd = __bfloat1622float2(hd[j]);
+      ho[j] = __floats2bfloat162_rn((((fa.x + fb.x) + fc.x) + fd.x) * scale, (((fa.y + fb.y) + fc.y) + fd.y) * scale);
+    }
+    y[i] = o;
+  }
+}
+static inline bool ttg_bf16x8_ok(int dtype, int C, const void* a, const void* b, long long items) {
+  return dtype == TTG_BF16 && C % 8 == 0 && items < (1ll << 31) - (1ll << 24) &&
+         !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15);
+}
 extern "C" int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (ttg_bf16x8_ok(dtype, C, x, y, (long long)N * Hi * Wi * (C / 8) * 4)) {
+    const long long total = (long long)N * Hi * Wi * (C / 8);
+    if (total == 0) return TTG_OK;
+    upsample2_bf16x8_kernel<<<ttg_grid_occ(upsample2_bf16x8_kernel, total, 512, 256), 256, 0, st>>>(
+        (const uint4*)x, (uint4*)y, (unsigned)total, (unsigned)Wi, (unsigned)(C / 8), scale);
+    TTG_CHECK_LAUNCH("upsample2");
+    return TTG_OK;
+  }
   TTG_DISPATCH(dtype, {
     if (vec2_ok<T>(C, x, y)) { upsample2_kernel<T, Vec<T>::N><<<ttg_grid_occ(upsample2_kernel<T, Vec<T>::N>, (long long)N * Hi * Wi * 4 * (C / Vec<T>::N), 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
     else { upsample2_kernel<T, 1><<<ttg_grid_occ(upsample2_kernel<T, 1>, (long long)N * Hi * Wi * 4 * C, 256, 256), 256, 0, st>>>((const T*)x, (T*)y, N, Hi, Wi, C, scale); }
