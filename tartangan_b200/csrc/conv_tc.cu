@@ -437,9 +437,24 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
 }
 // `Cout` = channels stored per pixel (row pitch of y): the accumulator width, or 8 for the 8-channel staging tensors
 // of the RGB layers (accumulator columns 8..15 are padding and are dropped).
+// Per-lane statistics accumulators for layers whose pixels are one chunk wide (Cout <= 64, Cout / 8 a power of two):
+// in the write-back loop a lane always handles the same 8-channel group (u % (Cout/8) == lane % (Cout/8)), so it sums
+// the units it is storing anyway and the cross-lane reduction happens ONCE per CTA (epi_stats_flush), not per tile.
+struct EpiStats { float s[8], q[8]; };
+__device__ __forceinline__ bool epi_stats_in_regs(int Cout) { const int u = Cout >> 3; return Cout <= TC_EPI_CHUNK && (u & (u - 1)) == 0; }
+__device__ __forceinline__ void epi_stats_flush(EpiStats& e, int lane, int Cout, float* s_stats) {
+  const int up = Cout >> 3, j = lane % up;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float a = e.s[k], b = e.q[k];
+    for (int o = 16; o >= up; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane < up) { atomicAdd(&s_stats[j * 8 + k], a); atomicAdd(&s_stats[Cout + j * 8 + k], b); }
+  }
+}
 __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_t* sE, int warp, int lane, int n, int y0, int x0,
                                                            int H, int W, int Cout, const float* __restrict__ bias,
-                                                           bf16* __restrict__ y, float* s_stats = nullptr) {
+                                                           bf16* __restrict__ y, float* s_stats = nullptr,
+                                                           EpiStats* est = nullptr) {
   if (Cout == 8) {                       // one 16-byte unit per pixel: lanes are already on consecutive units
     uint32_t r[16];
     tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16), r);
@@ -458,9 +473,15 @@ __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_
   }
   const int cc = Cout < TC_EPI_CHUNK ? Cout : TC_EPI_CHUNK;     // channels per chunk (16, 32, 48 or 64)
   const int upp = cc >> 3;                                       // 16-byte units per pixel in a chunk
-  const int pitch = cc * 2 + 16;
-  uint8_t* strip = sE + (size_t)warp * 32 * pitch;
+  // Strip layout: power-of-two `upp`: dense pixels, unit j of pixel p stored at slot j ^ ((p / (8/upp)) % upp) -- both the
+  // pixel-major 16-byte writes (lane = pixel) and the unit-major reads (lane = unit) then touch 8 distinct 16-byte
+  // bank groups per quarter warp.  Other widths (48 channels): padded pitch.
+  const bool swz = (upp & (upp - 1)) == 0;
+  const int pitch = swz ? cc * 2 : cc * 2 + 16;
+  const int fsh = swz ? 3 - (__ffs(upp) - 1) : 0;                // log2(8 / upp)
+  uint8_t* strip = sE + (size_t)warp * 32 * (cc * 2 + 16);
   const uint32_t strip_addr = smem_u32(strip);
+  const int wkey = swz ? ((lane >> fsh) & (upp - 1)) : 0;        // this lane's pixel (= lane) swizzle key
   for (int c0 = 0; c0 < Cout; c0 += cc) {
     const int ccur = min(cc, Cout - c0);
     for (int c1 = 0; c1 < ccur; c1 += 16) {
@@ -475,10 +496,12 @@ __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_
         __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
         o[j] = *reinterpret_cast<uint32_t*>(&h);
       }
-      const uint32_t d = strip_addr + (uint32_t)(lane * pitch + c1 * 2);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d + 16), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-      if (s_stats) {
+      const int u0 = c1 >> 3;                                    // first of the two units written here
+      const uint32_t d0 = strip_addr + (uint32_t)(lane * pitch + ((u0 ^ wkey) << 4));
+      const uint32_t d1 = strip_addr + (uint32_t)(lane * pitch + (((u0 + 1) ^ wkey) << 4));
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+      if (s_stats && !est) {
         // BatchNorm statistics of the tensor being written (the bf16-rounded values, pixels inside the image only)
         const bool inside = (y0 + warp * 4 + (lane >> 3)) < H && (x0 + (lane & 7)) < W;
         float v[16], q[16];
@@ -502,11 +525,22 @@ __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_
     for (int u = lane; u < units; u += 32) {
       const int p = sh >= 0 ? (u >> sh) : u / up_cur, j = u - p * up_cur;
       const int gy = y0 + warp * 4 + (p >> 3), gx = x0 + (p & 7);
+      const int slot = swz ? (j ^ ((p >> fsh) & (upp - 1))) : j;
       uint4 v;
       asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                   : "r"(strip_addr + (uint32_t)(p * pitch + j * 16)));
-      if (gy < H && gx < W)
+                   : "r"(strip_addr + (uint32_t)(p * pitch + (slot << 4))));
+      if (gy < H && gx < W) {
         *reinterpret_cast<uint4*>(y + (((long long)n * H + gy) * W + gx) * Cout + c0 + j * 8) = v;
+        if (est) {
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float f0 = __uint_as_float(w4[k] << 16), f1 = __uint_as_float(w4[k] & 0xffff0000u);
+            est->s[2 * k] += f0; est->q[2 * k] += f0 * f0;
+            est->s[2 * k + 1] += f1; est->q[2 * k + 1] += f1 * f1;
+          }
+        }
+      }
     }
     __syncwarp();
   }
@@ -717,7 +751,7 @@ __device__ __forceinline__ void resident_issue_tile(uint32_t dacc, uint64_t a0, 
   }
 }
 
-template <int K, int NBUF, int CIN>
+template <int K, int NBUF, int CIN, bool STATS>
 __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
                                                           int H, int W, int Cin_rt, int Cout, int total_tiles, int tmem_cols,
@@ -750,7 +784,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
   };
 
   float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256 + tc_epi_strip_bytes_dev(Cout));
-  if (stats)
+  if constexpr (STATS)
     for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
@@ -769,6 +803,12 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
 
   if (warp < 4) {
     // ------------------------------------------------------------ epilogue (LAG tiles behind)
+    EpiStats est;
+    if constexpr (STATS) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) est.s[k] = est.q[k] = 0.f;
+    }
+    const bool reg_stats = STATS && epi_stats_in_regs(Cout) && cstore == Cout;
     for (int j = 0; j < T; ++j) {
       const int acc = j & (NACC - 1);
       int n, y0, x0;
@@ -793,12 +833,14 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
         }
       } else if (!out_f32)
         conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
-                                   cstore, bias, reinterpret_cast<bf16*>(y), stats ? s_stats : nullptr);
+                                   cstore, bias, reinterpret_cast<bf16*>(y), STATS ? s_stats : nullptr,
+                                   (STATS && reg_stats) ? &est : nullptr);
       else
       conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32);
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[acc]);
     }
+    if constexpr (STATS) { if (reg_stats) epi_stats_flush(est, lane, Cout, s_stats); }
   } else if (warp == 4) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
@@ -852,7 +894,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
-  if (stats)
+  if constexpr (STATS)
     for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
 }
 
@@ -894,7 +936,8 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256 + tc_epi_bytes(Cout);
   static int smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
     smem_set = smem;
   }
@@ -904,8 +947,12 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
-  conv_tc_tma_kernel<K, NBUF, CIN><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout, (int)tiles,
-                                                                pcols, mode, cstore, stats);
+  if (stats)
+    conv_tc_tma_kernel<K, NBUF, CIN, true><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
+                                                                        (int)tiles, pcols, mode, cstore, stats);
+  else
+    conv_tc_tma_kernel<K, NBUF, CIN, false><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
+                                                                         (int)tiles, pcols, mode, cstore, stats);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
   return TTG_OK;
