@@ -215,7 +215,8 @@ def main():
             achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
             roof = dict(bound='hbm', achieved=achieved, peak=hbm, unit='GB/s', frac=achieved / hbm)
         # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel+shape (profiles/)
-        ncu_traffic = {('ttg_conv2d_tc', 'N256 128x128 16->16 k3 up0'): 220.6e6}
+        ncu_traffic = {('ttg_conv2d_tc', 'N256 128x128 16->16 k3 up0'): 229.6e6,       # profiles/r1_ncu_f_conv16.txt
+                       ('ttg_bn_act_bwd', 'M4194304 C16'): 637.6e6}                      # profiles/r1_ncu_f_bn_bwd.txt
         roof.update(traffic=ncu_traffic.get((top['name'], top.get('key', ''))), kernel=top['name'], shape=top.get('key', ''),
                     algorithmic_bytes_per_launch=top['bytes'] / max(top['calls'], 1), us_per_launch=per_launch_ms * 1e3,
                     peak_source=which, launches_per_step=top['calls'],
