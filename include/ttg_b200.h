@@ -57,6 +57,7 @@ int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int
                   int ksize, int up, int dtype_out, void* stream);
 /* tuning switch: 1 (default) = TMA-fed activation tiles where applicable, 0 = cp.async staging everywhere */
 int ttg_set_use_tma(int on);
+int ttg_set_use_fold(int on);   /* development switch: kx-folded row-tile conv kernel on / off */
 int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
                       int Cout, int ksize, int up, int dtype_out, const float* pre_scale, const float* pre_shift,
                       float slope, void* stream);

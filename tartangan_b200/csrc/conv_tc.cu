@@ -1271,6 +1271,233 @@ static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* 
 static int g_conv_tc_smem[2] = {0, 0};
 extern "C" int ttg_set_use_tma(int on) { g_use_tma = on; return TTG_OK; }
 
+
+// ------------------------------------------------------------------ fprop / dgrad, horizontal taps folded into N
+// Small-channel 3x3 layers are bound by the tensor pipe's operand fetch, not by HBM: an SS-mode 128 x 16 x 16 MMA
+// occupies the pipe ~57 cycles (4 KB A fragment from shared memory) and the tap-shift scheme needs 9 of them per
+// 128 pixels.  Here the three horizontal taps are folded into the N dimension:
+//     D[p, (kx, co)] = sum_{ky, ci} X[p + (ky-1) rows, ci] * Wf[(ky, ci), (kx, co)]          3 MMAs (N = 3 Cout) per k16
+//     out[x, co]     = D[x-1, (0, co)] + D[x, (1, co)] + D[x+1, (2, co)]                      shift-and-add in the epilogue
+// A tile is 4 full image rows (M groups of 128 consecutive pixels = 128 / W rows, W <= 128), so the x-neighbours of a
+// pixel are the neighbouring TMEM lanes (warp shuffles; warp-boundary values through shared memory) and image borders
+// are the conv's zero padding.  The activation tile [channel/8][6 rows][W] needs no horizontal halo: the vertical
+// taps are descriptor start addresses one row apart.  The packed filter [tap][ci/8][co][8] is re-ordered to
+// [ky][ci/8][(kx, co)][8] while it is copied into shared memory, so callers pass the usual packed weights.
+template <int CIN, int COUT, int W>
+__global__ void __launch_bounds__((4 * (4 / (128 / W)) + 2) * 32) conv_tc_fold_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
+                                                           const float* __restrict__ bias, bf16* __restrict__ y, int H,
+                                                           int total_tiles, int cstore) {
+  constexpr int C8N = CIN / 8, K16N = CIN / 16, NF = 3 * COUT;
+  constexpr int R = 128 / W, G = 4 / R, HY = 6;                  // rows per M group, M groups per tile, tile rows incl. halo
+  constexpr int NBUF = 3, NACC = 2;
+  constexpr uint32_t A_BYTES = (uint32_t)C8N * HY * W * 16;
+  constexpr uint32_t W_BYTES = 9u * K16N * COUT * 32;
+  static_assert(128 % W == 0 && W >= 32 && 4 % R == 0, "row tiles: W in {32, 64, 128}");
+  static_assert(NACC * G * NF <= 512, "TMEM columns");
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + ((W_BYTES + 127) & ~127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + NBUF * (size_t)A_BYTES);
+  uint64_t* empty = full + NBUF;
+  uint64_t* acc_full = empty + NBUF;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);       // [G sets][2 parity][4 warps][2][16]
+  constexpr int EPI_WARPS = 4 * G;          // one set of 4 epilogue warps per M group: a lone warp per scheduler cannot
+                                            // hide its own instruction latencies (measured 3100 cycles per group)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_img = (H + 3) / 4;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == EPI_WARPS) tmem_alloc(tmem_slot, 512u);
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128 * G); }
+    mbar_fence_init();
+  }
+  if (warp < EPI_WARPS) {
+    // packed filter unit (tap, c8, co) -> folded unit ((ky * C8N + c8) * 3 + kx) * COUT + co
+    for (int u = tid; u < 9 * C8N * COUT; u += 32 * EPI_WARPS) {
+      const int co = u % COUT, c8 = (u / COUT) % C8N, tap = u / (COUT * C8N);
+      const int ky = tap / 3, kx = tap - ky * 3;
+      reinterpret_cast<uint4*>(sW)[((ky * C8N + c8) * 3 + kx) * COUT + co] = __ldg(reinterpret_cast<const uint4*>(wp) + u);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < EPI_WARPS) {
+    // ------------------------------------------------------------ epilogue: shift-and-add of the three kx blocks
+    const int g = warp >> 2, q = warp & 3;                        // M group of this warp set, TMEM lane quadrant
+    const int m = q * 32 + lane;                                  // pixel of the M group = TMEM lane
+    const int r = m / W, xx = m - r * W;
+    const bool has_left = xx > 0, has_right = xx < W - 1;
+    float* xs = xch + g * (2 * 4 * 2 * 16);
+    // W is a multiple of 32: a row starts at lane 0 and ends at lane 31, so only those lanes can sit on an image
+    // border, and they are also the only lanes that take their neighbour from the exchange buffer
+    const bool edge_l = lane == 0, edge_r = lane == 31;
+    float bv[COUT];
+#pragma unroll
+    for (int k = 0; k < COUT; ++k) bv[k] = bias ? __ldg(bias + k) : 0.f;
+    int par = 0;
+    for (int j = 0; j < T; ++j) {
+      const int acc = j & (NACC - 1);
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int n = tile / tiles_img, y0 = (tile - n * tiles_img) * 4;
+      { TTG_T0(); mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u); if (tid == 0) { TTG_T1(5, j); } }
+      tc_fence_after_sync();
+      TTG_T0();
+      const int row = y0 + g * R + r;
+      const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * G + g) * NF);
+      bf16* yrow = y + (((long long)n * H + row) * W + xx) * (cstore == 8 ? 8 : COUT);
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16, par ^= 1) {
+        uint32_t d0[16], d1[16], d2[16];
+        tmem_ld16(tcol + (uint32_t)c0, d0);
+        tmem_ld16(tcol + (uint32_t)(COUT + c0), d1);
+        tmem_ld16(tcol + (uint32_t)(2 * COUT + c0), d2);
+        tmem_ld_wait();
+        float4* mine = reinterpret_cast<float4*>(xs + ((par * 4 + q) * 2) * 16);
+        if (edge_r) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)          // for lane 0 of the next warp
+            mine[k] = make_float4(__uint_as_float(d0[4 * k]), __uint_as_float(d0[4 * k + 1]), __uint_as_float(d0[4 * k + 2]), __uint_as_float(d0[4 * k + 3]));
+        }
+        if (edge_l) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)          // for lane 31 of the previous warp
+            mine[4 + k] = make_float4(__uint_as_float(d2[4 * k]), __uint_as_float(d2[4 * k + 1]), __uint_as_float(d2[4 * k + 2]), __uint_as_float(d2[4 * k + 3]));
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        // the one value a border lane cannot get from a shuffle: its neighbour in the adjacent warp (0 on an image border)
+        float ex[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ex[k] = 0.f;
+        if ((edge_l && has_left) || (edge_r && has_right)) {
+          const float4* src = edge_l ? reinterpret_cast<const float4*>(xs + ((par * 4 + ((q + 3) & 3)) * 2) * 16)
+                                     : reinterpret_cast<const float4*>(xs + ((par * 4 + ((q + 1) & 3)) * 2) * 16 + 16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float4 a4 = src[k]; ex[4 * k] = a4.x; ex[4 * k + 1] = a4.y; ex[4 * k + 2] = a4.z; ex[4 * k + 3] = a4.w; }
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          float v[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[k + h]), 1);
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k + h]), 1);
+            v[h] = (__uint_as_float(d1[k + h]) + bv[c0 + k + h]) + (edge_l ? ex[k + h] : left) + (edge_r ? ex[k + h] : right);
+          }
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[0], v[1]);
+          o[k >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        if (row < H) {
+          if (cstore == 8) {                  // 8-channel staging tensor of an RGB layer: channels 8..15 are padding
+            *reinterpret_cast<uint4*>(yrow) = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(yrow + c0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+      if (tid == 0) { TTG_T1(6, j); }
+    }
+  } else if (warp == EPI_WARPS) {
+    // ------------------------------------------------------------ MMA issuer: G groups x 3 vertical taps x K16N slices
+    const uint32_t idesc = umma_idesc_bf16(128, NF, 0, 0);
+    const uint64_t b0 = umma_desc(smem_u32(sW), (uint32_t)NF * 16, 128);
+    for (int it = 0; it < T; ++it) {
+      const int s = it % NBUF, acc = it & (NACC - 1);
+      { TTG_T0(); mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u); if (lane == 0) { TTG_T1(2, it); } }
+      { TTG_T0(); if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u); if (lane == 0) { TTG_T1(3, it); } }
+      tc_fence_after_sync();
+      if (elect_one()) {
+        TTG_T0();
+        // A: 8-pixel groups 128 B apart (rows are contiguous: no horizontal halo), channel groups HY*W units apart
+        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * A_BYTES), (uint32_t)HY * W * 16, 128);
+        static_for<G>([&](auto gg) {
+          constexpr int g = decltype(gg)::value;
+          const uint32_t dacc = tmem_base + (uint32_t)((acc * G + g) * NF);
+          static_for<3 * K16N>([&](auto ss) {
+            constexpr int sl = decltype(ss)::value, ky = sl / K16N, jj = sl % K16N;
+            constexpr uint32_t aoff = (uint32_t)((2 * jj) * HY * W + (g * R + ky) * W);
+            constexpr uint32_t boff = (uint32_t)((ky * C8N + 2 * jj) * NF);
+            umma_bf16_imm<(sl > 0)>(dacc, a0 + (uint64_t)aoff, b0 + (uint64_t)boff, idesc);
+          });
+        });
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[acc]);
+        TTG_T1(7, it);
+      }
+      __syncwarp();
+    }
+  } else if (elect_one()) {
+    // ------------------------------------------------------------ TMA producer: rows y0-1 .. y0+4 of the image, all channels
+    for (int j = 0; j < T; ++j) {
+      const int s = j % NBUF;
+      { TTG_T0(); if (j >= NBUF) mbar_wait(&empty[s], (uint32_t)((j / NBUF) - 1) & 1u); TTG_T1(4, j); }
+      const int tile = blockIdx.x + j * gridDim.x;
+      const int n = tile / tiles_img, y0 = (tile - n * tiles_img) * 4;
+      const uint32_t bar = smem_u32(&full[s]);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A_BYTES) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+          ::"r"(smem_u32(sA + (size_t)s * A_BYTES)), "l"(&tmap), "r"(0), "r"(0), "r"(y0 - 1), "r"(0), "r"(n), "r"(bar)
+          : "memory");
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512u);
+}
+
+// Off by default: correct (tests/test_gpu_paths.py) but not faster on B200 -- 16->16 @128^2: 90-93 us against 80-90 us for
+// the 9-MMA tap-shift kernel; the MMA count drops 3x but the shift-and-add epilogue (3 TMEM loads, 32 shuffles, a
+// cross-warp exchange per 16 channels) is issue-bound at ~1700-1900 cycles per 512-pixel tile even with one warp set
+// per M group (clock64 trace: epi.run).  Kept as the starting point for a version whose epilogue adds in TMEM.
+static int g_use_fold = 0;
+extern "C" int ttg_set_use_fold(int on) { g_use_fold = on; return TTG_OK; }
+
+template <int CIN, int COUT, int W>
+static int launch_conv_tc_fold(const void* x, const void* wp, const float* bias, void* y, int N, int H, int cin_mem, int cstore,
+                               cudaStream_t st) {
+  ttg_encode_tiled_fn enc = ttg_get_encode_tiled();
+  if (!enc) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled unavailable");
+  constexpr int C8N = CIN / 8, HY = 6;
+  CUtensorMap tmap;
+  // (8 channels, x, y, channel group, image): the box lands as [channel group][row][x] x 16 B
+  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(cin_mem / 8), (cuuint64_t)N};
+  const cuuint64_t gstr[4] = {(cuuint64_t)cin_mem * 2, (cuuint64_t)W * cin_mem * 2, 16, (cuuint64_t)H * W * cin_mem * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)W, (cuuint32_t)HY, (cuuint32_t)C8N, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  constexpr int W_BYTES = 9 * (CIN / 16) * COUT * 32, A_BYTES = C8N * HY * W * 16;
+  constexpr int G = 4 / (128 / W), THREADS = (4 * G + 2) * 32;
+  constexpr int smem = ((W_BYTES + 127) & ~127) + 3 * A_BYTES + 256 + G * 2 * 4 * 2 * 16 * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_fold_kernel<CIN, COUT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const long long tiles = (long long)N * ((H + 3) / 4);
+  long long grid = ttg_num_sms();
+  if (grid > tiles) grid = tiles;
+  conv_tc_fold_kernel<CIN, COUT, W><<<(unsigned)grid, THREADS, smem, st>>>(tmap, (const bf16*)wp, bias, (bf16*)y, H, (int)tiles, cstore);
+  TTG_CHECK_LAUNCH("conv2d_tc_fold");
+  return TTG_OK;
+}
+
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
 // tensors in memory (equal to Cin / Cout except for the RGB layers).
 // stats (optional): double[2 * Cout], zeroed by the caller; receives sum / sum of squares per output channel of the
@@ -1308,6 +1535,13 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
   TTG_REQUIRE(tiles > 0 && tiles < (1ll << 31), "conv2d_tc: bad problem size");
   const int w_bytes = total_slices * slice_bytes;
   TTG_REQUIRE(!padded || w_bytes <= TC_RESIDENT_W_BYTES, "conv2d_tc: padded layers must fit the resident-filter kernel");
+  if (g_use_fold && g_use_tma && ksize == 3 && up == 0 && !padded && !pre_scale && stats == nullptr && dtype_out == TTG_BF16) {
+    // small-channel 3x3 layers on full-row tiles: horizontal taps folded into N (see conv_tc_fold_kernel)
+#define TTG_FOLD(CI, CO, WW) if (Cin == CI && Cout == CO && W == WW) return launch_conv_tc_fold<CI, CO, WW>(x, wp, bias, y, N, H, cin_real, cout_real, st)
+    TTG_FOLD(16, 16, 128);
+    TTG_FOLD(32, 32, 64);
+#undef TTG_FOLD
+  }
   if (w_bytes <= TC_RESIDENT_W_BYTES) {
     const int a_bytes = (Cin / 8) * HP * 16;
     const int nbuf = a_bytes <= 12 * 1024 ? 4 : (a_bytes <= 24 * 1024 ? 3 : 2);

@@ -24,6 +24,8 @@ def timeit(fn, reps=10):
 
 def main():
     kind = sys.argv[1]
+    if os.environ.get('TTG_FOLD'):
+        _lib.lib.ttg_set_use_fold(int(os.environ['TTG_FOLD']))
     if os.environ.get('TTG_TMA_MODE'):
         _lib.lib.ttg_set_use_tma(int(os.environ["TTG_TMA_MODE"]), None)
     a = [int(v) for v in sys.argv[2:]]
