@@ -87,6 +87,10 @@ int ttg_pack_weights_multi(const float* flat, void* packed, const long long* tab
                            void* stream);
 int ttg_pad_channels8(const void* x, void* y8, long long npix, int c_real, void* stream);
 int ttg_unpad_channels8(const void* y8, void* y, long long npix, int c_real, void* stream);
+/* wgrad + bias gradient gbias[co] = sum_pixels gy (fp32) in ONE pass over gy (both halves of convolution_backward's
+ * parameter gradients, nn.Conv2d(bias=True): generator.py:41,44, discriminator.py:63,66) */
+int ttg_conv2d_wgrad_bias_tc_ex(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin,
+                                int Cout, int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
                         int up, void* workspace, void* stream);
 size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);

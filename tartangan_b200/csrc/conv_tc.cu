@@ -1754,7 +1754,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
                                                                int Cout, int up, int units_per_group, int fuse,
                                                                int tmem_cols, int g_bytes, int cin_real, int cout_real,
                                                                const __grid_constant__ CUtensorMap tmap_x,
-                                                               const __grid_constant__ CUtensorMap tmap_g) {
+                                                               const __grid_constant__ CUtensorMap tmap_g,
+                                                               float* __restrict__ gbias) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH, NPIX = TC_TH * TC_TW;
   constexpr int DIST = NBUF > 2 ? NBUF - 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1794,9 +1795,15 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
     x0 = (t2 % tiles_x) * TC_TW;
   };
 
+  // Bias gradient (sum over pixels of gy) for free: with TMA-fed tiles warps 0-3 are idle during the main loop, so
+  // they add up the gy tile that sits in shared memory anyway (CTAs of the first tap group only).  Replaces the
+  // separate ttg_channel_sum pass over gy.
+  const bool do_bias = TMA && gbias != nullptr && blockIdx.y == 0;
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);        // [128] floats after the barriers
+  if (do_bias && tid < 128) s_bias[tid] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
-    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], TMA ? 1 : 128); mbar_init(&empty[i], (uint32_t)n_issuers); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], TMA ? 1 : 128); mbar_init(&empty[i], (uint32_t)n_issuers + (do_bias ? 4u : 0u)); }
     mbar_init(done, (uint32_t)n_issuers);
     mbar_fence_init();
   }
@@ -1852,6 +1859,28 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
         mbar_arrive(&full[it % NBUF]);
       }
       cp_async_wait_all();
+    }
+    if (do_bias) {
+      // thread -> one 8-channel group and every ppg-th pixel of the tile: consecutive lanes read consecutive pixels
+      const int ppg = 128 / g8n, g8 = tid / ppg, p0 = tid - g8 * ppg;
+      float bs[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bs[k] = 0.f;
+      for (int it = 0; it < T; ++it) {
+        const int s = it % NBUF;
+        mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+        const uint8_t* gt = sG + (size_t)s * g_bytes + (size_t)g8 * NPIX * 16;
+        for (int p = p0; p < NPIX; p += ppg) {
+          const uint4 v = *reinterpret_cast<const uint4*>(gt + (size_t)p * 16);
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { bs[2 * k] += __uint_as_float(w4[k] << 16); bs[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u); }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_bias[g8 * 8 + k], bs[k]);
     }
     if (T > 0) {
       { TTG_T0(); mbar_wait(done, 0); if (tid == 0) { TTG_T1(9, 0); } }
@@ -1963,12 +1992,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (do_bias && tid < co_cnt && co_base + tid < cout_real) atomicAdd(&gbias[co_base + tid], s_bias[tid]);
 }
 
 template <int K, int NBUF>
 static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int up,
                            int upg, int fuse, int cols, int g_bytes, int smem, dim3 grid, int cin_real, int cout_real,
-                           cudaStream_t st) {
+                           float* gbias, bool* bias_done, cudaStream_t st) {
   constexpr int HALO = K / 2;
   CUtensorMap tx, tg;
   memset(&tx, 0, sizeof(tx)); memset(&tg, 0, sizeof(tg));
@@ -2001,10 +2031,11 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
   }
   if (tma)
     conv_wgrad_tc_ws_kernel<K, NBUF, true><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
-                                                                   fuse, cols, g_bytes, cin_real, cout_real, tx, tg);
+                                                                   fuse, cols, g_bytes, cin_real, cout_real, tx, tg, gbias);
   else
     conv_wgrad_tc_ws_kernel<K, NBUF, false><<<grid, 256, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, upg,
-                                                                    fuse, cols, g_bytes, cin_real, cout_real, tx, tg);
+                                                                    fuse, cols, g_bytes, cin_real, cout_real, tx, tg, nullptr);
+  *bias_done = tma && gbias != nullptr;
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc_ws");
   return TTG_OK;
 }
@@ -2022,7 +2053,7 @@ __global__ void ttg_wgrad_unpack_kernel(const float* __restrict__ gwp, float* __
 }
 static inline int ttg_pad16(int c) { return c <= 8 ? 16 : c; }
 extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize) {
-  return sizeof(float) * (size_t)ttg_pad16(Cin) * ttg_pad16(Cout) * ksize * ksize + 16;
+  return sizeof(float) * (size_t)ttg_pad16(Cin) * ttg_pad16(Cout) * ksize * ksize + 16 + 8 * 256 + 16;   // + channel-sum scratch
 }
 
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
@@ -2031,8 +2062,24 @@ extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int
                                    int ksize, int up, void* workspace, void* stream) {
   return ttg_conv2d_wgrad_tc_ex(x, gy, gw, N, H, W, Cin, Cout, Cin, Cout, ksize, up, workspace, stream);
 }
+extern "C" int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream);
+static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
+                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                       int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
+  return wgrad_tc_core(x, gy, gw, nullptr, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream);
+}
+// wgrad + bias gradient (gbias[co] = sum over pixels of gy[., co], fp32) in one pass over gy: the idle warps of the
+// TMA-fed wgrad kernel add up the gy tiles while the tensor cores consume them (Conv2d bias gradient of
+// convolution_backward).  Falls back to ttg_channel_sum internally where the fused path does not apply.
+extern "C" int ttg_conv2d_wgrad_bias_tc_ex(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin,
+                                           int Cout, int cin_real, int cout_real, int ksize, int up, void* workspace,
+                                           void* stream) {
+  TTG_REQUIRE(gbias != nullptr, "conv2d_wgrad_bias_tc: gbias is required");
+  return wgrad_tc_core(x, gy, gw, gbias, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream);
+}
+static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
+                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   TTG_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_wgrad_tc: workspace must be 16-byte aligned");
   float* gwp = reinterpret_cast<float*>(workspace);
@@ -2083,7 +2130,7 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
       int body = nbuf * (x_bytes + g_bytes);
       const int need = (nbuf - 1) * g_bytes + reach;
       if (body < need) body = need;
-      const int wsmem = body + xpad + 256;
+      const int wsmem = body + xpad + 1024;          // barriers + the bias partial sums
       if (wper_sm > (220 * 1024) / wsmem) wper_sm = (220 * 1024) / wsmem;
       if (wper_sm > 4) wper_sm = 4;
       if (wper_sm < 1) wper_sm = 1;
@@ -2091,8 +2138,10 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
       if (wsplits < 1) wsplits = 1;
       if (wsplits > tiles) wsplits = tiles;
       cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+      if (gbias) cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)cout_real, st);
+      bool bias_done = false;
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
-#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, st)
+#define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, gbias, &bias_done, st)
       int rc;
       if (ksize == 3) rc = nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
       else rc = nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
@@ -2101,6 +2150,10 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
       const int total = cout_real * cin_real * taps;
       ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0);
       TTG_CHECK_LAUNCH("conv2d_wgrad_unpack");
+      if (gbias && !bias_done) {
+        void* scratch = reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * (size_t)Cout * Cin * taps + 15) & ~(size_t)15);
+        return ttg_channel_sum(gy, (long long)N * H * W, cout_real, gbias, scratch, TTG_BF16, stream);
+      }
       return TTG_OK;
     }
   }
@@ -2123,6 +2176,10 @@ extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, 
   else
     conv_wgrad_tc_kernel<1><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc");
+  if (gbias) {
+    void* scratch = reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * (size_t)Cout * Cin * taps + 15) & ~(size_t)15);
+    return ttg_channel_sum(gy, (long long)N * H * W, cout_real, gbias, scratch, TTG_BF16, stream);
+  }
   return TTG_OK;
 }
 

@@ -277,10 +277,15 @@ class Conv2dFn(Function):
         if ctx.needs_input_grad[0]:
             gx = ConvDgradFn.apply(gy, w, ctx.up)
         if not state.inputs_only:
-            if ctx.needs_input_grad[1]:
-                gw = ConvWgradFn.apply(x, gy, w.shape[2], ctx.up)
-            if ctx.has_bias and ctx.needs_input_grad[2]:
-                gb = ChannelSumFn.apply(gy)
+            want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+            if (want_w and want_b and ctx.up == 0 and gy.dtype == torch.bfloat16 and w.shape[0] >= 16
+                    and _tc_ok(x.dtype, w.shape[1], w.shape[0])):
+                gw, gb = ConvWgradBiasFn.apply(x, gy, w.shape[2])      # one pass over gy for both
+            else:
+                if want_w:
+                    gw = ConvWgradFn.apply(x, gy, w.shape[2], ctx.up)
+                if want_b:
+                    gb = ChannelSumFn.apply(gy)
         return gx, gw, gb, None, None, None
 
 
@@ -346,6 +351,45 @@ class ConvWgradFn(Function):
         if ctx.needs_input_grad[1]:
             g_gy = Conv2dFn.apply(x, ggw, None, ctx.up, None)
         return g_x, g_gy, None, None
+
+
+class ConvWgradBiasFn(Function):
+    """(gw, gb): weight gradient and bias gradient (sum over pixels of gy) of a tensor-core conv in one kernel
+    (ttg_conv2d_wgrad_bias_tc_ex): the warps that are idle while TMA feeds the tensor cores add up the gy tiles."""
+
+    @staticmethod
+    def forward(ctx, x, gy, k):
+        ctx.save_for_backward(x, gy)
+        ctx.k = k
+        x, gy = nhwc(x), nhwc(gy)
+        n, cout, h, w = gy.shape
+        cin = x.shape[1]
+        gb = torch.empty(cout, dtype=torch.float32, device=x.device)
+        ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
+        if cin < 8:           # RGB input: 8-channel staging copy, the extra columns of the gradient are dropped
+            gw8 = torch.empty((cout, 8, k, k), dtype=torch.float32, device=x.device)
+            call('ttg_conv2d_wgrad_bias_tc_ex', ptr(_pad8(x)), ptr(gy), ptr(gw8), ptr(gb), n, h, w, 16, cout, 8, cout, k, 0,
+                 ptr(ws))
+            gw = gw8[:, :cin].contiguous()
+        else:
+            gw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
+            call('ttg_conv2d_wgrad_bias_tc_ex', ptr(x), ptr(gy), ptr(gw), ptr(gb), n, h, w, cin, cout, cin, cout, k, 0, ptr(ws))
+        return gw, gb
+
+    @staticmethod
+    def backward(ctx, ggw, ggb):
+        x, gy = ctx.saved_tensors
+        g_x = g_gy = None
+        if ggw is not None:
+            if ctx.needs_input_grad[0]:
+                g_x = ConvDgradFn.apply(gy, ggw, 0)
+            if ctx.needs_input_grad[1]:
+                g_gy = Conv2dFn.apply(x, ggw, None, 0, None)
+        if ggb is not None and ctx.needs_input_grad[1]:
+            n, c, h, w = gy.shape
+            bc = ggb.to(gy.dtype).view(1, c, 1, 1).expand(n, c, h, w)
+            g_gy = bc if g_gy is None else g_gy + bc
+        return g_x, g_gy, None
 
 
 def conv2d(x, w, bias=None, up=0, out_dtype=None, stats=False):
