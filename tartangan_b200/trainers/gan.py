@@ -104,12 +104,15 @@ class GanTrainer(Trainer):
 
     # The step is cut into four segments so that the same code runs eagerly or as CUDA graphs
     # (one graph on a single GPU; three graphs with the two gradient exchanges between them otherwise).
-    def d_forward_backward(self, imgs, overlap=True):
+    def d_forward_backward(self, imgs, overlap=True, fake=None):
+        """fake: the generator sample for this D step when it was produced ahead of time (graph mode generates it
+        while the host batch is still being copied to the device)."""
         toggle_grad(self.g, False)
         toggle_grad(self.d, True)
         self.optimizer_d.zero_grad()
-        with torch.no_grad():
-            fake = self.sample_g(len(imgs))
+        if fake is None:
+            with torch.no_grad():
+                fake = self.sample_g(len(imgs))
         real = imgs
         if self.args.grad_penalty:
             real = imgs.detach().requires_grad_()
@@ -198,7 +201,16 @@ class GanTrainer(Trainer):
             else:
                 torch.rand(b * nq, 1, out=st['tau_pin'][i])
                 st['tau'][i].copy_(st['tau_pin'][i], non_blocking=True)
-        st['imgs'].copy_(imgs, non_blocking=True)
+        cs = getattr(self, '_copy_stream', None)
+        if cs is None or self.world_size != 1:
+            st['imgs'].copy_(imgs, non_blocking=True)
+            return
+        # single GPU: the image batch travels on a copy stream while the first graph (the generator sample of the
+        # D step, which does not need the images) runs; the second graph waits for `imgs_ready`
+        cs.wait_stream(torch.cuda.current_stream())       # the previous step may still be reading the static buffer
+        with torch.cuda.stream(cs):
+            st['imgs'].copy_(imgs, non_blocking=True)
+            self._imgs_ready.record(cs)
 
     def _capture(self, imgs):
         dev, b = self.device, self.args.batch_size
@@ -256,13 +268,18 @@ class GanTrainer(Trainer):
 
         overlap = False                           # exchanges happen between graphs
         if self.world_size == 1:
-            def whole():
-                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap)
+            def gen():
+                with torch.no_grad():
+                    out['fake'] = self.sample_g(b)
+            def rest():
+                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
                 self.d_update()
                 out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
                 self.g_update()
-            seg(whole)
-            self._segments = [(graphs[0], None)]
+            seg(gen); seg(rest)
+            self._segments = [(graphs[0], 'imgs'), (graphs[1], None)]
+            self._copy_stream = torch.cuda.Stream()
+            self._imgs_ready = torch.cuda.Event()
         else:
             def s1():
                 out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap)
@@ -287,7 +304,10 @@ class GanTrainer(Trainer):
         _lib.Counters.kernels += self._graph_kernels
         for graph, exchange in self._segments:
             graph.replay()
-            if exchange is not None:
+            if isinstance(exchange, str):         # 'imgs': the next graph reads the image batch
+                if getattr(self, '_copy_stream', None) is not None:
+                    torch.cuda.current_stream().wait_event(self._imgs_ready)
+            elif exchange is not None:
                 torch.distributed.all_reduce(exchange)
         o = self._graph_out
         return o['d_loss'], o['gp'], o['g_loss']
