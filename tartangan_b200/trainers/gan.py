@@ -202,11 +202,11 @@ class GanTrainer(Trainer):
                 torch.rand(b * nq, 1, out=st['tau_pin'][i])
                 st['tau'][i].copy_(st['tau_pin'][i], non_blocking=True)
         cs = getattr(self, '_copy_stream', None)
-        if cs is None or self.world_size != 1:
+        if cs is None:
             st['imgs'].copy_(imgs, non_blocking=True)
             return
-        # single GPU: the image batch travels on a copy stream while the first graph (the generator sample of the
-        # D step, which does not need the images) runs; the second graph waits for `imgs_ready`
+        # the image batch travels on a copy stream while the first graph (the generator sample of the D step, which
+        # does not need the images) runs; the second graph waits for `imgs_ready`
         cs.wait_stream(torch.cuda.current_stream())       # the previous step may still be reading the static buffer
         with torch.cuda.stream(cs):
             st['imgs'].copy_(imgs, non_blocking=True)
@@ -267,28 +267,29 @@ class GanTrainer(Trainer):
             graphs.append(g)
 
         overlap = False                           # exchanges happen between graphs
+        def gen():
+            with torch.no_grad():
+                out['fake'] = self.sample_g(b)
+        seg(gen)                                  # needs no images: runs while the host batch is still in flight
         if self.world_size == 1:
-            def gen():
-                with torch.no_grad():
-                    out['fake'] = self.sample_g(b)
             def rest():
                 out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
                 self.d_update()
                 out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
                 self.g_update()
-            seg(gen); seg(rest)
+            seg(rest)
             self._segments = [(graphs[0], 'imgs'), (graphs[1], None)]
-            self._copy_stream = torch.cuda.Stream()
-            self._imgs_ready = torch.cuda.Event()
         else:
             def s1():
-                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap)
+                out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
             def s2():
                 self.d_update()
                 out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
             seg(s1); seg(s2); seg(self.g_update)
             gd, gg = self.optimizer_d._ensure_flat().grad, self.optimizer_g._ensure_flat().grad
-            self._segments = [(graphs[0], gd), (graphs[1], gg), (graphs[2], None)]
+            self._segments = [(graphs[0], 'imgs'), (graphs[1], gd), (graphs[2], gg), (graphs[3], None)]
+        self._copy_stream = torch.cuda.Stream()
+        self._imgs_ready = torch.cuda.Event()
         self._graph_out = out
         self._graph_kernels = _lib.Counters.kernels - k_before      # kernels recorded in the graphs = launched per replay
         st['active'] = False
