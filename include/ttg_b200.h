@@ -201,6 +201,20 @@ int ttg_softmax_bwd(const void* y, const void* gy, void* gx, long long rows, int
 /* backward of ttg_softmax_bwd given w = cotangent of gx: cot_gy, cot_y (D-side attention under R1) */
 int ttg_softmax_bwd2(const void* y, const void* gy, const void* w, void* cot_gy, void* cot_y, long long rows, int cols,
                      int dtype, void* stream);
+/* Fused attention core (attention.py:25-34: beta = softmax(bmm(theta^T, phi), -1); o = bmm(g, beta^T)) on the
+ * tensor cores, beta never written to memory.  Per image: q = theta [Nq][dk], k = max-pooled phi [Nk][dk],
+ * v = max-pooled g [Nk][dv] (rows = positions, bf16), o [Nq][dv] bf16, lse [Nq] fp32 (row max + log row sum).
+ * Supported: Nq % 128 == 0, Nk % 128 == 0, dk in {8, 16}, dv in {32, 64} (C = 64 / 128 of the '256', '512thin'
+ * and '512' configs, models/pluggan.py:252-325); ttg_attn_supported() tells, other shapes return an error.
+ * ttg_attn_bwd: first-order backward (dq, dk, dv from dout, recomputing beta tile by tile); workspace of
+ * ttg_attn_bwd_workspace_bytes() bytes, no initialisation needed. */
+int ttg_attn_supported(int Nq, int Nk, int dk, int dv);
+int ttg_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int Nq, int Nk, int dk,
+                 int dv, void* stream);
+size_t ttg_attn_bwd_workspace_bytes(int batch, int Nq, int dk);
+int ttg_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                 void* dq, void* dk_out, void* dv_out, int batch, int Nq, int Nk, int dk, int dv, void* workspace,
+                 void* stream);
 /* gamma * o (attention.py:35): out = x * (*dev_scale); and the dot product giving d/dgamma */
 int ttg_scale_dev(const void* x, void* out, long long n, const float* dev_scale, int dtype, void* stream);
 int ttg_dot_f32out(const void* a, const void* b, float* out, long long n, void* workspace, int dtype, void* stream);

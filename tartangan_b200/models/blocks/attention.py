@@ -27,8 +27,7 @@ class SelfAttention2d(nn.Module):
         theta = self.theta(x1).permute(0, 2, 3, 1).reshape(n, h * w, c // 8)
         phi = ops.max_pool2(self.phi(x2)).permute(0, 2, 3, 1).reshape(n, h * w // 4, c // 8)
         g = ops.max_pool2(self.g(x3)).permute(0, 2, 3, 1).reshape(n, h * w // 4, c // 2)
-        beta = ops.SoftmaxFn.apply(ops.BmmFn.apply(theta, phi, False, True))      # (n, HW, HW/4)
-        mixed = ops.BmmFn.apply(beta, g, False, False)                            # (n, HW, C/2)
+        mixed = ops.attention_core(theta, phi, g)                                 # (n, HW, C/2); beta = (n, HW, HW/4)
         mixed = mixed.reshape(n, h, w, c // 2).permute(0, 3, 1, 2)
         o = self.o(mixed)
         return ops.add(ops.ScaleDevFn.apply(o, self.gamma.reshape(1)), xs)

@@ -29,6 +29,7 @@ class _State:
     launches = 0                   # kernels launched through the C ABI (bench counter)
     pack_generation = 0            # bumped to invalidate every packed-weight cache (CUDA-graph capture)
     producer_stats = None          # (tensor, float64 sums) left by a producer kernel (conv / residual join) for bn_act
+    fused_attention = True         # tcgen05 attention kernels when the shape allows (else bmm / softmax / bmm)
 
 
 state = _State()
@@ -1208,6 +1209,61 @@ class SoftmaxBwdFn(Function):
         call('ttg_softmax_bwd2', ptr(y), ptr(g), ptr(w), ptr(cot_g), ptr(cot_y), y.numel() // y.shape[-1],
              y.shape[-1], dtype_code(y.dtype))
         return cot_y, cot_g
+
+
+def _attention_unfused(q, k, v):
+    """softmax(q k^T) v with beta materialised: every step is a differentiable op of this file."""
+    beta = SoftmaxFn.apply(BmmFn.apply(q, k, False, True))
+    return BmmFn.apply(beta, v, False, False)
+
+
+def attention_fused_ok(q, k, v):
+    return (state.fused_attention and q.dtype == torch.bfloat16 and q.dim() == 3 and
+            bool(_lib.lib.ttg_attn_supported(q.shape[1], k.shape[1], q.shape[2], v.shape[2])))
+
+
+class FusedAttentionFn(Function):
+    """o = softmax(q k^T) v per image on the tcgen05 kernels (reference attention.py:25-34), beta never stored.
+
+    backward: the fused recompute kernel; under ``create_graph`` (the R1 penalty differentiates D's attention
+    twice, models/losses.py:23) the gradients are rebuilt from the differentiable bmm / softmax ops instead, so
+    the second backward sees an ordinary graph."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        q, k, v = _flat(q), _flat(k), _flat(v)
+        bt, nq, dk = q.shape
+        nk, dv = k.shape[1], v.shape[2]
+        o = torch.empty((bt, nq, dv), dtype=q.dtype, device=q.device)
+        lse = torch.empty((bt, nq), dtype=torch.float32, device=q.device)
+        call('ttg_attn_fwd', ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), bt, nq, nk, dk, dv)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.mark_non_differentiable(lse)
+        return o
+
+    @staticmethod
+    def backward(ctx, go):
+        q, k, v, o, lse = ctx.saved_tensors
+        go = _flat(go)
+        if torch.is_grad_enabled():
+            beta = SoftmaxFn.apply(BmmFn.apply(q, k, False, True))
+            gv = BmmFn.apply(beta, go, True, False)
+            gs = SoftmaxBwdFn.apply(beta, BmmFn.apply(go, v, False, True))
+            return BmmFn.apply(gs, k, False, False), BmmFn.apply(gs, q, True, False), gv
+        bt, nq, dk = q.shape
+        nk, dv = k.shape[1], v.shape[2]
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ws = _ws(_lib.lib.ttg_attn_bwd_workspace_bytes(bt, nq, dk), q.device)
+        call('ttg_attn_bwd', ptr(q), ptr(k), ptr(v), ptr(o), ptr(go), ptr(lse), ptr(gq), ptr(gk), ptr(gv), bt, nq, nk,
+             dk, dv, ptr(ws))
+        return gq, gk, gv
+
+
+def attention_core(q, k, v):
+    """(batch, Nq, dk), (batch, Nk, dk), (batch, Nk, dv) -> (batch, Nq, dv)."""
+    if attention_fused_ok(q, k, v):
+        return FusedAttentionFn.apply(q, k, v)
+    return _attention_unfused(q, k, v)
 
 
 class ScaleDevFn(Function):
