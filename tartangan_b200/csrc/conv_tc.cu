@@ -1507,11 +1507,12 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
                           const float* pre_scale, const float* pre_shift, float slope, double* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // 8-channel staging tensors (ttg_pad_channels8) ride the TMA path: not "padded" in the scalar-access sense
-  const bool in8 = cin_real == 8 && Cin == 16, out8 = cout_real == 8 && Cout == 16;
+  // (genuine 8-channel layers of the '512thin' config look the same; with an upsample, a prologue or an fp32 output
+  // they take the scalar-access padded path below instead)
+  const bool tma8 = !pre_scale && up == 0 && g_use_tma && dtype_out == TTG_BF16 && ttg_get_encode_tiled() != nullptr;
+  const bool in8 = tma8 && cin_real == 8 && Cin == 16, out8 = tma8 && cout_real == 8 && Cout == 16;
   const bool padded = (cin_real != Cin && !in8) || (cout_real != Cout && !out8);
   TTG_REQUIRE(cin_real >= 1 && cin_real <= Cin && cout_real >= 1 && cout_real <= Cout, "conv2d_tc: bad real channel counts");
-  TTG_REQUIRE(!(in8 || out8) || (!pre_scale && up == 0 && g_use_tma && dtype_out == TTG_BF16 && ttg_get_encode_tiled() != nullptr),
-              "conv2d_tc: 8-channel staging tensors need the TMA path (bf16 output, no upsample / prologue)");
   TTG_REQUIRE(!padded || ((cin_real == Cin || cin_real <= 8) && (cout_real == Cout || (cout_real <= 16 && Cout == 16)) && !pre_scale),
               "conv2d_tc: channel padding supports <= 8 real input channels / Cout padded to 16, without prologue");
   TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_tc: ksize %d unsupported", ksize);
@@ -1558,10 +1559,12 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
       const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
 #define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, stats, st, &used)
       int rc;
+      // activation slots that fit next to the resident filter (256 -> 128 1x1: 64 KB filter + 64 KB tiles -> 2 slots)
+      const bool three = ((w_bytes + 127) & ~127) + 3 * a_bytes + 256 + tc_epi_bytes(Cout) <= 227 * 1024;
       if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 4, 16) : Cin == 32 ? TTG_TMA(3, 4, 32) : Cin == 64 ? TTG_TMA(3, 3, 64)
-                                     : (deep ? TTG_TMA(3, 4, 0) : TTG_TMA(3, 3, 0));
+                                     : (deep ? TTG_TMA(3, 4, 0) : three ? TTG_TMA(3, 3, 0) : TTG_TMA(3, 2, 0));
       else rc = Cin == 16 ? TTG_TMA(1, 4, 16) : Cin == 32 ? TTG_TMA(1, 4, 32) : Cin == 64 ? TTG_TMA(1, 3, 64)
-                          : (deep ? TTG_TMA(1, 4, 0) : TTG_TMA(1, 3, 0));
+                          : (deep ? TTG_TMA(1, 4, 0) : three ? TTG_TMA(1, 3, 0) : TTG_TMA(1, 2, 0));
 #undef TTG_TMA
       if (rc != TTG_OK || used) return rc;
     }

@@ -374,7 +374,8 @@ class ConvWgradBiasFn(Function):
             gw = gw8[:, :cin].contiguous()
         else:
             gw = torch.empty((cout, cin, k, k), dtype=torch.float32, device=x.device)
-            call('ttg_conv2d_wgrad_bias_tc_ex', ptr(x), ptr(gy), ptr(gw), ptr(gb), n, h, w, cin, cout, cin, cout, k, 0, ptr(ws))
+            call('ttg_conv2d_wgrad_bias_tc_ex', ptr(x), ptr(gy), ptr(gw), ptr(gb), n, h, w, _pad16(cin), cout, cin, cout, k, 0,
+                 ptr(ws))
         return gw, gb
 
     @staticmethod

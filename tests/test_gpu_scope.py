@@ -134,6 +134,57 @@ def test_attention_configs_run_and_track_oracle(kind, config):
         assert abs(got[k] - ref[k]) <= 5e-3 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
 
 
+@pytest.mark.parametrize('kind,config,kw', [('cnn', '256sa', {}), ('iqn', '512thin', {'num_quantiles': 64}),
+                                            ('iqn', '512', {'num_quantiles': 64, 'attention': '3'})])
+def test_attention_configs_full_width_bf16(kind, config, kw):
+    """BASELINE configs 4 and 5 at FULL width (256 / 8-channel layers, fused tcgen05 attention at 64x64 and 32x32),
+    bf16 mode, batch 2: first-step losses within 5 % of the CPU oracle (fp32) for '256sa' / '512thin' (the
+    bf16 first-step bar of DESIGN.md section 6); for every config the fused and the un-fused attention paths agree
+    and a CUDA-graph replay of the step reproduces the eager losses' magnitude."""
+    from oracle import tartan_oracle as O
+    from tartangan_b200 import ops
+    from tartangan_b200.trainers.cnn import CNNTrainer
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    cls = IQNTrainer if kind == 'iqn' else CNNTrainer
+
+    def build(**extra):
+        torch.manual_seed(0)
+        t = make_trainer(cls, config=config, batch_size=2, precision='bf16', **kw, **extra)
+        with torch.no_grad():
+            for m in list(t.g.modules()) + list(t.d.modules()) + list(t.target_g.modules()):
+                if hasattr(m, 'gamma'):
+                    m.gamma.fill_(0.5)
+        return t
+    res = {}
+    for fused in (True, False):
+        ops.state.fused_attention = fused
+        try:
+            t = build()
+            imgs = O.tartan_batch(5, 2, t.g.max_size)
+            if fused and config != '512':
+                cfg = t.gan_config
+                spec = O.Spec(4, cfg.latent_dims, 3, tuple(cfg.blocks), tuple(cfg.attention))
+                cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+                orc = O.OracleTrainer(kind, spec, cpu(t.g), cpu(t.target_g), cpu(t.d), 2, num_quantiles=kw.get('num_quantiles', 8))
+                torch.manual_seed(77)
+                res['oracle'] = orc.train_batch(imgs)
+            torch.manual_seed(77)
+            res[fused] = t.train_batch(imgs)
+        finally:
+            ops.state.fused_attention = True
+    for k in res[True]:
+        assert res[True][k] == res[True][k] and abs(res[True][k]) < 1e4, (k, res[True])
+        assert abs(res[True][k] - res[False][k]) <= 3e-2 * max(1.0, abs(res[False][k])), (k, res[True], res[False])
+        if 'oracle' in res:
+            assert abs(res[True][k] - res['oracle'][k]) <= 5e-2 * max(1.0, abs(res['oracle'][k])), (k, res[True], res['oracle'])
+    tg = build(cuda_graph=True)
+    torch.manual_seed(77)
+    got = tg.train_batch(O.tartan_batch(5, 2, tg.g.max_size))
+    for k in got:
+        assert abs(got[k] - res[True][k]) <= 3e-2 * max(1.0, abs(res[True][k])), (k, got, res[True])
+
+
 def test_checkpoint_layout_round_trip(tmp_path):
     """components/model_checkpoint.py layout: {output}/{run_id}/checkpoints/{steps}/{g,g_target,d,opt_d,opt_g}.pt + trainer.json"""
     from tartangan_b200.trainers.iqn import IQNTrainer

@@ -12,6 +12,9 @@ SHAPES = [  # cin, cout, k, h, w, n, up
     (64, 64, 3, 8, 8, 2, 0), (128, 128, 3, 16, 16, 2, 0), (256, 256, 3, 8, 8, 1, 0), (128, 64, 1, 8, 8, 2, 0),
     (64, 32, 3, 16, 16, 2, 1), (32, 32, 3, 4, 4, 3, 0), (256, 128, 3, 16, 16, 1, 0),
     (3, 16, 3, 32, 24, 2, 0), (16, 3, 1, 16, 16, 2, 0), (3, 32, 1, 16, 16, 2, 0), (32, 3, 3, 20, 12, 1, 0),
+    # layers of the '256' / '512' configs (BASELINE configs 4 and 5): 256-channel 1x1 projections and 3x3 convs
+    (256, 128, 1, 16, 16, 2, 0), (128, 256, 1, 16, 16, 2, 0), (128, 256, 3, 16, 16, 1, 0), (256, 256, 3, 16, 16, 2, 1),
+    (256, 256, 1, 8, 8, 2, 0), (8, 8, 3, 32, 32, 1, 0), (16, 8, 3, 32, 32, 2, 1), (16, 8, 1, 32, 32, 2, 0),
 ]
 
 
