@@ -30,73 +30,94 @@ __device__ __forceinline__ void att_cp16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void att_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void att_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void att_cp_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ uint32_t att_pack2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int DK8, int DV, int NKT>
-__global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
-                                                       const bf16* __restrict__ V, bf16* __restrict__ O,
-                                                       float* __restrict__ LSE, int Nq, int Nk, int tiles_per_cta) {
-  constexpr int DK = DK8 * 8, DV8 = DV / 8;
+__device__ __forceinline__ void att_group_sync(int g) { asm volatile("bar.sync %0, 160;" ::"r"(g + 1) : "memory"); }
+
+// NG = query-tile groups per CTA (each: 4 softmax warps + 1 issuer warp, own Q / P buffers, own TMEM columns and
+// barriers, sharing the resident K / V).  NG = 2 puts two warps on every SM sub-partition, so that one group's
+// TMEM loads / barrier waits hide under the other group's MUFU work.
+template <int DK8, int DV, int NKT, int NG>
+__global__ void __launch_bounds__(NG * 160) attn_fwd_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ K,
+                                                            const bf16* __restrict__ V, bf16* __restrict__ O,
+                                                            float* __restrict__ LSE, int Nq, int Nk, int tiles_per_cta) {
+  constexpr int DK = DK8 * 8, DV8 = DV / 8, NT = NG * 160, TCOLS = 2 * NKT + 2 * DV;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sQ = smem;                                   // [2 planes][128 rows] x 16 B
-  uint8_t* sK = sQ + 2 * 128 * 16;                      // [2 planes][Nk] x 16 B
+  uint8_t* sQ = smem;                                   // [NG][2 planes][128 rows] x 16 B
+  uint8_t* sK = sQ + NG * 4096;                         // [2 planes][Nk] x 16 B
   uint8_t* sV = sK + (size_t)2 * Nk * 16;               // [DV8 planes][Nk] x 16 B
-  uint8_t* sP = sV + (size_t)DV8 * Nk * 16;             // [2 buffers][NKT/8 planes][128 rows] x 16 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * NKT * 256);
-  uint64_t* s_full = bars;                              // [2] S_j landed in TMEM
-  uint64_t* p_full = bars + 2;                          // [2] P_j written (128 arrivals); S buffer free
-  uint64_t* o_full = bars + 4;                          // [2] OP_j landed; P buffer free
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint8_t* sP = sV + (size_t)DV8 * Nk * 16;             // [NG][2 buffers][NKT/8 planes][128 rows] x 16 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NG * 2 * NKT * 256);     // per group: s_full[2], p_full[2], o_full[2]
+  uint64_t* v_ready = bars + 6 * NG;                     // V landed (one arrival per softmax thread)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 * NG + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer = warp >= 4 * NG;
+  const int grp = issuer ? warp - 4 * NG : warp >> 2;
+  const int row = tid & 127;                            // softmax threads: query row of the group's tile = TMEM lane
   const int qtiles = Nq >> 7, nkt = Nk / NKT;
   const long long t0 = (long long)blockIdx.x * tiles_per_cta;
   const int img = (int)(t0 / qtiles), qt0 = (int)(t0 % qtiles);
   Q += (long long)img * Nq * DK; K += (long long)img * Nk * DK; V += (long long)img * Nk * DV;
   O += (long long)img * Nq * DV; LSE += (long long)img * Nq;
 
-  if (warp == 4) tmem_alloc(tmem_slot, 512u);
+  if (warp == 4 * NG) tmem_alloc(tmem_slot, 512u);
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) { mbar_init(&s_full[b], 1); mbar_init(&p_full[b], 128); mbar_init(&o_full[b], 1); }
+    for (int g = 0; g < NG; ++g)
+      for (int b = 0; b < 2; ++b) { mbar_init(&bars[6 * g + b], 1); mbar_init(&bars[6 * g + 2 + b], 128); mbar_init(&bars[6 * g + 4 + b], 1); }
+    mbar_init(v_ready, 128 * NG);
     mbar_fence_init();
   }
-  const uint32_t sQ_a = smem_u32(sQ), sK_a = smem_u32(sK), sV_a = smem_u32(sV), sP_a = smem_u32(sP);
-  for (int u = tid; u < Nk * DK8; u += 160) {
+  const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+  for (int u = tid; u < Nk * DK8; u += NT) {
     const int key = u / DK8, g = u - key * DK8;
     att_cp16(sK_a + (uint32_t)(g * Nk + key) * 16, K + (long long)key * DK + g * 8);
   }
-  for (int u = tid; u < Nk * DV8; u += 160) {
-    const int key = u / DV8, g = u - key * DV8;
-    att_cp16(sV_a + (uint32_t)(g * Nk + key) * 16, V + (long long)key * DV + g * 8);
-  }
+  att_cp_commit();
+  // V is not needed before the first P V product: the softmax threads fetch it as a second cp.async group and
+  // publish it through v_ready after their first score tile
+  if (!issuer)
+    for (int u = tid; u < Nk * DV8; u += 128 * NG) {
+      const int key = u / DV8, g = u - key * DV8;
+      att_cp16(sV_a + (uint32_t)(g * Nk + key) * 16, V + (long long)key * DV + g * 8);
+    }
+  att_cp_commit();
   if (DK8 == 1) {          // the contraction is padded to one k16 step: the second channel group is zero
-    for (int u = tid; u < Nk; u += 160) *reinterpret_cast<uint4*>(sK + (size_t)(Nk + u) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < 128) *reinterpret_cast<uint4*>(sQ + (size_t)(128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int u = tid; u < Nk; u += NT) *reinterpret_cast<uint4*>(sK + (size_t)(Nk + u) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (!issuer) *reinterpret_cast<uint4*>(sQ + (size_t)grp * 4096 + (size_t)(128 + row) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
-  att_cp_wait_all();
+  att_cp_wait_but_one();
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 2 * NKT;
+  const uint32_t tS = tmem_base + (uint32_t)(grp * TCOLS), tO = tS + 2 * NKT;
+  uint64_t* s_full = bars + 6 * grp;                    // [2] S_j landed in TMEM
+  uint64_t* p_full = s_full + 2;                        // [2] P_j written (128 arrivals); S buffer free
+  uint64_t* o_full = s_full + 4;                        // [2] OP_j landed; P buffer free
+  uint8_t* sQg = sQ + (size_t)grp * 4096;
+  uint8_t* sPg = sP + (size_t)grp * 2 * NKT * 256;
+  const uint32_t sQ_a = smem_u32(sQg), sP_a = smem_u32(sPg);
 
   uint32_t ph_s = 0, ph_p = 0, ph_o = 0;                // bit b = parity the next wait on barrier b expects
-  for (int t = 0; t < tiles_per_cta; ++t) {
+  for (int t = grp; t < tiles_per_cta; t += NG) {
     const int q0 = (qt0 + t) * 128;
-    if (tid < 128) {
+    if (!issuer) {
 #pragma unroll
       for (int g = 0; g < DK8; ++g)
-        *reinterpret_cast<uint4*>(sQ + (size_t)(g * 128 + tid) * 16) =
-            *reinterpret_cast<const uint4*>(Q + (long long)(q0 + tid) * DK + g * 8);
+        *reinterpret_cast<uint4*>(sQg + (size_t)(g * 128 + row) * 16) =
+            *reinterpret_cast<const uint4*>(Q + (long long)(q0 + row) * DK + g * 8);
     }
     fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 4) {
+    att_group_sync(grp);
+    if (issuer) {
       if (elect_one()) {
         tc_fence_after_sync();
         const uint32_t idS = umma_idesc_bf16(128, NKT, 0, 0), idO = umma_idesc_bf16(128, DV, 0, 1);
@@ -112,6 +133,7 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
         for (int j = 0; j < nkt; ++j) {
           const int b = j & 1;
           mbar_wait(&p_full[b], (php >> b) & 1u); php ^= 1u << b;
+          if (t == grp && j == 0) mbar_wait(v_ready, 0u);
           tc_fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < NKT / 16; ++ks) {
@@ -127,7 +149,7 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
       // every lane tracks the parities so that any lane may be elected for the next tile
       ph_p ^= (uint32_t)(((nkt + 1) >> 1) & 1) | ((uint32_t)((nkt >> 1) & 1) << 1);
     } else {
-      const uint32_t lane_t = (uint32_t)(warp * 32) << 16;
+      const uint32_t lane_t = (uint32_t)((warp & 3) * 32) << 16;
       float m = -INFINITY, l = 0.f;
       float o[DV];
 #pragma unroll
@@ -137,34 +159,27 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
         mbar_wait(&s_full[b], (ph_s >> b) & 1u); ph_s ^= 1u << b;
         tc_fence_after_sync();
         const uint32_t ts = tS + lane_t + (uint32_t)(b * NKT);
+        uint32_t s[NKT];                                 // the whole score row of this key tile, read from TMEM once
+#pragma unroll
+        for (int c = 0; c < NKT; c += 16) tmem_ld16(ts + c, s + c);
+        tmem_ld_wait();
         float mx = m;
 #pragma unroll
-        for (int c = 0; c < NKT; c += 32) {
-          uint32_t r[32];
-          tmem_ld16(ts + c, r); tmem_ld16(ts + c + 16, r + 16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+        for (int c = 0; c < NKT; ++c) mx = fmaxf(mx, __uint_as_float(s[c]));
         const float mxl = mx * ATT_LOG2E;
         const float alpha = att_ex2(m * ATT_LOG2E - mxl);
         float rs = 0.f;
-        uint8_t* prow = sP + (size_t)b * NKT * 256 + (size_t)tid * 16;
+        uint8_t* prow = sPg + (size_t)b * NKT * 256 + (size_t)row * 16;
 #pragma unroll
-        for (int c = 0; c < NKT; c += 32) {
-          uint32_t r[32];
-          tmem_ld16(ts + c, r); tmem_ld16(ts + c + 16, r + 16);
-          tmem_ld_wait();
+        for (int c = 0; c < NKT; c += 8) {
+          float p[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            float p[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { p[e] = att_ex2(fmaf(__uint_as_float(r[i + e]), ATT_LOG2E, -mxl)); rs += p[e]; }
-            *reinterpret_cast<uint4*>(prow + (size_t)((c + i) >> 3) * 2048) =
-                make_uint4(att_pack2(p[0], p[1]), att_pack2(p[2], p[3]), att_pack2(p[4], p[5]), att_pack2(p[6], p[7]));
-          }
+          for (int e = 0; e < 8; ++e) { p[e] = att_ex2(fmaf(__uint_as_float(s[c + e]), ATT_LOG2E, -mxl)); rs += p[e]; }
+          *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 2048) =
+              make_uint4(att_pack2(p[0], p[1]), att_pack2(p[2], p[3]), att_pack2(p[4], p[5]), att_pack2(p[6], p[7]));
         }
         l = l * alpha + rs; m = mx;
+        if (t == grp && j == 0) { att_cp_wait_all(); fence_proxy_async_smem(); mbar_arrive(v_ready); }
         tc_fence_before_sync();
         fence_proxy_async_smem();
         mbar_arrive(&p_full[b]);
@@ -172,17 +187,21 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
           const int pb = b ^ 1;
           mbar_wait(&o_full[pb], (ph_o >> pb) & 1u); ph_o ^= 1u << pb;
           tc_fence_after_sync();
+          // the running maximum settles after a few key tiles: skip the multiply when no row of the warp moved
+          const bool rescale = __any_sync(0xffffffffu, alpha != 1.f);
 #pragma unroll
           for (int c = 0; c < DV; c += 16) {
             uint32_t r[16];
             tmem_ld16(tO + lane_t + (uint32_t)(pb * DV + c), r);
             tmem_ld_wait();
+            if (rescale) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[c + i] = (o[c + i] + __uint_as_float(r[i])) * alpha;
+              for (int i = 0; i < 16; ++i) o[c + i] = (o[c + i] + __uint_as_float(r[i])) * alpha;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(r[i]);
+            }
           }
-        } else {
-#pragma unroll
-          for (int c = 0; c < DV; ++c) o[c] *= alpha;    // o is 0 on the first tile; keeps the recurrence uniform
         }
       }
       {
@@ -190,7 +209,7 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
         mbar_wait(&o_full[pb], (ph_o >> pb) & 1u); ph_o ^= 1u << pb;
         tc_fence_after_sync();
         const float inv = 1.f / l;
-        bf16* orow = O + (long long)(q0 + tid) * DV;
+        bf16* orow = O + (long long)(q0 + row) * DV;
 #pragma unroll
         for (int c = 0; c < DV; c += 16) {
           uint32_t r[16];
@@ -202,46 +221,55 @@ __global__ void __launch_bounds__(160) attn_fwd_kernel(const bf16* __restrict__ 
           *reinterpret_cast<uint4*>(orow + c) = make_uint4(att_pack2(f[0], f[1]), att_pack2(f[2], f[3]), att_pack2(f[4], f[5]), att_pack2(f[6], f[7]));
           *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(att_pack2(f[8], f[9]), att_pack2(f[10], f[11]), att_pack2(f[12], f[13]), att_pack2(f[14], f[15]));
         }
-        LSE[q0 + tid] = m + __logf(l);
+        LSE[q0 + row] = m + __logf(l);
       }
     }
     tc_fence_before_sync();
-    __syncthreads();
+    att_group_sync(grp);                                 // the group's MMAs have all completed: sQ / TMEM may be reused
     tc_fence_after_sync();
   }
-  if (warp == 4) tmem_dealloc(tmem_base, 512u);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4 * NG) tmem_dealloc(tmem_base, 512u);
 }
 
-static inline size_t attn_fwd_smem(int Nk, int dv, int nkt) { return 4096 + (size_t)32 * Nk + (size_t)2 * dv * Nk + (size_t)512 * nkt + 64; }
-static inline int attn_pick_nkt(int Nk, int dv) {
-  if (Nk % 128 == 0 && attn_fwd_smem(Nk, dv, 128) <= 232448) return 128;
-  if (Nk % 64 == 0 && attn_fwd_smem(Nk, dv, 64) <= 232448) return 64;
-  return 0;
+// shared memory of the forward kernel: Q, resident K (padded to 16 channels) and V, P double buffers, barriers
+static inline size_t attn_fwd_smem(int Nk, int dv, int nkt, int ng) {
+  return (size_t)ng * 4096 + (size_t)32 * Nk + (size_t)2 * dv * Nk + (size_t)ng * 512 * nkt + 128;   // 13 barriers + TMEM slot
+}
+// (key tile, groups): two groups of 64-key tiles when they fit (TMEM: 2 x (128 + 2 dv) columns), else one group
+static inline void attn_pick(int Nq, int Nk, int dv, int* nkt, int* ng) {
+  *nkt = 0; *ng = 0;
+  if ((Nq / 128) % 2 == 0 && Nk % 64 == 0 && attn_fwd_smem(Nk, dv, 64, 2) <= 232448) { *nkt = 64; *ng = 2; return; }
+  if (Nk % 128 == 0 && attn_fwd_smem(Nk, dv, 128, 1) <= 232448) { *nkt = 128; *ng = 1; return; }
+  if (Nk % 64 == 0 && attn_fwd_smem(Nk, dv, 64, 1) <= 232448) { *nkt = 64; *ng = 1; return; }
 }
 extern "C" int ttg_attn_supported(int Nq, int Nk, int dk, int dv) {
   if (Nq <= 0 || Nq % 128 != 0) return 0;
   if (!(dk == 8 || dk == 16) || !(dv == 32 || dv == 64)) return 0;
   if (Nk < 128 || Nk % 128 != 0) return 0;               // the backward kernel owns 128 keys per CTA
-  return attn_pick_nkt(Nk, dv) != 0;
+  int nkt, ng;
+  attn_pick(Nq, Nk, dv, &nkt, &ng);
+  return nkt != 0;
 }
 
-template <int DK8, int DV, int NKT>
+template <int DK8, int DV, int NKT, int NG>
 static int attn_fwd_launch(const void* q, const void* k, const void* v, void* o, float* lse, int batch, int Nq, int Nk,
                            cudaStream_t st) {
-  const size_t smem = attn_fwd_smem(Nk, DV, NKT);
+  const size_t smem = attn_fwd_smem(Nk, DV, NKT, NG);
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DK8, DV, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<DK8, DV, NKT, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "attn_fwd: %s", cudaGetErrorString(e));
     attr = true;
   }
-  // consecutive query tiles of one image per CTA (K / V staged once); the smallest group that fits one wave
+  // consecutive query tiles of one image per CTA (K / V staged once): the smallest multiple of NG that fits one wave
   const int qtiles = Nq / 128;
   int tpc = qtiles;
-  for (int d = 1; d <= qtiles; ++d)
+  for (int d = NG; d <= qtiles; d += NG)
     if (qtiles % d == 0 && (long long)batch * (qtiles / d) <= ttg_num_sms()) { tpc = d; break; }
   const int grid = batch * (qtiles / tpc);
-  attn_fwd_kernel<DK8, DV, NKT><<<grid, 160, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lse, Nq, Nk, tpc);
+  attn_fwd_kernel<DK8, DV, NKT, NG><<<grid, NG * 160, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)o, lse, Nq, Nk, tpc);
   TTG_CHECK_LAUNCH("attn_fwd");
   return TTG_OK;
 }
@@ -252,11 +280,14 @@ extern "C" int ttg_attn_fwd(const void* q, const void* k, const void* v, void* o
     return ttg_set_error(TTG_ERR_UNSUPPORTED, "attn_fwd: unsupported shape Nq=%d Nk=%d dk=%d dv=%d", Nq, Nk, dk, dv);
   TTG_REQUIRE(batch > 0, "attn_fwd: empty batch");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nkt = attn_pick_nkt(Nk, dv);
-#define ATT_FWD(D8, DVV)                                                                              \
-  if (dk == D8 * 8 && dv == DVV)                                                                      \
-    return nkt == 128 ? attn_fwd_launch<D8, DVV, 128>(q, k, v, o, lse, batch, Nq, Nk, st)             \
-                      : attn_fwd_launch<D8, DVV, 64>(q, k, v, o, lse, batch, Nq, Nk, st);
+  int nkt, ng;
+  attn_pick(Nq, Nk, dv, &nkt, &ng);
+#define ATT_FWD(D8, DVV)                                                                                        \
+  if (dk == D8 * 8 && dv == DVV) {                                                                              \
+    if (ng == 2) return attn_fwd_launch<D8, DVV, 64, 2>(q, k, v, o, lse, batch, Nq, Nk, st);                    \
+    return nkt == 128 ? attn_fwd_launch<D8, DVV, 128, 1>(q, k, v, o, lse, batch, Nq, Nk, st)                    \
+                      : attn_fwd_launch<D8, DVV, 64, 1>(q, k, v, o, lse, batch, Nq, Nk, st);                    \
+  }
   ATT_FWD(1, 32) ATT_FWD(2, 32) ATT_FWD(1, 64) ATT_FWD(2, 64)
 #undef ATT_FWD
   return ttg_set_error(TTG_ERR_UNSUPPORTED, "attn_fwd: no instantiation");
