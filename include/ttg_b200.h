@@ -150,6 +150,12 @@ int ttg_spatial_bcast(const float* g, void* gx, int N, int HW, int C, int dtype,
 /* module boundary: reference tensors are fp32 NCHW (trainers/trainer.py:57-61,69-74) */
 int ttg_nchw_to_nhwc(const float* x, void* y, int N, int C, int HW, int dtype, void* stream);
 int ttg_nhwc_to_nchw(const void* x, float* y, int N, int C, int HW, int dtype, void* stream);
+/* Device-side input pipeline (datasets/image_bytes_dataset.py:44-49 + trainers/trainer.py:69-74: random crop of a
+ * uint8 HWC image, ToTensor, Normalize(0.5, 0.5)): stack [M][H][W][C] uint8 resident in device memory;
+ * out[b][c][y][x] = stack[index[b]][oy[b] + y][ox[b] + x][c] / 127.5 - 1 as fp32 NCHW (nchw_out = 1) or as the
+ * NHWC activation tensor (nchw_out = 0, dtype_out).  index / oy / ox: int32 device arrays of length B. */
+int ttg_u8_crop_normalize(const unsigned char* stack, const int* index, const int* oy, const int* ox, void* out, int B,
+                          int H, int W, int C, int size, int dtype_out, int nchw_out, void* stream);
 int ttg_cast(const void* x, int src_dtype, void* y, int dst_dtype, long long n, void* stream);
 /* nn.Tanh at the generator output (generator.py:126) */
 int ttg_tanh_fwd(const float* x, float* y, long long n, void* stream);

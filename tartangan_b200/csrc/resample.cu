@@ -519,3 +519,39 @@ extern "C" int ttg_tanh_bwd(const float* y, const float* g, float* gx, long long
   TTG_CHECK_LAUNCH("tanh_bwd");
   return TTG_OK;
 }
+
+// ---------------------------------------------------------------- device-side input pipeline
+// The reference keeps its dataset as a uint8 stack (datasets/image_bytes_dataset.py:44-49: random crop, then
+// ToTensor + Normalize(0.5, 0.5) = v / 127.5 - 1).  Here the stack [M][H][W][C] stays in HBM and one kernel crops
+// and normalises a whole batch: out[b][c][y][x] = stack[index[b]][oy[b] + y][ox[b] + x][c] / 127.5 - 1, written
+// either as fp32 NCHW (the reference's batch layout) or as the internal NHWC activation tensor.
+template <typename T, bool NCHW>
+__global__ void u8_crop_norm_kernel(const unsigned char* __restrict__ stack, const int* __restrict__ index,
+                                    const int* __restrict__ oy, const int* __restrict__ ox, T* __restrict__ out, int B, int H,
+                                    int W, int C, int S) {
+  const long long total = (long long)B * S * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S); long long p = i / S;
+    const int y = (int)(p % S); const int b = (int)(p / S);
+    const unsigned char* src = stack + (((long long)index[b] * H + oy[b] + y) * W + ox[b] + x) * C;
+    for (int c = 0; c < C; ++c) {
+      const float v = (float)src[c] / 127.5f - 1.f;           // IEEE division: bit-identical to the host pipeline
+      if (NCHW) out[(((long long)b * C + c) * S + y) * S + x] = from_f<T>(v);
+      else out[i * C + c] = from_f<T>(v);
+    }
+  }
+}
+extern "C" int ttg_u8_crop_normalize(const unsigned char* stack, const int* index, const int* oy, const int* ox, void* out,
+                                     int B, int H, int W, int C, int size, int dtype_out, int nchw_out, void* stream) {
+  TTG_REQUIRE(B > 0 && C > 0 && size > 0 && size <= H && size <= W, "u8_crop_normalize: bad sizes");
+  TTG_REQUIRE(!nchw_out || dtype_out == TTG_F32, "u8_crop_normalize: NCHW output is fp32 (the reference's batch layout)");
+  const long long total = (long long)B * size * size;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nchw_out) {
+    u8_crop_norm_kernel<float, true><<<ttg_grid_for(total, 256), 256, 0, st>>>(stack, index, oy, ox, (float*)out, B, H, W, C, size);
+  } else {
+    TTG_DISPATCH(dtype_out, { u8_crop_norm_kernel<T, false><<<ttg_grid_for(total, 256), 256, 0, st>>>(stack, index, oy, ox, (T*)out, B, H, W, C, size); });
+  }
+  TTG_CHECK_LAUNCH("u8_crop_normalize");
+  return TTG_OK;
+}

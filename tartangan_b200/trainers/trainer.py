@@ -15,6 +15,7 @@ from datetime import datetime
 import numpy as np
 import torch
 
+from .._lib import call, dtype_code, ptr
 from .utils import set_device_from_args
 
 
@@ -76,6 +77,56 @@ class NpzImageDataset(torch.utils.data.Dataset):
         return crop.permute(2, 0, 1).float() / 127.5 - 1.0
 
 
+class DeviceImageStack:
+    """Device-side input pipeline: the uint8 image stack of an .npz lives in HBM and a
+    batch is cropped + normalised by ONE kernel (ttg_u8_crop_normalize) instead of a per-image numpy / PIL loop and
+    a host-to-device copy of fp32 pixels.  Same contract as NpzImageDataset + DataLoader(shuffle=True,
+    drop_last=True): every epoch visits each image once in a random order, every visit takes a fresh uniform crop;
+    batches are fp32 NCHW in [-1, 1] (what `train_batch` is given by the reference, trainers/trainer.py:84-86).
+    Index / crop draws come from a CPU torch.Generator, like z and tau (trainer.py:153-156)."""
+
+    def __init__(self, images, size, device='cuda', seed=None):
+        images = torch.as_tensor(np.ascontiguousarray(images))
+        if images.dtype != torch.uint8 or images.dim() != 4:
+            raise ValueError('DeviceImageStack: expected a uint8 array of shape (M, H, W, C)')
+        self.stack = images.to(device)
+        self.size = size
+        self.m, self.h, self.w, self.c = images.shape
+        if size > self.h or size > self.w:
+            raise ValueError(f'DeviceImageStack: crop {size} larger than the images ({self.h}x{self.w})')
+        self.gen = torch.Generator()
+        if seed is not None:
+            self.gen.manual_seed(seed)
+
+    def __len__(self):
+        return self.m
+
+    def crop(self, index, oy, ox, internal=False):
+        """Batch for explicit (image index, crop origin) triples (int tensors of equal length)."""
+        from .. import ops
+        b = len(index)
+        dev = self.stack.device
+        # one packed host->device copy for the three int32 vectors
+        meta = torch.stack([torch.as_tensor(index), torch.as_tensor(oy), torch.as_tensor(ox)]).to(torch.int32)
+        meta = meta.pin_memory().to(dev, non_blocking=True) if dev.type == 'cuda' else meta
+        if internal:
+            out = ops.empty_nhwc(b, self.c, self.size, self.size, ops.state.act_dtype, dev)
+        else:
+            out = torch.empty((b, self.c, self.size, self.size), dtype=torch.float32, device=dev)
+        call('ttg_u8_crop_normalize', ptr(self.stack), ptr(meta[0]), ptr(meta[1]), ptr(meta[2]), ptr(out), b, self.h,
+             self.w, self.c, self.size, dtype_code(out.dtype), 0 if internal else 1)
+        return out
+
+    def epoch(self, batch_size):
+        """Batches of one epoch (shuffled, drop_last)."""
+        perm = torch.randperm(self.m, generator=self.gen)
+        for s in range(0, self.m - batch_size + 1, batch_size):
+            idx = perm[s:s + batch_size]
+            oy = torch.randint(0, self.h - self.size + 1, (batch_size,), generator=self.gen)
+            ox = torch.randint(0, self.w - self.size + 1, (batch_size,), generator=self.gen)
+            yield self.crop(idx, oy, ox)
+
+
 class Trainer:
     def __init__(self, args, components=()):
         self.args = args
@@ -100,6 +151,10 @@ class Trainer:
         if self.args.data_path == 'synthetic':
             return SyntheticTartanDataset(size)
         if self.args.data_path.endswith('.npz'):
+            if getattr(self.args, 'device_dataset', False):
+                data = np.load(self.args.data_path)
+                key = 'images' if 'images' in data.files else data.files[0]
+                return DeviceImageStack(data[key], size, self.device)
             return NpzImageDataset(self.args.data_path, size)
         raise NotImplementedError('tartangan_b200: data_path must be "synthetic" or an .npz of uint8 images; the '
                                   'image-folder pipeline of the reference is outside the training-step scope')
@@ -107,8 +162,14 @@ class Trainer:
     def train(self, max_steps=None):
         self.build_models()
         self.dataset = self.prepare_dataset()
-        loader = torch.utils.data.DataLoader(self.dataset, batch_size=self.args.batch_size, shuffle=True,
-                                             drop_last=True)
+        if isinstance(self.dataset, DeviceImageStack):
+            class _Epochs:                       # re-iterable like a DataLoader
+                def __iter__(it):
+                    return self.dataset.epoch(self.args.batch_size)
+            loader = _Epochs()
+        else:
+            loader = torch.utils.data.DataLoader(self.dataset, batch_size=self.args.batch_size, shuffle=True,
+                                                 drop_last=True)
         logs = defaultdict(list)
         self._maybe_resume()
         try:
@@ -254,5 +315,7 @@ class Trainer:
         p.add_argument('--num-quantiles', type=int, default=8, help='IQN quantile count (reference: 8)')
         p.add_argument('--cuda-graph', action='store_true',
                        help='run the training step as CUDA graphs (static shapes; z/tau staged from the CPU generator)')
+        p.add_argument('--device-dataset', action='store_true',
+                       help='keep the uint8 .npz image stack in GPU memory; crop + normalise batches with one kernel')
         p.add_argument('--attention', type=type_or_none(str), default=None,
                        help='comma-separated block indices with self-attention (overrides the config)')

@@ -209,3 +209,39 @@ def test_pack_weights_multi_matches_single_pack():
     for i, p in enumerate(params[:-1]):
         for m in (0, 1):
             assert torch.equal(ops._packed(p, m, 'tc'), singles[(i, m)]), (i, m)
+
+
+def test_device_image_stack_matches_host_pipeline(tmp_path):
+    """uint8 stack in HBM, crop + normalise in one kernel == the host pipeline of NpzImageDataset
+    (image_bytes_dataset.py:44-49: crop, ToTensor, Normalize(0.5, 0.5)) bit for bit in fp32; ragged crop origins,
+    the last row / column of the image included; and one trainer epoch over an .npz runs through it."""
+    import numpy as np
+    import tartangan_b200 as tb
+    from tartangan_b200 import ops
+    from tartangan_b200.trainers.trainer import DeviceImageStack
+    rng = np.random.RandomState(0)
+    imgs = rng.randint(0, 256, size=(7, 40, 52, 3), dtype=np.uint8)
+    ds = DeviceImageStack(imgs, 32, 'cuda', seed=3)
+    index = torch.tensor([6, 0, 3, 3, 5]); oy = torch.tensor([8, 0, 3, 8, 1]); ox = torch.tensor([20, 0, 7, 19, 20])
+    got = ds.crop(index, oy, ox)
+    ref = torch.stack([torch.from_numpy(np.ascontiguousarray(imgs[i, y:y + 32, x:x + 32])).permute(2, 0, 1).float() / 127.5 - 1.0
+                       for i, y, x in zip(index.tolist(), oy.tolist(), ox.tolist())])
+    assert got.shape == (5, 3, 32, 32) and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), ref)                            # same IEEE operations as the host pipeline
+    tb.set_precision('bf16')
+    internal = ds.crop(index, oy, ox, internal=True)
+    assert torch.equal(ops.from_internal(internal).cpu(), ref.bfloat16().float()) or \
+        float((ops.from_internal(internal).cpu() - ref).abs().max()) < 8e-3
+    batches = list(ds.epoch(3))
+    assert len(batches) == 2 and all(b.shape == (3, 3, 32, 32) for b in batches)      # drop_last
+    assert all(float(b.min()) >= -1.0 and float(b.max()) <= 1.0 for b in batches)
+    # end to end: the trainer loop over an .npz with --device-dataset
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    np.savez(tmp_path / 'imgs.npz', images=rng.randint(0, 256, size=(9, 36, 36, 3), dtype=np.uint8))
+    torch.manual_seed(0)
+    t = make_trainer(IQNTrainer, config='32', batch_size=4, model_scale=0.25, output=str(tmp_path), device_dataset=True,
+                     quiet_logs=True, epochs=1)
+    t.args.data_path = str(tmp_path / 'imgs.npz')
+    logs = t.train(max_steps=2)
+    assert len(logs['d_loss']) == 2 and all(v == v for v in logs['d_loss'])
