@@ -26,6 +26,16 @@ CASES = {
 }
 
 
+WORLD = int(os.environ.get('WORLD_SIZE', '1'))
+RANK = int(os.environ.get('RANK', '0'))
+
+
+def barrier():
+    if WORLD > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
 def run(name, steps, warmup, fused, graph=True):
     tag, cls, config, batch, kw = CASES[name]
     ops.state.fused_attention = fused
@@ -36,21 +46,26 @@ def run(name, steps, warmup, fused, graph=True):
             if hasattr(m, 'gamma'):
                 m.gamma.fill_(0.5)
     size = t.g.max_size
-    imgs = tartan_batch(1234, batch, size).cuda()
-    torch.manual_seed(1000)
+    imgs = tartan_batch(1234 + RANK, batch, size).cuda()
+    torch.manual_seed(1000 + RANK)
     for _ in range(warmup):
         out = t.train_batch(imgs, as_floats=False)
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         out = t.train_batch(imgs, as_floats=False)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:                                    # max over ranks
+        tm = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        torch.distributed.all_reduce(tm, op=torch.distributed.ReduceOp.MAX)
+        ms = float(tm[0])
     out = {k: (float(v) if v is not None else None) for k, v in out.items()}
     return {'case': name, 'baseline_config': tag, 'config': config, 'size': size, 'batch_per_gpu': batch,
-            'fused_attention': fused, 'cuda_graph': graph, 'ms_per_step': round(ms, 3), 'images_per_sec': round(batch / ms * 1e3, 1),
+            'n_gpus': WORLD, 'global_batch': batch * WORLD,
+            'fused_attention': fused, 'cuda_graph': graph, 'ms_per_step': round(ms, 3), 'images_per_sec': round(batch * WORLD / ms * 1e3, 1),
             'peak_mem_gb': round(torch.cuda.max_memory_allocated() / 2**30, 2), 'losses': out}
 
 
@@ -60,10 +75,18 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--only', default=None)
     ap.add_argument('--eager', action='store_true')
+    ap.add_argument('--fused-only', action='store_true')
     a = ap.parse_args()
+    if WORLD > 1:
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0'))))
     for name in ([a.only] if a.only else list(CASES)):
         has_attn = name != 'iqn64'
-        for fused in ((True, False) if has_attn else (True,)):
+        for fused in ((True, False) if has_attn and not a.fused_only else (True,)):
             torch.cuda.reset_peak_memory_stats()
-            print(json.dumps(run(name, a.steps, a.warmup, fused, not a.eager)), flush=True)
+            line = run(name, a.steps, a.warmup, fused, not a.eager)
+            if RANK == 0:
+                print(json.dumps(line), flush=True)
             torch.cuda.empty_cache()
+    if WORLD > 1:
+        torch.distributed.destroy_process_group()
