@@ -122,6 +122,21 @@ int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n, float slo
 /* conv bias gradient: out[c] = sum over rows of x[M,C] */
 int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream);
 
+/* ---- parameter gradients accumulated in place (torch::autograd::AccumulateGrad, i.e. `param.grad += g` after
+ * loss.backward() in trainers/cnn.py:134,150 and iqn.py:128,139): the `_acc` variants ADD the parameter gradient to the
+ * caller's buffer (a view of the model's flat .grad buffer) instead of returning a fresh tensor that autograd then adds
+ * with one more kernel per parameter.  `accumulate` = 0 gives the plain behaviour of the entry point without suffix. */
+int ttg_conv2d_wgrad_tc_acc(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
+                            int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
+int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
+                       const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
+                       float* gbeta, int accumulate, void* workspace, int dtype, void* stream);
+int ttg_bn_act_bwd2_acc(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
+                        const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                        float* ggamma, int accumulate, void* workspace, int dtype, void* stream);
+int ttg_channel_sum_acc(const void* x, long long M, int C, float* out, int accumulate, void* workspace, int dtype,
+                        void* stream);
+
 /* ---- resampling / glue
  * pool2_sum: nn.AvgPool2d(2) with scale 0.25 (discriminator.py:67); adjoint of upsample2.
  * upsample2: F.interpolate nearest x2 (generator.py:58); adjoint of pool2_sum.

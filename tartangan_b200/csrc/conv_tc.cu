@@ -2046,17 +2046,19 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
 static int g_wgrad_tc_smem[2] = {0, 0};
 
 // packed partial-sum image -> OIHW fp32 (layout 0: gwp[tap][co][ci], 1: gwp[tap][ci][co]; padded sizes CoutP x CinP)
+// acc != 0: added to gw (a view of the flat .grad buffer) instead of overwriting it
 __global__ void ttg_wgrad_unpack_kernel(const float* __restrict__ gwp, float* __restrict__ gw, int Cout, int Cin, int CoutP, int CinP,
-                                        int taps, int layout) {
+                                        int taps, int layout, int acc) {
   const int total = Cout * Cin * taps;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);
-    gw[i] = layout == 0 ? gwp[((long long)tap * CoutP + co) * CinP + ci] : gwp[((long long)tap * CinP + ci) * CoutP + co];
+    const float v = layout == 0 ? gwp[((long long)tap * CoutP + co) * CinP + ci] : gwp[((long long)tap * CinP + ci) * CoutP + co];
+    gw[i] = acc ? gw[i] + v : v;
   }
 }
 static inline int ttg_pad16(int c) { return c <= 8 ? 16 : c; }
 extern "C" size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize) {
-  return sizeof(float) * (size_t)ttg_pad16(Cin) * ttg_pad16(Cout) * ksize * ksize + 16 + 8 * 256 + 16;   // + channel-sum scratch
+  return sizeof(float) * (size_t)ttg_pad16(Cin) * ttg_pad16(Cout) * ksize * ksize + 16 + 8 * 256 + 16;   // + channel-sum scratch (fp64 [C])
 }
 
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
@@ -2065,9 +2067,9 @@ extern "C" int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int
                                    int ksize, int up, void* workspace, void* stream) {
   return ttg_conv2d_wgrad_tc_ex(x, gy, gw, N, H, W, Cin, Cout, Cin, Cout, ksize, up, workspace, stream);
 }
-extern "C" int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream);
+extern "C" int ttg_channel_sum_acc(const void* x, long long M, int C, float* out, int accumulate, void* workspace, int dtype, void* stream);
 static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
-                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
+                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream, int accumulate = 0);
 extern "C" int ttg_conv2d_wgrad_tc_ex(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                       int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
   return wgrad_tc_core(x, gy, gw, nullptr, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream);
@@ -2081,8 +2083,14 @@ extern "C" int ttg_conv2d_wgrad_bias_tc_ex(const void* x, const void* gy, float*
   TTG_REQUIRE(gbias != nullptr, "conv2d_wgrad_bias_tc: gbias is required");
   return wgrad_tc_core(x, gy, gw, gbias, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream);
 }
+// gw += / gbias += variant: the weight (and optional bias) gradient is accumulated into the caller's buffers
+// (views of the flat .grad buffer of the model), which removes autograd's per-parameter add kernels.
+extern "C" int ttg_conv2d_wgrad_tc_acc(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin,
+                                       int Cout, int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
+  return wgrad_tc_core(x, gy, gw, gbias, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream, 1);
+}
 static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
-                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
+                         int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream, int accumulate) {
   cudaStream_t st = (cudaStream_t)stream;
   TTG_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "conv2d_wgrad_tc: workspace must be 16-byte aligned");
   float* gwp = reinterpret_cast<float*>(workspace);
@@ -2141,7 +2149,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
       if (wsplits < 1) wsplits = 1;
       if (wsplits > tiles) wsplits = tiles;
       cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
-      if (gbias) cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)cout_real, st);
+      if (gbias && !accumulate) cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)cout_real, st);
       bool bias_done = false;
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
 #define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, gbias, &bias_done, st)
@@ -2151,11 +2159,11 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
 #undef TTG_WG
       if (rc != TTG_OK) return rc;
       const int total = cout_real * cin_real * taps;
-      ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0);
+      ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0, accumulate);
       TTG_CHECK_LAUNCH("conv2d_wgrad_unpack");
       if (gbias && !bias_done) {
         void* scratch = reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * (size_t)Cout * Cin * taps + 15) & ~(size_t)15);
-        return ttg_channel_sum(gy, (long long)N * H * W, cout_real, gbias, scratch, TTG_BF16, stream);
+        return ttg_channel_sum_acc(gy, (long long)N * H * W, cout_real, gbias, accumulate, scratch, TTG_BF16, stream);
       }
       return TTG_OK;
     }
@@ -2172,7 +2180,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
     g_wgrad_tc_smem[ki] = smem;
   }
-  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+  if (!accumulate) cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
   dim3 grid((unsigned)splits, groups, halves);
   if (ksize == 3)
     conv_wgrad_tc_kernel<3><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);
@@ -2181,7 +2189,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
   TTG_CHECK_LAUNCH("conv2d_wgrad_tc");
   if (gbias) {
     void* scratch = reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * (size_t)Cout * Cin * taps + 15) & ~(size_t)15);
-    return ttg_channel_sum(gy, (long long)N * H * W, cout_real, gbias, scratch, TTG_BF16, stream);
+    return ttg_channel_sum_acc(gy, (long long)N * H * W, cout_real, gbias, accumulate, scratch, TTG_BF16, stream);
   }
   return TTG_OK;
 }

@@ -144,14 +144,27 @@ template <typename T> struct BnActBwdMapOp {
     o[0] = p.c.g[j] * p.c.r[j] * (d - p.db[j] - xh * p.cc[j]);
   }
 };
-__global__ void bn_param_grads_kernel(const double* sums, int C, float* ggamma, float* gbeta) {
+// acc != 0: the parameter gradients are ADDED to ggamma / gbeta (the caller passes views of the flat .grad buffer, so
+// autograd's AccumulateGrad add kernels disappear)
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* ggamma, float* gbeta, int acc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { if (gbeta) gbeta[c] = (float)sums[c]; if (ggamma) ggamma[c] = (float)sums[C + c]; }
+  if (c < C) {
+    if (gbeta) gbeta[c] = (acc ? gbeta[c] : 0.f) + (float)sums[c];
+    if (ggamma) ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)sums[C + c];
+  }
 }
 
+extern "C" int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
+                                  const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
+                                  float* gbeta, int accumulate, void* workspace, int dtype, void* stream);
 extern "C" int ttg_bn_act_bwd(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
                               const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
                               float* gbeta, void* workspace, int dtype, void* stream) {
+  return ttg_bn_act_bwd_acc(x, ga, gx, M, C, mean, invstd, gamma, beta, slope, ggamma, gbeta, 0, workspace, dtype, stream);
+}
+extern "C" int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
+                                  const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
+                                  float* gbeta, int accumulate, void* workspace, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   double* ws = (double*)workspace;
   TTG_DISPATCH(dtype, {
@@ -168,7 +181,7 @@ extern "C" int ttg_bn_act_bwd(const void* x, const void* ga, void* gx, long long
     }
   });
   if (ggamma || gbeta) {
-    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta);
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta, accumulate);
     TTG_CHECK_LAUNCH("bn_param_grads");
   }
   return TTG_OK;
@@ -219,19 +232,27 @@ template <typename T> struct BnActBwd2MapOp {
     o[1] = g * r * r * (xh * p.k[j] - p.e[j] * Pd - p.cc[j] * Pu);
   }
 };
-__global__ void bn_bwd2_gamma_kernel(const double* sums, const float* invstd, long long M, int C, float* ggamma) {
+__global__ void bn_bwd2_gamma_kernel(const double* sums, const float* invstd, long long M, int C, float* ggamma, int acc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     double invM = 1.0 / (double)M;
     double db = sums[c] * invM, cc = sums[C + c] * invM, ub = sums[2 * C + c] * invM, e = sums[3 * C + c] * invM;
     double cov = sums[4 * C + c] * invM - ub * db;
-    ggamma[c] = (float)((double)invstd[c] * (double)M * (cov - cc * e));
+    ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)((double)invstd[c] * (double)M * (cov - cc * e));
   }
 }
 
+extern "C" int ttg_bn_act_bwd2_acc(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                   float slope, float* ggamma, int accumulate, void* workspace, int dtype, void* stream);
 extern "C" int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
                                const float* mean, const float* invstd, const float* gamma, const float* beta,
                                float slope, float* ggamma, void* workspace, int dtype, void* stream) {
+  return ttg_bn_act_bwd2_acc(x, ga, u, g_ga, g_x, M, C, mean, invstd, gamma, beta, slope, ggamma, 0, workspace, dtype, stream);
+}
+extern "C" int ttg_bn_act_bwd2_acc(const void* x, const void* ga, const void* u, void* g_ga, void* g_x, long long M, int C,
+                                   const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                   float slope, float* ggamma, int accumulate, void* workspace, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   double* ws = (double*)workspace;
   TTG_DISPATCH(dtype, {
@@ -247,7 +268,7 @@ extern "C" int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, voi
     if (rc) return rc;
   });
   if (ggamma) {
-    bn_bwd2_gamma_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, invstd, M, C, ggamma);
+    bn_bwd2_gamma_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, invstd, M, C, ggamma, accumulate);
     TTG_CHECK_LAUNCH("bn_bwd2_gamma");
   }
   return TTG_OK;
@@ -285,11 +306,15 @@ template <typename T> struct SumOp : NoParams {
   const T* in[1];
   template <int V> __device__ __forceinline__ void acc(const float* v, int, const P<V>&, float* a) const { a[0] += v[0]; }
 };
-__global__ void d2f_kernel(const double* s, int n, float* o) {
+__global__ void d2f_kernel(const double* s, int n, float* o, int acc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) o[i] = (float)s[i];
+  if (i < n) o[i] = (acc ? o[i] : 0.f) + (float)s[i];
 }
+extern "C" int ttg_channel_sum_acc(const void* x, long long M, int C, float* out, int accumulate, void* workspace, int dtype, void* stream);
 extern "C" int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream) {
+  return ttg_channel_sum_acc(x, M, C, out, 0, workspace, dtype, stream);
+}
+extern "C" int ttg_channel_sum_acc(const void* x, long long M, int C, float* out, int accumulate, void* workspace, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   double* ws = (double*)workspace;
   TTG_DISPATCH(dtype, {
@@ -297,7 +322,7 @@ extern "C" int ttg_channel_sum(const void* x, long long M, int C, float* out, vo
     int rc = launch_chan_reduce<T>("channel_sum", op, M, C, ws, st);
     if (rc) return rc;
   });
-  d2f_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, out);
+  d2f_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, out, accumulate);
   TTG_CHECK_LAUNCH("channel_sum_finalize");
   return TTG_OK;
 }

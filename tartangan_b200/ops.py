@@ -30,6 +30,7 @@ class _State:
     pack_generation = 0            # bumped to invalidate every packed-weight cache (CUDA-graph capture)
     producer_stats = None          # (tensor, float64 sums) left by a producer kernel (conv / residual join) for bn_act
     fused_attention = True         # tcgen05 attention kernels when the shape allows (else bmm / softmax / bmm)
+    direct_grads = False           # inside direct_param_grads(): parameter gradients are added to p.grad by the kernels
 
 
 state = _State()
@@ -53,6 +54,49 @@ class inputs_only_grads:
 
     def __exit__(self, *a):
         state.inputs_only = self.prev
+
+
+class direct_param_grads:
+    """Context for `loss.backward()`: conv / BatchNorm parameter gradients are ADDED to `p.grad` by the producing
+    kernels (ttg_*_acc) and the backward returns None for them, so autograd launches no AccumulateGrad / gradient
+    fan-in add kernel per parameter (~190 launches per training step).  Only leaf parameters whose `.grad` is a
+    pre-attached contiguous fp32 buffer (optim.FlatParams.attach_grads) take this path, and never under
+    `create_graph`.  Not for `torch.autograd.grad(..., params)`: that must not touch `.grad`."""
+
+    def __enter__(self):
+        self.prev, state.direct_grads = state.direct_grads, True
+
+    def __exit__(self, *a):
+        state.direct_grads = self.prev
+
+
+def _direct(p):
+    """The buffer to accumulate p's gradient into, or None when the ordinary autograd path must be used."""
+    if (state.direct_grads and p is not None and not torch.is_grad_enabled() and p.is_leaf and p.requires_grad
+            and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+            and p.grad.shape == p.shape):
+        return p.grad
+    return None
+
+
+def _wgrad_direct(x, gy, w, bias, up, want_b):
+    """gw (and gb) of a tensor-core conv added straight into w.grad (bias.grad).  True if done."""
+    cout, cin, k, _ = w.shape
+    dw = _direct(w)
+    db = _direct(bias) if want_b else None
+    if (dw is None or (want_b and db is None) or up != 0 or cin < 8 or cout < 8 or gy.dtype != torch.bfloat16
+            or x.dtype != torch.bfloat16 or not _tc_ok(x.dtype, cin, cout)):
+        return False
+    x, gy = nhwc(x), nhwc(gy)
+    n, _, h, wd_ = gy.shape
+    ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
+    fused_bias = want_b and cout >= 16
+    call('ttg_conv2d_wgrad_tc_acc', ptr(x), ptr(gy), ptr(dw), ptr(db) if fused_bias else None, n, h, wd_, _pad16(cin),
+         _pad16(cout), cin, cout, k, 0, ptr(ws))
+    if want_b and not fused_bias:
+        ws2 = _ws(_lib.lib.ttg_bn_workspace_bytes(cout), x.device)
+        call('ttg_channel_sum_acc', ptr(gy), n * h * wd_, cout, ptr(db), 1, ptr(ws2), dtype_code(gy.dtype))
+    return True
 
 
 # --------------------------------------------------------------------------- helpers
@@ -267,6 +311,7 @@ class Conv2dFn(Function):
     def forward(ctx, x, w, bias, up, out_dtype, stats=None):
         ctx.save_for_backward(x, w)
         ctx.up, ctx.has_bias, ctx.in_dtype = up, bias is not None, x.dtype
+        ctx.bias = bias            # only its .grad buffer is touched (direct_param_grads)
         return _conv_raw(x, w, bias, 0, up, out_dtype, stats)
 
     @staticmethod
@@ -279,7 +324,9 @@ class Conv2dFn(Function):
             gx = ConvDgradFn.apply(gy, w, ctx.up)
         if not state.inputs_only:
             want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
-            if (want_w and want_b and ctx.up == 0 and gy.dtype == torch.bfloat16 and w.shape[0] >= 16
+            if want_w and _wgrad_direct(x, gy, w, ctx.bias, ctx.up, want_b):
+                pass                                                    # added to w.grad / bias.grad by the kernel
+            elif (want_w and want_b and ctx.up == 0 and gy.dtype == torch.bfloat16 and w.shape[0] >= 16
                     and _tc_ok(x.dtype, w.shape[1], w.shape[0])):
                 gw, gb = ConvWgradBiasFn.apply(x, gy, w.shape[2])      # one pass over gy for both
             else:
@@ -308,7 +355,7 @@ class ConvDgradFn(Function):
         g_gy = g_w = None
         if ctx.needs_input_grad[0]:
             g_gy = Conv2dFn.apply(ggx, w, None, ctx.up, None)
-        if ctx.needs_input_grad[1] and not state.inputs_only:
+        if ctx.needs_input_grad[1] and not state.inputs_only and not _wgrad_direct(ggx, gy, w, None, ctx.up, False):
             g_w = ConvWgradFn.apply(ggx, gy, w.shape[2], ctx.up)
         return g_gy, g_w, None
 
@@ -490,6 +537,16 @@ class BnActFn(Function):
             raise NotImplementedError('tartangan_b200: backward through eval-mode BatchNorm is not on the '
                                       'reference path (D/G are always in train mode) and is not implemented')
         x, gamma, beta, mean, invstd = ctx.saved_tensors
+        dg, db = _direct(gamma), _direct(beta)
+        if (dg is not None and db is not None and not state.inputs_only and ctx.needs_input_grad[1]
+                and ctx.needs_input_grad[2]):
+            x, ga = nhwc(x), nhwc(ga)
+            n, c, h, w = x.shape
+            gx = _empty_like(x)
+            ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), x.device)
+            call('ttg_bn_act_bwd_acc', ptr(x), ptr(ga), ptr(gx), n * h * w, c, ptr(mean), ptr(invstd), ptr(gamma),
+                 ptr(beta), ctx.slope, ptr(dg), ptr(db), 1, ptr(ws), dtype_code(x.dtype))
+            return gx, None, None, None, None, None, None, None, None, None, None, None
         gx, ggamma, gbeta = BnActBwdFn.apply(x, ga, gamma, beta, mean, invstd, ctx.slope)
         if state.inputs_only:
             ggamma = gbeta = None
@@ -525,10 +582,12 @@ class BnActBwdFn(Function):
         n, c, h, w = x.shape
         dev = x.device
         g_ga, g_x = _empty_like(x), _empty_like(x)
-        g_gamma = None if state.inputs_only else torch.empty(c, dtype=torch.float32, device=dev)
+        dg = None if state.inputs_only or not ctx.needs_input_grad[2] else _direct(gamma)
+        g_gamma = None if (state.inputs_only or dg is not None) else torch.empty(c, dtype=torch.float32, device=dev)
         ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
-        call('ttg_bn_act_bwd2', ptr(x), ptr(ga), ptr(u), ptr(g_ga), ptr(g_x), n * h * w, c, ptr(mean), ptr(invstd),
-             ptr(gamma), ptr(beta), ctx.slope, ptr(g_gamma), ptr(ws), dtype_code(x.dtype))
+        call('ttg_bn_act_bwd2_acc', ptr(x), ptr(ga), ptr(u), ptr(g_ga), ptr(g_x), n * h * w, c, ptr(mean), ptr(invstd),
+             ptr(gamma), ptr(beta), ctx.slope, ptr(dg if dg is not None else g_gamma), 1 if dg is not None else 0, ptr(ws),
+             dtype_code(x.dtype))
         return g_x, g_ga, g_gamma, None, None, None, None
 
 

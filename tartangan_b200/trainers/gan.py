@@ -93,12 +93,14 @@ class GanTrainer(Trainer):
         """loss.backward(); in data parallel the loss is scaled by 1/world so the SUMMED gradients are the
         global-batch average, and (eager mode) the exchange is overlapped with the rest of backward."""
         if self.world_size == 1:
-            loss.backward()
+            with ops.direct_param_grads():      # conv / BatchNorm parameter gradients land in the flat .grad buffer
+                loss.backward()
             return
         red = self._reducer(optimizer) if overlap else None
         if red is not None:
             red.begin()
-        loss.backward(torch.full_like(loss, 1.0 / self.world_size))
+        with ops.direct_param_grads():          # (their grad hooks do not fire: finish() launches those buckets)
+            loss.backward(torch.full_like(loss, 1.0 / self.world_size))
         if red is not None:
             red.finish()
 
