@@ -109,6 +109,13 @@ int ttg_bn_eval_stats(const float* running_mean, const float* running_var, float
                       float* invstd, void* stream);
 int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const float* mean, const float* invstd,
                    const float* gamma, const float* beta, float slope, int dtype, void* stream);
+/* statistics finalisation + apply in one launch: sums = {sum x, sum x^2} (fp64 [2C]) from the kernel that produced x
+ * (ttg_conv2d_tc_stats, ttg_add_up2_stats, ...) or NULL (then they are reduced into `workspace` first); writes y,
+ * mean / invstd (for backward) and updates running_mean / running_var / num_batches like ttg_bn_stats. */
+int ttg_bn_act_fwd_stats(const void* x, void* y, long long M, int C, const double* sums, const float* gamma,
+                         const float* beta, float eps, float momentum, float slope, float* mean, float* invstd,
+                         float* running_mean, float* running_var, long long* num_batches, long long count_mult,
+                         void* workspace, int dtype, void* stream);
 int ttg_bn_act_bwd(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
                    const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
                    float* gbeta, void* workspace, int dtype, void* stream);

@@ -144,6 +144,12 @@ __device__ __forceinline__ void cb_producer(const Op& op, uint8_t* ring, uint64_
   }
 }
 
+// Optional per-launch epilogue of a map op: `__device__ void finalize(int C) const`, run by block 0 (all its threads)
+// before the streaming loop - per-channel outputs derived from already reduced sums (parameter gradients, saved
+// BatchNorm statistics) ride along with the apply pass instead of costing one more tiny kernel launch each.
+template <class Op, class = void> struct chan_has_finalize : std::false_type {};
+template <class Op> struct chan_has_finalize<Op, std::void_t<decltype(&Op::finalize)>> : std::true_type {};
+
 template <class Op>
 __global__ void __launch_bounds__(CB_THREADS) chan_map_bulk_kernel(Op op, long long nvec, int C) {
   extern __shared__ __align__(128) uint8_t cb_smem[];
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(CB_THREADS) chan_map_bulk_kernel(Op op, long l
     mbar_fence_init();
   }
   __syncthreads();
+  if constexpr (chan_has_finalize<Op>::value) { if (blockIdx.x == 0) op.finalize(C); }
   const long long nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
   if (warp == 8) { cb_producer(op, ring, full, empty, nvec, nchunks); return; }
   typename Op::template P<8> prm;
@@ -354,6 +361,7 @@ __global__ void __launch_bounds__(256) chan_map_kernel(Op op, long long nvec, in
   long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   typename Op::template P<V> prm;
   const long long last = nvec - 1;
+  if constexpr (chan_has_finalize<Op>::value) { if (blockIdx.x == 0) op.finalize(C); }
   if (invariant && i0 < nvec) op.template load<V>((int)(((reverse ? last - i0 : i0) * V) % C), prm);
   for (; i0 < nvec; i0 += U * stride) {
     float v[U][Op::NIN][V];

@@ -105,6 +105,72 @@ extern "C" int ttg_bn_act_fwd(const void* x, void* y, long long M, int C, const 
   return TTG_OK;
 }
 
+// BatchNorm finalisation folded into the apply pass: every thread derives its channels' (mean, invstd) from the
+// fp64 sums (same arithmetic as bn_finalize_kernel, so results are bit-identical), block 0 also stores them for the
+// backward pass and updates the running statistics.
+template <typename T> struct BnActFwdStatsOp {
+  static constexpr int NIN = 1, NOUT = 1;
+  const T* in[1]; T* out[1];
+  const double* sums; const float *gamma, *beta; float slope, eps, momentum; long long M, count_mult; int C;
+  float *mean, *invstd, *running_mean, *running_var; long long* num_batches;
+  __device__ __forceinline__ void chan(int c, float& mf, float& rf, double& var) const {
+    const double m = sums[c] / (double)M;
+    var = sums[C + c] / (double)M - m * m;
+    if (var < 0) var = 0;
+    mf = (float)m; rf = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  template <int V> struct P { float a[V], b[V]; };     // y = x*a + b
+  template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float mf, rf; double var;
+      chan(c0 + j, mf, rf, var);
+      const float a = rf * gamma[c0 + j]; p.a[j] = a; p.b[j] = beta[c0 + j] - mf * a;
+    }
+  }
+  template <int V> __device__ __forceinline__ void apply(const float* v, int j, const P<V>& p, float* o) const {
+    o[0] = lrelu(v[0] * p.a[j] + p.b[j], slope);
+  }
+  __device__ void finalize(int) const {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mf, rf; double var;
+      chan(c, mf, rf, var);
+      mean[c] = mf; invstd[c] = rf;
+      if (running_mean) {
+        const double Mu = (double)M * (double)count_mult;
+        const double unbiased = Mu > 1 ? var * Mu / (Mu - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mf;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+    if (threadIdx.x == 0 && num_batches) *num_batches += 1;
+  }
+};
+// train-mode BatchNorm + LeakyReLU in (at most) two launches: statistics (skipped when `sums` = {sum x, sum x^2} was
+// already produced by the conv / join kernel that wrote x) and one apply pass that also finalises the statistics.
+extern "C" int ttg_bn_act_fwd_stats(const void* x, void* y, long long M, int C, const double* sums, const float* gamma,
+                                    const float* beta, float eps, float momentum, float slope, float* mean, float* invstd,
+                                    float* running_mean, float* running_var, long long* num_batches, long long count_mult,
+                                    void* workspace, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(M > 0 && C > 0 && count_mult >= 1 && mean && invstd, "bn_act_fwd_stats: bad arguments");
+  TTG_REQUIRE(sums != nullptr || workspace != nullptr, "bn_act_fwd_stats: needs sums or a workspace to reduce them into");
+  TTG_DISPATCH(dtype, {
+    if (sums == nullptr) {
+      StatsOp<T> r; r.in[0] = (const T*)x;
+      int rc = launch_chan_reduce<T>("bn_stats", r, M, C, (double*)workspace, st);
+      if (rc) return rc;
+      sums = (const double*)workspace;
+    }
+    BnActFwdStatsOp<T> op; op.in[0] = (const T*)x; op.out[0] = (T*)y;
+    op.sums = sums; op.gamma = gamma; op.beta = beta; op.slope = slope; op.eps = eps; op.momentum = momentum;
+    op.M = M; op.count_mult = count_mult; op.C = C; op.mean = mean; op.invstd = invstd;
+    op.running_mean = running_mean; op.running_var = running_var; op.num_batches = num_batches;
+    return launch_chan_map<T>("bn_act_fwd_stats", op, M * C, C, st);
+  });
+  return TTG_OK;
+}
+
 // ---------------------------------------------------------------- backward
 // d = ga * lrelu'(y);  gx = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
 // per-channel cache shared by the backward ops: xhat = x*r - mr,  y = g*xhat + b
@@ -132,6 +198,13 @@ template <typename T> struct BnActBwdMapOp {
   static constexpr int NIN = 2, NOUT = 1;
   const T* in[2]; T* out[1];
   const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
+  float *ggamma, *gbeta; int acc;                      // parameter gradients (block 0), added to the buffers when acc
+  __device__ void finalize(int) const {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (gbeta) gbeta[c] = (acc ? gbeta[c] : 0.f) + (float)sums[c];
+      if (ggamma) ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)sums[C + c];
+    }
+  }
   template <int V> struct P { BnChan<V> c; float db[V], cc[V]; };
   template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
     bn_chan_load<V>(c0, p.c, mean, invstd, gamma, beta);
@@ -176,11 +249,12 @@ extern "C" int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long 
       BnActBwdMapOp<T> m; m.in[0] = (const T*)x; m.in[1] = (const T*)ga; m.out[0] = (T*)gx;
       m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
       m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
+      m.ggamma = ggamma; m.gbeta = gbeta; m.acc = accumulate;
       rc = launch_chan_map<T>("bn_act_bwd_apply", m, M * C, C, st);
       if (rc) return rc;
     }
   });
-  if (ggamma || gbeta) {
+  if (!gx && (ggamma || gbeta)) {                       // (with gx the apply pass wrote them)
     bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta, accumulate);
     TTG_CHECK_LAUNCH("bn_param_grads");
   }
@@ -211,6 +285,16 @@ template <typename T> struct BnActBwd2MapOp {
   static constexpr int NIN = 3, NOUT = 2;
   const T* in[3]; T* out[2];   // out: g_ga, g_x
   const float *mean, *invstd, *gamma, *beta; float slope; const double* sums; int C; float invM;
+  float* ggamma; long long M; int acc;
+  __device__ void finalize(int) const {
+    if (!ggamma) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double iM = 1.0 / (double)M;
+      const double db = sums[c] * iM, cc = sums[C + c] * iM, ub = sums[2 * C + c] * iM, e = sums[3 * C + c] * iM;
+      const double cov = sums[4 * C + c] * iM - ub * db;
+      ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)((double)invstd[c] * (double)M * (cov - cc * e));
+    }
+  }
   template <int V> struct P { BnChan<V> c; float db[V], cc[V], ub[V], e[V], k[V]; };   // k = cc*e - cov
   template <int V> __device__ __forceinline__ void load(int c0, P<V>& p) const {
     bn_chan_load<V>(c0, p.c, mean, invstd, gamma, beta);
@@ -264,13 +348,10 @@ extern "C" int ttg_bn_act_bwd2_acc(const void* x, const void* ga, const void* u,
     m.out[0] = (T*)g_ga; m.out[1] = (T*)g_x;
     m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
     m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
+    m.ggamma = ggamma; m.M = M; m.acc = accumulate;
     rc = launch_chan_map<T>("bn_act_bwd2_apply", m, M * C, C, st);
     if (rc) return rc;
   });
-  if (ggamma) {
-    bn_bwd2_gamma_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, invstd, M, C, ggamma, accumulate);
-    TTG_CHECK_LAUNCH("bn_bwd2_gamma");
-  }
   return TTG_OK;
 }
 

@@ -515,18 +515,18 @@ class BnActFn(Function):
         dev = x.device
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         invstd = torch.empty(c, dtype=torch.float32, device=dev)
-        if training and sums is not None:       # statistics already reduced by the producing conv's epilogue
-            call('ttg_bn_finalize', ptr(sums), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
-                 ptr(running_var), ptr(num_batches), count_mult)
-        elif training:
-            ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
-            call('ttg_bn_stats', ptr(x), m, c, eps, momentum, ptr(mean), ptr(invstd), ptr(running_mean),
-                 ptr(running_var), ptr(num_batches), ptr(ws), count_mult, dtype_code(x.dtype))
+        y = _empty_like(x)
+        if training:
+            # statistics (already reduced by the producing conv / join kernel when `sums` is given), their
+            # finalisation and the apply pass: one entry point, one or two launches
+            ws = None if sums is not None else _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
+            call('ttg_bn_act_fwd_stats', ptr(x), ptr(y), m, c, ptr(sums), ptr(gamma), ptr(beta), eps, momentum, slope,
+                 ptr(mean), ptr(invstd), ptr(running_mean), ptr(running_var), ptr(num_batches), count_mult, ptr(ws),
+                 dtype_code(x.dtype))
         else:
             call('ttg_bn_eval_stats', ptr(running_mean), ptr(running_var), eps, c, ptr(mean), ptr(invstd))
-        y = _empty_like(x)
-        call('ttg_bn_act_fwd', ptr(x), ptr(y), m, c, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), slope,
-             dtype_code(x.dtype))
+            call('ttg_bn_act_fwd', ptr(x), ptr(y), m, c, ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), slope,
+                 dtype_code(x.dtype))
         ctx.save_for_backward(x, gamma, beta, mean, invstd)
         ctx.slope, ctx.training = slope, training
         return y

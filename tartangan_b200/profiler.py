@@ -70,6 +70,23 @@ class KernelProfiler:
         elif name == 'ttg_bn_act_fwd':
             key = f'M{args[2]} C{args[3]}'
             nbytes = args[2] * args[3] * 2 * 2
+        elif name == 'ttg_bn_act_fwd_stats':       # (x, y, M, C, sums, ...): statistics pass only when sums is NULL
+            key = f'M{args[2]} C{args[3]}'
+            nbytes = args[2] * args[3] * 2 * (2 if args[4] else 3)
+            name = 'ttg_bn_act_fwd'
+        elif name in ('ttg_conv2d_wgrad_tc_acc', 'ttg_conv2d_wgrad_bias_tc_ex'):   # (x, gy, gw, gbias, N, H, W, CinP, CoutP, cin, cout, k, up, ws)
+            a = list(args[:3]) + list(args[4:7]) + [args[9], args[10], args[11], args[12]]
+            key = _wgrad_key(a)
+            nbytes, flops = _wgrad_bytes_flops(a)
+            name = 'ttg_conv2d_wgrad_tc'
+        elif name == 'ttg_bn_act_bwd_acc':
+            key = f'M{args[3]} C{args[4]}'
+            nbytes = args[3] * args[4] * 2 * 5
+            name = 'ttg_bn_act_bwd'
+        elif name == 'ttg_bn_act_bwd2_acc':
+            key = f'M{args[5]} C{args[6]}'
+            nbytes = args[5] * args[6] * 2 * 8
+            name = 'ttg_bn_act_bwd2'
         elif name == 'ttg_bn_act_bwd':
             key = f'M{args[3]} C{args[4]}'
             nbytes = args[3] * args[4] * 2 * 5          # reduce reads x,ga; apply reads x,ga writes gx
