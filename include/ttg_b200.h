@@ -132,9 +132,11 @@ int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspa
 /* ---- parameter gradients accumulated in place (torch::autograd::AccumulateGrad, i.e. `param.grad += g` after
  * loss.backward() in trainers/cnn.py:134,150 and iqn.py:128,139): the `_acc` variants ADD the parameter gradient to the
  * caller's buffer (a view of the model's flat .grad buffer) instead of returning a fresh tensor that autograd then adds
- * with one more kernel per parameter.  `accumulate` = 0 gives the plain behaviour of the entry point without suffix. */
+ * with one more kernel per parameter.  `accumulate` / `flags`: bit 0 = add to the gradient buffers (0 gives the plain
+ * behaviour of the entry point without suffix; ttg_conv2d_wgrad_tc_acc always accumulates), bit 1 = the caller
+ * guarantees that `workspace` is all zero already (one clear per training step instead of one memset per call). */
 int ttg_conv2d_wgrad_tc_acc(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
-                            int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream);
+                            int cin_real, int cout_real, int ksize, int up, int flags, void* workspace, void* stream);
 int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long long M, int C, const float* mean,
                        const float* invstd, const float* gamma, const float* beta, float slope, float* ggamma,
                        float* gbeta, int accumulate, void* workspace, int dtype, void* stream);

@@ -312,10 +312,10 @@ template <typename T> static inline bool ttg_vec_ok(int C, const void* const* pt
   return true;
 }
 
-// out must hold NACC*C doubles; zeroed here.
+// out must hold NACC*C doubles; zeroed here unless the caller guarantees it already is (out_is_zero).
 template <typename T, class Op>
-static int launch_chan_reduce(const char* name, Op op, long long M, int C, double* out, cudaStream_t st) {
-  cudaMemsetAsync(out, 0, sizeof(double) * Op::NACC * C, st);
+static int launch_chan_reduce(const char* name, Op op, long long M, int C, double* out, cudaStream_t st, bool out_is_zero = false) {
+  if (!out_is_zero) cudaMemsetAsync(out, 0, sizeof(double) * Op::NACC * C, st);
   const void* ptrs[Op::NIN];
   for (int i = 0; i < Op::NIN; ++i) ptrs[i] = op.in[i];
   if constexpr (std::is_same<T, bf16>::value) {

@@ -2085,9 +2085,11 @@ extern "C" int ttg_conv2d_wgrad_bias_tc_ex(const void* x, const void* gy, float*
 }
 // gw += / gbias += variant: the weight (and optional bias) gradient is accumulated into the caller's buffers
 // (views of the flat .grad buffer of the model), which removes autograd's per-parameter add kernels.
+// flags: bit 0 = accumulate (always set by this entry point's callers), bit 1 = the workspace is already all zero
 extern "C" int ttg_conv2d_wgrad_tc_acc(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin,
-                                       int Cout, int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream) {
-  return wgrad_tc_core(x, gy, gw, gbias, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream, 1);
+                                       int Cout, int cin_real, int cout_real, int ksize, int up, int flags, void* workspace,
+                                       void* stream) {
+  return wgrad_tc_core(x, gy, gw, gbias, N, H, W, Cin, Cout, cin_real, cout_real, ksize, up, workspace, stream, flags | 1);
 }
 static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias, int N, int H, int W, int Cin, int Cout,
                          int cin_real, int cout_real, int ksize, int up, void* workspace, void* stream, int accumulate) {
@@ -2148,8 +2150,8 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
       long long wsplits = (long long)ttg_num_sms() * wper_sm / (wgroups * halves);
       if (wsplits < 1) wsplits = 1;
       if (wsplits > tiles) wsplits = tiles;
-      cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
-      if (gbias && !accumulate) cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)cout_real, st);
+      if (!(accumulate & 2)) cudaMemsetAsync(gwp, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+      if (gbias && !(accumulate & 1)) cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)cout_real, st);
       bool bias_done = false;
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
 #define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, gbias, &bias_done, st)
@@ -2159,7 +2161,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
 #undef TTG_WG
       if (rc != TTG_OK) return rc;
       const int total = cout_real * cin_real * taps;
-      ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0, accumulate);
+      ttg_wgrad_unpack_kernel<<<ttg_grid_for(total, 256), 256, 0, st>>>(gwp, gw, cout_real, cin_real, Cout, Cin, taps, swap_ok ? 1 : 0, accumulate & 1);
       TTG_CHECK_LAUNCH("conv2d_wgrad_unpack");
       if (gbias && !bias_done) {
         void* scratch = reinterpret_cast<uint8_t*>(workspace) + ((sizeof(float) * (size_t)Cout * Cin * taps + 15) & ~(size_t)15);
@@ -2180,7 +2182,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
     if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: smem attribute: %s", cudaGetErrorString(e));
     g_wgrad_tc_smem[ki] = smem;
   }
-  if (!accumulate) cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
+  if (!(accumulate & 1)) cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * taps, st);
   dim3 grid((unsigned)splits, groups, halves);
   if (ksize == 3)
     conv_wgrad_tc_kernel<3><<<grid, 128, smem, st>>>((const bf16*)x, (const bf16*)gy, gw, N, H, W, Cin, Cout, up, tpg, cols);

@@ -243,19 +243,19 @@ extern "C" int ttg_bn_act_bwd_acc(const void* x, const void* ga, void* gx, long 
   TTG_DISPATCH(dtype, {
     BnActBwdRedOp<T> r; r.in[0] = (const T*)x; r.in[1] = (const T*)ga;
     r.mean = mean; r.invstd = invstd; r.gamma = gamma; r.beta = beta; r.slope = slope;
-    int rc = launch_chan_reduce<T>("bn_act_bwd_reduce", r, M, C, ws, st);
+    int rc = launch_chan_reduce<T>("bn_act_bwd_reduce", r, M, C, ws, st, (accumulate & 2) != 0);
     if (rc) return rc;
     if (gx) {
       BnActBwdMapOp<T> m; m.in[0] = (const T*)x; m.in[1] = (const T*)ga; m.out[0] = (T*)gx;
       m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
       m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
-      m.ggamma = ggamma; m.gbeta = gbeta; m.acc = accumulate;
+      m.ggamma = ggamma; m.gbeta = gbeta; m.acc = accumulate & 1;
       rc = launch_chan_map<T>("bn_act_bwd_apply", m, M * C, C, st);
       if (rc) return rc;
     }
   });
   if (!gx && (ggamma || gbeta)) {                       // (with gx the apply pass wrote them)
-    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta, accumulate);
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, ggamma, gbeta, accumulate & 1);
     TTG_CHECK_LAUNCH("bn_param_grads");
   }
   return TTG_OK;
@@ -342,13 +342,13 @@ extern "C" int ttg_bn_act_bwd2_acc(const void* x, const void* ga, const void* u,
   TTG_DISPATCH(dtype, {
     BnActBwd2RedOp<T> r; r.in[0] = (const T*)x; r.in[1] = (const T*)ga; r.in[2] = (const T*)u;
     r.mean = mean; r.invstd = invstd; r.gamma = gamma; r.beta = beta; r.slope = slope;
-    int rc = launch_chan_reduce<T>("bn_act_bwd2_reduce", r, M, C, ws, st);
+    int rc = launch_chan_reduce<T>("bn_act_bwd2_reduce", r, M, C, ws, st, (accumulate & 2) != 0);
     if (rc) return rc;
     BnActBwd2MapOp<T> m; m.in[0] = (const T*)x; m.in[1] = (const T*)ga; m.in[2] = (const T*)u;
     m.out[0] = (T*)g_ga; m.out[1] = (T*)g_x;
     m.mean = mean; m.invstd = invstd; m.gamma = gamma; m.beta = beta; m.slope = slope;
     m.sums = ws; m.C = C; m.invM = 1.f / (float)M;
-    m.ggamma = ggamma; m.M = M; m.acc = accumulate;
+    m.ggamma = ggamma; m.M = M; m.acc = accumulate & 1;
     rc = launch_chan_map<T>("bn_act_bwd2_apply", m, M * C, C, st);
     if (rc) return rc;
   });
@@ -400,10 +400,10 @@ extern "C" int ttg_channel_sum_acc(const void* x, long long M, int C, float* out
   double* ws = (double*)workspace;
   TTG_DISPATCH(dtype, {
     SumOp<T> op; op.in[0] = (const T*)x;
-    int rc = launch_chan_reduce<T>("channel_sum", op, M, C, ws, st);
+    int rc = launch_chan_reduce<T>("channel_sum", op, M, C, ws, st, (accumulate & 2) != 0);
     if (rc) return rc;
   });
-  d2f_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, out, accumulate);
+  d2f_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, out, accumulate & 1);
   TTG_CHECK_LAUNCH("channel_sum_finalize");
   return TTG_OK;
 }

@@ -31,6 +31,7 @@ class _State:
     producer_stats = None          # (tensor, float64 sums) left by a producer kernel (conv / residual join) for bn_act
     fused_attention = True         # tcgen05 attention kernels when the shape allows (else bmm / softmax / bmm)
     direct_grads = False           # inside direct_param_grads(): parameter gradients are added to p.grad by the kernels
+    arena = None                   # ZeroArena of the running trainer (pre-zeroed workspaces), or None
 
 
 state = _State()
@@ -54,6 +55,50 @@ class inputs_only_grads:
 
     def __exit__(self, *a):
         state.inputs_only = self.prev
+
+
+class ZeroArena:
+    """One pre-zeroed device buffer that hands out the zero-initialised workspaces of a training step (partial-sum
+    images of the wgrad kernels, fp64 reduction slots of the BatchNorm backward passes).  The kernels are told that
+    their workspace is already clear (flag bit 1 of the ttg_*_acc entry points), so the ~120 per-call memsets of a
+    step become ONE clear of the used prefix at `reset()` (start of the D and of the G half-step).  Slices are
+    bump-allocated, 256-byte aligned, never reused within a period; a request that does not fit returns None and
+    the caller falls back to an ordinary workspace + memset."""
+
+    def __init__(self, device, nbytes=128 << 20):
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.offset = 0            # bump pointer of the current period
+        self.dirty = 0             # prefix that may hold non-zero data (high-water mark since the buffer was created)
+        self.clean_from = 0        # takes below this offset are guaranteed zero in the current period
+
+    def reset(self):
+        self.dirty = max(self.dirty, self.offset)
+        if self.dirty:
+            self.buf[:self.dirty].zero_()
+        self.offset = 0
+        self.clean_from = self.dirty
+
+    def take(self, nbytes):
+        start = (self.offset + 255) & ~255
+        if start + nbytes > self.buf.numel():
+            return None
+        self.offset = start + nbytes
+        out = self.buf[start:start + nbytes]
+        # beyond the prefix cleared by reset() the buffer has never been written (torch.zeros at creation), unless an
+        # earlier period reached further than the last reset knew: then clear explicitly
+        if self.offset > self.clean_from and start < self.dirty:
+            out.zero_()
+        return out
+
+
+def _ws_zero(nbytes, device):
+    """(workspace, flag): a zeroed arena slice and 2 (= 'workspace is already zero'), or an ordinary one and 0."""
+    arena = state.arena
+    if arena is not None and arena.buf.device == torch.device(device):
+        t = arena.take(nbytes)
+        if t is not None:
+            return t, 2
+    return _ws(nbytes, device), 0
 
 
 class direct_param_grads:
@@ -89,13 +134,13 @@ def _wgrad_direct(x, gy, w, bias, up, want_b):
         return False
     x, gy = nhwc(x), nhwc(gy)
     n, _, h, wd_ = gy.shape
-    ws = _ws(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
+    ws, z = _ws_zero(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
     fused_bias = want_b and cout >= 16
     call('ttg_conv2d_wgrad_tc_acc', ptr(x), ptr(gy), ptr(dw), ptr(db) if fused_bias else None, n, h, wd_, _pad16(cin),
-         _pad16(cout), cin, cout, k, 0, ptr(ws))
+         _pad16(cout), cin, cout, k, 0, 1 | z, ptr(ws))
     if want_b and not fused_bias:
-        ws2 = _ws(_lib.lib.ttg_bn_workspace_bytes(cout), x.device)
-        call('ttg_channel_sum_acc', ptr(gy), n * h * wd_, cout, ptr(db), 1, ptr(ws2), dtype_code(gy.dtype))
+        ws2, z2 = _ws_zero(_lib.lib.ttg_bn_workspace_bytes(cout), x.device)
+        call('ttg_channel_sum_acc', ptr(gy), n * h * wd_, cout, ptr(db), 1 | z2, ptr(ws2), dtype_code(gy.dtype))
     return True
 
 
@@ -543,9 +588,9 @@ class BnActFn(Function):
             x, ga = nhwc(x), nhwc(ga)
             n, c, h, w = x.shape
             gx = _empty_like(x)
-            ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), x.device)
+            ws, z = _ws_zero(_lib.lib.ttg_bn_workspace_bytes(c), x.device)
             call('ttg_bn_act_bwd_acc', ptr(x), ptr(ga), ptr(gx), n * h * w, c, ptr(mean), ptr(invstd), ptr(gamma),
-                 ptr(beta), ctx.slope, ptr(dg), ptr(db), 1, ptr(ws), dtype_code(x.dtype))
+                 ptr(beta), ctx.slope, ptr(dg), ptr(db), 1 | z, ptr(ws), dtype_code(x.dtype))
             return gx, None, None, None, None, None, None, None, None, None, None, None
         gx, ggamma, gbeta = BnActBwdFn.apply(x, ga, gamma, beta, mean, invstd, ctx.slope)
         if state.inputs_only:
@@ -584,10 +629,10 @@ class BnActBwdFn(Function):
         g_ga, g_x = _empty_like(x), _empty_like(x)
         dg = None if state.inputs_only or not ctx.needs_input_grad[2] else _direct(gamma)
         g_gamma = None if (state.inputs_only or dg is not None) else torch.empty(c, dtype=torch.float32, device=dev)
-        ws = _ws(_lib.lib.ttg_bn_workspace_bytes(c), dev)
+        ws, z = _ws_zero(_lib.lib.ttg_bn_workspace_bytes(c), dev)
         call('ttg_bn_act_bwd2_acc', ptr(x), ptr(ga), ptr(u), ptr(g_ga), ptr(g_x), n * h * w, c, ptr(mean), ptr(invstd),
-             ptr(gamma), ptr(beta), ctx.slope, ptr(dg if dg is not None else g_gamma), 1 if dg is not None else 0, ptr(ws),
-             dtype_code(x.dtype))
+             ptr(gamma), ptr(beta), ctx.slope, ptr(dg if dg is not None else g_gamma), (1 if dg is not None else 0) | z,
+             ptr(ws), dtype_code(x.dtype))
         return g_x, g_ga, g_gamma, None, None, None, None
 
 

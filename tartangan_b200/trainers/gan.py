@@ -89,6 +89,14 @@ class GanTrainer(Trainer):
             optimizer._ttg_reducer = red
         return red
 
+    def _reset_arena(self):
+        """Start a new period of the pre-zeroed workspace arena (ops.ZeroArena): one clear per half-step."""
+        arena = getattr(self, '_arena', None)
+        if arena is None:
+            arena = self._arena = ops.ZeroArena(self.device)
+        ops.state.arena = arena        # (the arena of the trainer that is stepping)
+        arena.reset()
+
     def _backward(self, loss, optimizer, overlap=True):
         """loss.backward(); in data parallel the loss is scaled by 1/world so the SUMMED gradients are the
         global-batch average, and (eager mode) the exchange is overlapped with the rest of backward."""
@@ -112,6 +120,7 @@ class GanTrainer(Trainer):
         toggle_grad(self.g, False)
         toggle_grad(self.d, True)
         self.optimizer_d.zero_grad()
+        self._reset_arena()
         if fake is None:
             with torch.no_grad():
                 fake = self.sample_g(len(imgs))
@@ -133,6 +142,7 @@ class GanTrainer(Trainer):
         toggle_grad(self.g, True)
         toggle_grad(self.d, False)
         self.optimizer_g.zero_grad()
+        self._reset_arena()
         fake = self.sample_g(len(imgs))
         g_loss = self.g_loss(fake)
         self._backward(g_loss, self.optimizer_g, overlap)
