@@ -20,6 +20,10 @@ from . import _lib
 from ._lib import call, ptr, dtype_code
 
 SLOPE = 0.2
+# development switches (A/B runs): TTG_NO_DIRECT=1 keeps autograd's AccumulateGrad path, TTG_NO_ARENA=1 the per-call memsets
+import os as _os
+_NO_DIRECT = _os.environ.get('TTG_NO_DIRECT', '0') == '1'
+_NO_ARENA = _os.environ.get('TTG_NO_ARENA', '0') == '1'
 
 
 class _State:
@@ -109,7 +113,7 @@ class direct_param_grads:
     `create_graph`.  Not for `torch.autograd.grad(..., params)`: that must not touch `.grad`."""
 
     def __enter__(self):
-        self.prev, state.direct_grads = state.direct_grads, True
+        self.prev, state.direct_grads = state.direct_grads, not _NO_DIRECT
 
     def __exit__(self, *a):
         state.direct_grads = self.prev

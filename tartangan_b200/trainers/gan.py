@@ -91,6 +91,8 @@ class GanTrainer(Trainer):
 
     def _reset_arena(self):
         """Start a new period of the pre-zeroed workspace arena (ops.ZeroArena): one clear per half-step."""
+        if ops._NO_ARENA:
+            return
         arena = getattr(self, '_arena', None)
         if arena is None:
             arena = self._arena = ops.ZeroArena(self.device)

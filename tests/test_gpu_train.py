@@ -115,9 +115,11 @@ def test_vs_oracle_reference_widths(kind):
     for k, v in orc.d.items():
         if v.is_floating_point() and not k.endswith('.bias') and 'running' not in k:
             # the fp32 wgrad kernel sums with float atomics (run-to-run order), so which near-zero gradients flip
-            # their Adam sign varies between runs: observed 1-3 % of a tensor's elements, bounded at 5 % here; the
-            # losses above and the step-0 gradients of test_golden_fp32 are the tight checks
-            assert _params_close(t.d.state_dict()[k], v, lr=8e-4, rare=0.05), k
+            # their Adam sign in step 1 varies between runs and step 2 amplifies it: tools/flaky_probe.py over 46
+            # repeats (same at the start of round 1's third session): worst tensor 0.65 % of its elements in two
+            # thirds of the runs, 3.8-4.0 % in one third (bimodal), never more; bounded at 8 % here.  The losses
+            # above and the step-0 gradients of test_golden_fp32 are the tight checks.
+            assert _params_close(t.d.state_dict()[k], v, lr=8e-4, rare=0.08), k
 
 
 @pytest.mark.parametrize('kind', ['cnn', 'iqn'])

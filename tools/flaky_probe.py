@@ -1,0 +1,25 @@
+import sys, torch
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import test_gpu_train as T
+from oracle import tartan_oracle as O
+from tartangan_b200.models.pluggan import GAN_CONFIGS
+cfg = GAN_CONFIGS['32']
+for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
+    torch.manual_seed(0)
+    t = T._trainer('cnn', cfg, 8, 'fp32')
+    spec = O.Spec(4, cfg.latent_dims, 3, tuple(cfg.blocks), ())
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer('cnn', spec, cpu(t.g), cpu(t.target_g), cpu(t.d), 8)
+    for s in range(2):
+        imgs = O.tartan_batch(50 + s, 8, 32)
+        torch.manual_seed(300 + s); orc.train_batch(imgs)
+        torch.manual_seed(300 + s); t.train_batch(imgs)
+    worst = (0, '')
+    for k, v in orc.d.items():
+        if v.is_floating_point() and not k.endswith('.bias') and 'running' not in k:
+            a, b = t.d.state_dict()[k].detach().float().cpu(), v.float()
+            diff = (a - b).abs()
+            tight = diff <= 1e-4 * float(b.abs().max().clamp_min(1e-6)) + 0.05 * 8e-4
+            f = float((~tight).float().mean())
+            if f > worst[0]: worst = (f, k, float(diff.max()), a.numel())
+    print(rep, worst, flush=True)
