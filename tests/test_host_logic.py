@@ -140,3 +140,43 @@ def test_bench_reference_arm_prints_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['unit'] == 'images/sec' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
+
+
+def test_zero_arena_invariants():
+    """ops.ZeroArena (pre-zeroed workspaces of a half-step): every slice handed out is all zero, slices never
+    overlap within a period, a reset clears whatever earlier periods dirtied (also when a later period is shorter
+    than an earlier one), and a request that does not fit yields None (the caller then memsets an ordinary buffer)."""
+    from tartangan_b200 import ops
+    a = ops.ZeroArena('cpu', nbytes=4096)
+    seen = []
+    for period, sizes in enumerate([(100, 700, 8, 1024), (16, 16), (2000, 1000), (5000,), (64,)]):
+        a.reset()
+        spans = []
+        for n in sizes:
+            t = a.take(n)
+            if n > 4096:
+                assert t is None
+                continue
+            assert t is not None and t.numel() == n and int(t.abs().sum()) == 0, (period, n)
+            lo = t.data_ptr() - a.buf.data_ptr()
+            assert lo % 256 == 0
+            assert all(lo >= hi2 or lo + n <= lo2 for lo2, hi2 in spans)
+            spans.append((lo, lo + n))
+            t.fill_(255)                    # the kernels leave their partial sums behind
+        seen.append(spans)
+    # without a reset the bump pointer keeps going: still zero, still disjoint from the current period's slices
+    t = a.take(32)
+    assert t is not None and int(t.abs().sum()) == 0
+    assert a.take(4096) is None
+
+
+def test_fused_attention_shape_support():
+    """ttg_attn_supported: the attention shapes of BASELINE configs 4 and 5 are covered, tiny test shapes and channel
+    counts outside C = 64 / 128 are not (they take the bmm / softmax / bmm path, never a silent CPU fallback)."""
+    from tartangan_b200 import _lib
+    ok = _lib.lib.ttg_attn_supported
+    for nq, nk, dk, dv in [(4096, 1024, 8, 32), (1024, 256, 8, 32), (4096, 1024, 16, 64), (1024, 256, 16, 64)]:
+        assert ok(nq, nk, dk, dv) == 1
+    for nq, nk, dk, dv in [(64, 16, 2, 8), (4096, 1024, 32, 128), (1000, 256, 8, 32), (1024, 192, 8, 32), (1024, 64, 8, 32)]:
+        assert ok(nq, nk, dk, dv) == 0
+    assert _lib.lib.ttg_attn_bwd_workspace_bytes(2, 1024, 8) == (2 * 1024 * 8 + 2 * 2 * 1024) * 4
