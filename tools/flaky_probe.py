@@ -1,3 +1,6 @@
+"""Run-to-run spread of tests/test_gpu_train.py::test_vs_oracle_reference_widths[cnn]: repeats the two fp32 train steps
+and prints, per repeat, the D tensor with the largest fraction of elements outside the tight bound (Adam sign flips
+caused by the float-atomic summation order of the fp32 wgrad kernel).  python tools/flaky_probe.py [repeats]"""
 import sys, torch
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import test_gpu_train as T
