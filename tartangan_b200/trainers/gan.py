@@ -109,7 +109,7 @@ class GanTrainer(Trainer):
         red = self._reducer(optimizer) if overlap else None
         if red is not None:
             red.begin()
-        with ops.direct_param_grads():          # (their grad hooks do not fire: finish() launches those buckets)
+        with ops.direct_param_grads():          # (the grad hooks still fire: AccumulateGrad runs with an undefined grad)
             loss.backward(torch.full_like(loss, 1.0 / self.world_size))
         if red is not None:
             red.finish()

@@ -133,6 +133,67 @@ def test_data_parallel_gloo_world2(tmp_path):
     assert torch.allclose(got, flat.grad, atol=1e-6)
 
 
+class _DirectLinearFn(torch.autograd.Function):
+    """y = x w^T whose backward ADDS the weight gradient to w.grad and returns None for it: the CPU twin of
+    ops.direct_param_grads (ttg_conv2d_wgrad_tc_acc ...).  autograd still runs w's AccumulateGrad node (with an
+    undefined gradient: no add kernel), so the post-accumulate-grad hook fires once every contribution is in."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return x @ w.t()
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        w.grad.add_(gy.t() @ x)
+        return gy @ w, None
+
+
+def _dp_worker_direct(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tartangan_b200.optim import FlatParams
+    from tartangan_b200.parallel import BucketedAllReduce, shard_batch
+    torch.manual_seed(0)
+    ws = [torch.nn.Parameter(torch.randn(6, 6) * 0.3) for _ in range(4)]
+    flat = FlatParams(ws)
+    red = BucketedAllReduce(flat.params, flat.offsets, flat.grad, num_buckets=2)
+    torch.manual_seed(7)
+    x = torch.randn(8, 6)[shard_batch(8, world, rank)]
+    flat.attach_grads()
+    red.begin()
+    h = x
+    for i, w in enumerate(ws):            # parameters 1 and 2 take the in-place path
+        h = torch.tanh(_DirectLinearFn.apply(h, w) if i in (1, 2) else h @ w.t())
+    loss = h.pow(2).mean()
+    loss.backward(torch.full_like(loss, 1.0 / world))
+    assert all(p == 0 for p in red.pending)         # every hook fired: the buckets were launched during backward
+    red.finish()
+    if rank == 0:
+        torch.save(flat.grad.clone(), out)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_with_in_place_parameter_gradients(tmp_path):
+    """Data parallel + ops.direct_param_grads: parameters whose gradient is added to .grad by the producing kernel
+    (backward returns None) still fire their bucket hooks after the last contribution, so the exchange keeps
+    overlapping backward and yields the full-batch gradient (gloo, world 2)."""
+    out = str(tmp_path / 'grad.pt')
+    port = 29500 + (os.getpid() + 17) % 1000
+    mp.spawn(_dp_worker_direct, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(0)
+    ws = [torch.nn.Parameter(torch.randn(6, 6) * 0.3) for _ in range(4)]
+    torch.manual_seed(7)
+    h = torch.randn(8, 6)
+    for w in ws:
+        h = torch.tanh(h @ w.t())
+    h.pow(2).mean().backward()
+    ref = torch.cat([w.grad.reshape(-1) for w in ws])
+    assert got.numel() == ref.numel() and torch.allclose(got, ref, atol=1e-6)
+
+
 def test_bench_reference_arm_prints_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
                         '--warmup', '1'], capture_output=True, text=True, timeout=600)
