@@ -37,9 +37,11 @@ def _noise_grad(g, net, name):
     return float(ref.abs().max()) < max(2e-3 * scale, 5e-5)
 
 
-def _params_close(a, b, lr, rare=0.02):
+def _params_close(a, b, lr, rare=0.05):
     """Adam with beta1=0 moves every element by ~lr*sign(g) per step, so an element whose gradient
-    is rounding noise may differ by 2*lr; require that to be rare and everything else tight."""
+    is rounding noise may differ by 2*lr; require that to be rare and everything else tight.
+    `rare`: the fp32 wgrad kernel sums with float atomics, so WHICH near-zero gradients flip varies from run to
+    run (tools/flaky_probe.py: usually < 1 % of a tensor, up to 4 % in a third of the runs of the widest test)."""
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     diff = (a - b).abs()
     tight = diff <= 1e-4 * float(b.abs().max().clamp_min(1e-6)) + 0.05 * lr
