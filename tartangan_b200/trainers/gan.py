@@ -2,6 +2,7 @@
 D-step / G-step / EMA schedule of reference trainers/cnn.py:29-165 and trainers/iqn.py:30-156.
 """
 import functools
+import os
 
 import torch
 from torch import nn
@@ -15,6 +16,8 @@ from ..models.pluggan import GAN_CONFIGS, Generator
 from ..optim import FlatParams, FusedAdam
 from .trainer import Trainer
 from .utils import toggle_grad
+
+_EARLY_GEN = os.environ.get('TTG_EARLY_GEN', '0') == '1'      # development switch, see _stage_inputs
 
 
 class GanTrainer(Trainer):
@@ -200,13 +203,19 @@ class GanTrainer(Trainer):
         st['ti'] += 1
         return t
 
-    def _stage_inputs(self, imgs):
+    def _stage_inputs(self, imgs, part=None):
         """Draw z / tau from the CPU generator in the reference's order (trainer.py:153-156, iqn.py:105-108:
         z, tau, tau, z, tau) into pinned buffers and copy them, with the images, into the static device
-        buffers the graphs read."""
+        buffers the graphs read.  part: None = everything; 'first' = z0 and the image copy only, 'rest' = the
+        remaining draws (TTG_EARLY_GEN=1: the generator-sample graph, which reads only z0, is launched between
+        the two parts so that the other CPU draws overlap it; same draw order, off by default until measured)."""
         st = self._st
         b, nq = self.args.batch_size, (self.d.to_output.iqn.num_quantiles if st['tau'] else 0)
         order = ['z0'] + (['t0', 't1'] if st['tau'] else []) + ['z1'] + (['t2'] if st['tau'] else [])
+        if part == 'first':
+            order = order[:1]
+        elif part == 'rest':
+            order = order[1:]
         for key in order:
             i = int(key[1])
             if key[0] == 'z':
@@ -215,6 +224,8 @@ class GanTrainer(Trainer):
             else:
                 torch.rand(b * nq, 1, out=st['tau_pin'][i])
                 st['tau'][i].copy_(st['tau_pin'][i], non_blocking=True)
+        if part == 'rest':
+            return                                        # the images went with the first part
         cs = getattr(self, '_copy_stream', None)
         if cs is None:
             st['imgs'].copy_(imgs, non_blocking=True)
@@ -311,14 +322,20 @@ class GanTrainer(Trainer):
         # the capture pass itself executed nothing: restore nothing, the first replay is step 1
 
     def _train_batch_graphed(self, imgs):
+        early = False
         if getattr(self, '_segments', None) is None:
             self._capture(imgs)
+        elif _EARLY_GEN:
+            self._stage_inputs(imgs, 'first')
+            early = True
         else:
             self._stage_inputs(imgs)
         from .. import _lib
         _lib.Counters.kernels += self._graph_kernels
-        for graph, exchange in self._segments:
+        for si, (graph, exchange) in enumerate(self._segments):
             graph.replay()
+            if early and si == 0:
+                self._stage_inputs(imgs, 'rest')          # CPU draws of tau / z1 while the generator sample runs
             if isinstance(exchange, str):         # 'imgs': the next graph reads the image batch
                 if getattr(self, '_copy_stream', None) is not None:
                     torch.cuda.current_stream().wait_event(self._imgs_ready)

@@ -14,3 +14,4 @@ python tools/bench_configs.py --steps 10 --warmup 4 > gpurun_out/bench_configs.l
 # 8 GPUs: python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/bench_configs.py --fused-only
 # run-to-run spread of the fp32 oracle-width test: python tools/flaky_probe.py 16
 # A/B of the launch-count changes: TTG_NO_DIRECT=1 / TTG_NO_ARENA=1 python bench.py --no-cpu-baseline
+# e2e with the CPU draws overlapping the generator-sample graph (unmeasured, off by default): TTG_EARLY_GEN=1 python bench.py --no-cpu-baseline
