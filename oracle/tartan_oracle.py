@@ -86,8 +86,19 @@ def _act(x):
     return F.leaky_relu(x, SLOPE)
 
 
+# Optional activation trace for the per-layer parity tests: set ``TRACE`` to a dict and every conv /
+# residual-block output of the next forward passes is recorded under its state-dict key (detached).
+TRACE = None
+
+
+def _trace(key, out):
+    if TRACE is not None:
+        TRACE[key] = out.detach().clone()
+    return out
+
+
 def _conv(sd, key, x, pad):
-    return F.conv2d(x, sd[key + '.weight'], sd.get(key + '.bias'), padding=pad)
+    return _trace(key, F.conv2d(x, sd[key + '.weight'], sd.get(key + '.bias'), padding=pad))
 
 
 def _attention(sd, key, x):
@@ -122,7 +133,7 @@ def _g_block(sd, key, x, first, norm):
     h = _residual_convs(sd, key, x, first, norm)
     if key + '.project_input.0.weight' in sd:
         x = _conv(sd, key + '.project_input.0', x, 0)
-    return x + h
+    return _trace(key, x + h)
 
 
 def _d_block(sd, key, x, first, norm):
@@ -132,7 +143,7 @@ def _d_block(sd, key, x, first, norm):
     x = F.interpolate(x, scale_factor=0.5, mode='bilinear', align_corners=True)
     if key + '.project_input.0.weight' in sd:
         x = _conv(sd, key + '.project_input.0', x, 0)
-    return x + h
+    return _trace(key, x + h)
 
 
 # --------------------------------------------------------------------------

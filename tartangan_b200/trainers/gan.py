@@ -216,14 +216,27 @@ class GanTrainer(Trainer):
             order = order[:1]
         elif part == 'rest':
             order = order[1:]
+        # The pinned staging buffers are double-buffered: the host may run ahead of the GPU (as_floats=False), and
+        # redrawing into a buffer whose asynchronous copy of the PREVIOUS step is still in flight would tear that
+        # step's draws.  Slot k is reused only after the copies issued from it two steps ago have completed.
+        if part != 'rest':
+            st['slot'] ^= 1
+            ev = st['pin_done'][st['slot']]
+            if ev is not None:
+                ev.synchronize()
+        slot = st['slot']
         for key in order:
             i = int(key[1])
             if key[0] == 'z':
-                torch.randn(b, self.gan_config.latent_dims, out=st['z_pin'][i])
-                st['z'][i].copy_(st['z_pin'][i], non_blocking=True)
+                torch.randn(b, self.gan_config.latent_dims, out=st['z_pin'][slot][i])
+                st['z'][i].copy_(st['z_pin'][slot][i], non_blocking=True)
             else:
-                torch.rand(b * nq, 1, out=st['tau_pin'][i])
-                st['tau'][i].copy_(st['tau_pin'][i], non_blocking=True)
+                torch.rand(b * nq, 1, out=st['tau_pin'][slot][i])
+                st['tau'][i].copy_(st['tau_pin'][slot][i], non_blocking=True)
+        if part != 'first':
+            ev = st['pin_done'][slot] or torch.cuda.Event()
+            ev.record()
+            st['pin_done'][slot] = ev
         if part == 'rest':
             return                                        # the images went with the first part
         cs = getattr(self, '_copy_stream', None)
@@ -244,9 +257,10 @@ class GanTrainer(Trainer):
         self._st = st = dict(
             imgs=torch.empty((b,) + tuple(imgs.shape[1:]), dtype=torch.float32, device=dev),
             z=[torch.empty(b, self.gan_config.latent_dims, device=dev) for _ in range(2)],
-            z_pin=[torch.empty(b, self.gan_config.latent_dims).pin_memory() for _ in range(2)],
+            z_pin=[[torch.empty(b, self.gan_config.latent_dims).pin_memory() for _ in range(2)] for _ in range(2)],
             tau=[torch.empty(b * nq, 1, device=dev) for _ in range(nt)],
-            tau_pin=[torch.empty(b * nq, 1).pin_memory() for _ in range(nt)], zi=0, ti=0, active=False)
+            tau_pin=[[torch.empty(b * nq, 1).pin_memory() for _ in range(nt)] for _ in range(2)],
+            slot=0, pin_done=[None, None], zi=0, ti=0, active=False)
         # warm-up (eager, on a side stream as torch.cuda.graph requires): sets lazy kernel attributes, flattens
         # the parameter buffers, fills the packed-weight caches.  RNG state is restored afterwards so that the
         # first graphed step consumes the same draws an eager first step would have.
@@ -341,8 +355,19 @@ class GanTrainer(Trainer):
                     torch.cuda.current_stream().wait_event(self._imgs_ready)
             elif exchange is not None:
                 torch.distributed.all_reduce(exchange)
+        # the replays changed every parameter behind Python's back (Adam, EMA of target_g): invalidate the per-tensor
+        # packed-weight caches so that the next EAGER use of g / d / target_g (sampling, an eager step) repacks
+        ops.state.pack_generation += 1
         o = self._graph_out
         return o['d_loss'], o['gp'], o['g_loss']
+
+    def parameters_changed(self):
+        """Call after parameters were modified outside the optimiser (load_state_dict, manual edits): drops every
+        packed-weight cache and refreshes the shared packed buffers the captured graphs read."""
+        ops.state.pack_generation += 1
+        for opt in (self.optimizer_d, self.optimizer_g):
+            if getattr(opt, 'flat', None) is not None:
+                opt.repack()
 
     def _flat_target(self):
         if self._target_flat is None or not self._target_flat.intact():

@@ -132,8 +132,11 @@ class Trainer:
         self.args = args
         self.run_id = args.run_id if getattr(args, 'run_id', None) is not None else self._generate_run_id()
         os.makedirs(self.output_root, exist_ok=True)
+        # one argument per line, so that `@{output}/{run_id}/config.args` feeds the same command line back through
+        # fromfile_prefix_chars='@' (the contract of the reference's utils/cli.py:6-22 save_cli_arguments)
+        argv = getattr(args, '_argv', None)
         with open(f'{self.output_root}/config.args', 'w') as f:
-            json.dump({k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool, type(None)))}, f)
+            f.write('\n'.join(argv if argv is not None else self._args_as_argv(args)) + '\n')
         self.components = list(components)
         self.steps = 0
         self.epoch = 1
@@ -178,7 +181,10 @@ class Trainer:
                     metrics = self.train_batch(images)
                     for name, value in metrics.items():
                         logs[name].append(value)
-                    if self.steps and self.steps % self.args.checkpoint_freq == 0:
+                    # (a run resumed from step N must not immediately overwrite checkpoints/N with weights that are one
+                    # step further on: the reference's `_loaded_from` guard, model_checkpoint.py:23-27)
+                    if (self.steps and self.steps % self.args.checkpoint_freq == 0
+                            and self.steps != getattr(self, '_loaded_from', None)):
                         self.save_checkpoint()
                     if not self.args.quiet_logs or self.steps % self.args.log_iters == 0:
                         print(f'step {self.steps} ' + ' '.join(f'{k}={v:.4f}' for k, v in metrics.items()), flush=True)
@@ -241,6 +247,9 @@ class Trainer:
             getattr(self, attr).load_state_dict(sd)
         with open(f'{self.checkpoint_root}/trainer.json') as f:
             self.set_state(json.load(f))
+        self._loaded_from = self.steps
+        if hasattr(self, 'parameters_changed'):
+            self.parameters_changed()
 
     def _maybe_resume(self):
         if getattr(self.args, 'resume_training_step', None):
@@ -270,11 +279,33 @@ class Trainer:
     def get_component_classes(cls, args):
         return []
 
+    @staticmethod
+    def _args_as_argv(args):
+        """A namespace built without a command line (tests, make_trainer) rendered as one: positional first."""
+        out = [str(getattr(args, 'data_path', 'synthetic'))]
+        for k, v in sorted(vars(args).items()):
+            if k in ('data_path', 'device') or k.startswith('_') or v is None or v is False:
+                continue
+            flag = '--' + k.replace('_', '-')
+            out += [flag] if v is True else [flag, str(v)]
+        return out
+
     @classmethod
     def create_from_cli(cls, argv=None):
+        import sys
         parser = argparse.ArgumentParser(description='TartanGAN trainer (B200)', fromfile_prefix_chars='@')
         cls.add_args_to_parser(parser)
-        args = parser.parse_args(argv)
+        raw = list(sys.argv[1:] if argv is None else argv)
+        args = parser.parse_args(raw)
+        # what gets echoed to config.args: the command line with @files expanded
+        expanded = []
+        for a in raw:
+            if a.startswith('@'):
+                with open(a[1:]) as f:
+                    expanded += [ln for ln in f.read().splitlines() if ln]
+            else:
+                expanded.append(a)
+        args._argv = expanded
         set_device_from_args(args)
         print(f'Using device "{args.device}"')
         return cls(args, [])
