@@ -58,6 +58,13 @@ int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int
 /* tuning switch: 1 (default) = TMA-fed activation tiles where applicable, 0 = cp.async staging everywhere */
 int ttg_set_use_tma(int on);
 int ttg_set_use_fold(int on);   /* development switch: kx-folded row-tile conv kernel on / off */
+/* A/B switch (default 1): resident-filter layers (Cin in {16, 32, 64}) fetch their halo tiles as whole pixel rows with
+ * cp.async.bulk and re-lay them out in shared memory (where the fused BatchNorm/LeakyReLU prologue, the fused nearest
+ * upsample and the channel padding of 8-channel tensors are applied); 0 = tensor-map (TMA tile) loads. */
+int ttg_set_use_rows(int on);
+/* A/B switch (default 1): the TMA-fed resident-filter conv kernel fetches its halo tile pixel-major with a
+ * SWIZZLE_32B/64B/128B tensor map (one L2 request per pixel) instead of 16-byte channel-group rows. */
+int ttg_set_use_swz(int on);
 int ttg_conv2d_tc_pre(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin,
                       int Cout, int ksize, int up, int dtype_out, const float* pre_scale, const float* pre_shift,
                       float slope, void* stream);
@@ -94,6 +101,10 @@ int ttg_conv2d_wgrad_bias_tc_ex(const void* x, const void* gy, float* gw, float*
 int ttg_conv2d_wgrad_tc(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int ksize,
                         int up, void* workspace, void* stream);
 size_t ttg_conv2d_wgrad_tc_workspace_bytes(int Cin, int Cout, int ksize);
+/* A/B switch (default 1): 3x3 wgrad of narrow layers (3 Cout <= 128, 3 Cin <= 256) with the filter column folded into
+ * the MMA's M dimension (three column-shifted copies of the gy tile) and the filter row into N: 8 instead of 24 MMAs
+ * per 128-pixel tile.  0 restores the per-column variant. */
+int ttg_set_wgrad_mfold(int on);
 
 /* ---- train-mode BatchNorm2d fused with LeakyReLU
  * (nn.BatchNorm2d + nn.LeakyReLU(0.2) pairs: generator.py:38-43,120-122;

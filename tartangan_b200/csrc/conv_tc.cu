@@ -451,10 +451,80 @@ __device__ __forceinline__ void epi_stats_flush(EpiStats& e, int lane, int Cout,
     if (lane < up) { atomicAdd(&s_stats[j * 8 + k], a); atomicAdd(&s_stats[Cout + j * 8 + k], b); }
   }
 }
+// Lean write-back for the common case (bf16 NHWC output, compile-time Cout in {16, 32, 64}, tile completely inside
+// the image): everything that the generic routine below derives at run time (chunking, swizzle shifts, bounds) is a
+// constant here.  The small-channel layers are bound by the instruction count per 128-pixel tile (round 2, ncu:
+// ~1100 warp instructions per tile in the generic epilogue, issue slots 67 % busy at 2.6 TB/s), not by HBM.
+template <int COUT, bool STATS>
+__device__ __forceinline__ void conv_tc_epilogue_lean(uint32_t tacc, uint8_t* sE, int warp, int lane, long long pix0, int W,
+                                                      const float* __restrict__ bias, bf16* __restrict__ y, EpiStats* est) {
+  constexpr int UPP = COUT / 8, LOG = UPP == 2 ? 1 : UPP == 4 ? 2 : 3, FSH = 3 - LOG, PITCH = COUT * 2;
+  const uint32_t strip = smem_u32(sE + (size_t)warp * 32 * (PITCH + 16));
+  const int key = (lane >> FSH) & (UPP - 1);
+  const uint32_t mine = strip + (uint32_t)(lane * PITCH);
+#pragma unroll
+  for (int c1 = 0; c1 < COUT; c1 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c1, r);
+    tmem_ld_wait();
+    if (bias) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c1) + q);
+        r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b4.x);
+        r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b4.y);
+        r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b4.z);
+        r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b4.w);
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    const int u0 = c1 >> 3;
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(mine + (uint32_t)((u0 ^ key) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(mine + (uint32_t)(((u0 + 1) ^ key) << 4)), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < UPP; ++i) {
+    const int u = lane + 32 * i, p = u >> LOG, j = u & (UPP - 1);      // j == lane & (UPP - 1): a lane always owns the same channel group
+    const int slot = j ^ ((p >> FSH) & (UPP - 1));
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(strip + (uint32_t)(p * PITCH + (slot << 4))));
+    *reinterpret_cast<uint4*>(y + (pix0 + (long long)(warp * 4 + (p >> 3)) * W + (p & 7)) * COUT + j * 8) = v;
+    if constexpr (STATS) {
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float f0 = __uint_as_float(w4[k] << 16), f1 = __uint_as_float(w4[k] & 0xffff0000u);
+        est->s[2 * k] += f0; est->q[2 * k] += f0 * f0;
+        est->s[2 * k + 1] += f1; est->q[2 * k + 1] += f1 * f1;
+      }
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void conv_tc_epilogue_coalesced(uint32_t tacc, uint8_t* sE, int warp, int lane, int n, int y0, int x0,
                                                            int H, int W, int Cout, const float* __restrict__ bias,
                                                            bf16* __restrict__ y, float* s_stats = nullptr,
                                                            EpiStats* est = nullptr) {
+  if (y0 + TC_TH <= H && x0 + TC_TW <= W && (s_stats == nullptr || est != nullptr) && (Cout == 16 || Cout == 32 || Cout == 64)) {
+    const long long pix0 = ((long long)n * H + y0) * W + x0;
+    if (est) {
+      if (Cout == 16) conv_tc_epilogue_lean<16, true>(tacc, sE, warp, lane, pix0, W, bias, y, est);
+      else if (Cout == 32) conv_tc_epilogue_lean<32, true>(tacc, sE, warp, lane, pix0, W, bias, y, est);
+      else conv_tc_epilogue_lean<64, true>(tacc, sE, warp, lane, pix0, W, bias, y, est);
+    } else {
+      if (Cout == 16) conv_tc_epilogue_lean<16, false>(tacc, sE, warp, lane, pix0, W, bias, y, nullptr);
+      else if (Cout == 32) conv_tc_epilogue_lean<32, false>(tacc, sE, warp, lane, pix0, W, bias, y, nullptr);
+      else conv_tc_epilogue_lean<64, false>(tacc, sE, warp, lane, pix0, W, bias, y, nullptr);
+    }
+    return;
+  }
   if (Cout == 8) {                       // one 16-byte unit per pixel: lanes are already on consecutive units
     uint32_t r[16];
     tmem_ld16(tacc + ((uint32_t)(warp * 32) << 16), r);
@@ -751,11 +821,38 @@ __device__ __forceinline__ void resident_issue_tile(uint32_t dacc, uint64_t a0, 
   }
 }
 
-template <int K, int NBUF, int CIN, bool STATS>
-__global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
+// Pixel-major ("NHWC as it lies in memory") activation tile for the A operand: halo pixel (hy, hx) at
+// (hy * WH + hx) * CIN * 2 bytes, its CIN channels contiguous -- the K-major canonical layout with a
+// SWIZZLE_{32,64,128}B row of CIN * 2 bytes, written by ONE tensor-map load whose inner box dimension is the whole
+// pixel (32-128 bytes per L2 request instead of the 16-byte requests of the [row][channel group][col] image: ncu of
+// the 16->16 layers showed 8.4 M L2 read requests for 134 MB and the L2 request pipe, not HBM, near its limit).
+// The swizzle XOR is a function of the absolute shared-memory address for both the TMA write and the UMMA read, so
+// tap (ky, kx) is still just a shifted start address (rows are pixels) and a K step is +32 bytes inside the row.
+__device__ __forceinline__ uint64_t umma_desc_swz(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
+         ((uint64_t)layout_type << 61);
+}
+template <int K, int CIN, int SL = 0>
+__device__ __forceinline__ void resident_issue_tile_swz(uint32_t dacc, uint64_t a0, uint64_t b, uint32_t b_step, uint32_t idesc) {
+  constexpr int K16N = CIN / 16, WH = TC_TW + 2 * (K / 2);
+  if constexpr (SL < K * K * K16N) {
+    constexpr int tap = SL / K16N, j = SL % K16N, ky = tap / K, kx = tap % K;
+    umma_bf16_imm<(SL > 0)>(dacc, a0 + (uint64_t)((ky * WH + kx) * (CIN / 8) + 2 * j), b, idesc);
+    resident_issue_tile_swz<K, CIN, SL + 1>(dacc, a0, b + b_step, b_step, idesc);
+  }
+}
+
+// PRE (needs the pixel-major swizzled tile, compile-time CIN): four extra warps apply the BatchNorm + LeakyReLU that
+// precedes the conv (a = lrelu(x * scale[c] + shift[c]); generator.py:38-47, discriminator.py:60-66) IN PLACE on the
+// tile the TMA engine has just delivered, before the MMAs read it; pixels outside the image keep the TMA's zero fill
+// (the reference pads the activation, not x).  The separate BatchNorm-apply pass over the tensor disappears.
+template <int K, int NBUF, int CIN, bool STATS, bool PRE = false>
+__global__ void __launch_bounds__(PRE ? 320 : 192) conv_tc_tma_kernel(const __grid_constant__ CUtensorMap tmap, const bf16* __restrict__ wp,
                                                           const float* __restrict__ bias, void* __restrict__ y, int out_f32,
                                                           int H, int W, int Cin_rt, int Cout, int total_tiles, int tmem_cols,
-                                                          int mode, int cstore, double* __restrict__ stats) {
+                                                          int mode, int cstore, double* __restrict__ stats, int swz,
+                                                          const float* __restrict__ pre_scale = nullptr,
+                                                          const float* __restrict__ pre_shift = nullptr, float slope = 1.f) {
   constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
   constexpr int NACC = 4;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -771,7 +868,8 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
   uint64_t* empty = full + NBUF;
   uint64_t* acc_full = empty + NBUF;
   uint64_t* acc_empty = acc_full + NACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  uint64_t* ready = acc_empty + NACC;                                         // PRE: tile transformed in place (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + NBUF);
 
   const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
   const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -788,7 +886,7 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
     for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
   if (tid == 0) {
-    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], 128); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     mbar_fence_init();
   }
@@ -813,7 +911,9 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       const int acc = j & (NACC - 1);
       int n, y0, x0;
       tile_coords(j, n, y0, x0);
-      mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      // one warp polls the mbarrier, the other three park on a hardware barrier: spinning warps cost issue slots
+      if (warp == 0) mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       tc_fence_after_sync();
       if (mode == 1) {       // TIMING EXPERIMENT: stores as a [N][H][C/8][W][8] layout would issue them
         const uint32_t tacc = tmem_base + (uint32_t)(acc * Cout);
@@ -848,13 +948,17 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
     const uint32_t b_step = slice_bytes >> 4;
     for (int it = 0; it < T; ++it) {
       const int s = it % NBUF, acc = it & (NACC - 1);
-      mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
+      mbar_wait(PRE ? &ready[s] : &full[s], (uint32_t)(it / NBUF) & 1u);
       if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u);
       tc_fence_after_sync();
       if (elect_one()) {
         const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, c8n * WH * 16);
         const uint32_t dacc = tmem_base + (uint32_t)(acc * Cout);
         if constexpr (CIN > 0) {
+          if (swz) {
+            const uint64_t a0s = umma_desc_swz(smem_u32(sA + (size_t)s * a_bytes), (uint32_t)(WH * CIN * 2), (uint32_t)swz);
+            resident_issue_tile_swz<K, CIN>(dacc, a0s, b0, b_step, idesc);
+          } else
           resident_issue_tile<K, CIN>(dacc, a0, b0, b_step, idesc);
         } else {
           uint32_t sl = 0;
@@ -870,7 +974,44 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (elect_one()) {
+  } else if (PRE && warp >= 6) {
+    // ------------------------------------------------------------ in-place BatchNorm + LeakyReLU on the delivered tile
+    if constexpr (PRE && CIN > 0) {
+      constexpr int C8N = CIN / 8, PSTEP = 128 / C8N;
+      const int tt = tid - 192, lc = tt % C8N, p0 = tt / C8N;       // this thread's (logical) channel group: fixed
+      float sc[8], sh[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sc[k] = __ldg(pre_scale + lc * 8 + k); sh[k] = __ldg(pre_shift + lc * 8 + k); }
+      for (int j = 0; j < T; ++j) {
+        const int s = j % NBUF;
+        if (warp == 6) mbar_wait(&full[s], (uint32_t)(j / NBUF) & 1u);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        int n, y0, x0;
+        tile_coords(j, n, y0, x0);
+        const uint32_t sa = smem_u32(sA + (size_t)s * a_bytes);
+        for (int p = p0; p < HP; p += PSTEP) {
+          const int hy = p / WH, hx = p - hy * WH;
+          const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
+          if (gy < 0 || gy >= H || gx < 0 || gx >= W) continue;      // zero fill = the conv's padding of the ACTIVATION
+          const uint32_t pa = sa + (uint32_t)p * (CIN * 2);
+          const uint32_t ua = pa + (uint32_t)((lc ^ (int)((pa >> 7) & (C8N - 1))) << 4);   // swizzled home of chunk lc
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ua));
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 f = __bfloat1622float2(h[q]);
+            f.x = lrelu(f.x * sc[2 * q] + sh[2 * q], slope);
+            f.y = lrelu(f.y * sc[2 * q + 1] + sh[2 * q + 1], slope);
+            h[q] = __floats2bfloat162_rn(f.x, f.y);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ua), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&ready[s]);
+      }
+    }
+  } else if (warp == 5 && elect_one()) {
     // ------------------------------------------------------------ TMA producer (warp 5, one lane)
     for (int j = 0; j < T; ++j) {
       const int s = j % NBUF;
@@ -879,7 +1020,12 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
       tile_coords(j, n, y0, x0);
       const uint32_t bar = smem_u32(&full[s]);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a_bytes) : "memory");
-      if (mode == 0)
+      if (swz)
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+          ::"r"(smem_u32(sA + (size_t)s * a_bytes)), "l"(&tmap), "r"(0), "r"(x0 - HALO), "r"(y0 - HALO), "r"(n), "r"(bar)
+          : "memory");
+      else if (mode == 0)
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
           ::"r"(smem_u32(sA + (size_t)s * a_bytes)), "l"(&tmap), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
@@ -898,11 +1044,14 @@ __global__ void __launch_bounds__(192) conv_tc_tma_kernel(const __grid_constant_
     for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
 }
 
+static int g_use_swz = 1;       // A/B switch: pixel-major swizzled activation tiles in the TMA-fed conv kernel
+extern "C" int ttg_set_use_swz(int on) { g_use_swz = on ? 1 : 0; return TTG_OK; }
 static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
 template <int K, int NBUF, int CIN>
 static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
                               int Cin, int Cout, int cin_mem, int cstore, long long tiles, int w_bytes, int a_bytes, int pcols,
-                              double* stats, cudaStream_t st, bool* used) {
+                              double* stats, cudaStream_t st, bool* used, const float* pre_scale = nullptr,
+                              const float* pre_shift = nullptr, float slope = 1.f) {
   *used = false;
   ttg_encode_tiled_fn enc = ttg_get_encode_tiled();
   if (!enc) return TTG_OK;
@@ -915,8 +1064,17 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   const cuuint32_t box[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r;
-  const int mode = g_use_tma - 1;
-  if (mode == 1) {
+  int mode = g_use_tma - 1;
+  // pixel-major swizzled tile (see umma_desc_swz): compile-time channel counts 16 / 32 / 64 only
+  const int swz = (g_use_swz && CIN > 0 && mode == 0) ? (CIN == 16 ? 6 : CIN == 32 ? 4 : 2) : 0;
+  if (swz) {
+    const cuuint64_t d4[4] = {(cuuint64_t)cin_mem, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t s4[3] = {(cuuint64_t)cin_mem * 2, (cuuint64_t)W * cin_mem * 2, (cuuint64_t)H * W * cin_mem * 2};
+    const cuuint32_t b4[4] = {(cuuint32_t)Cin, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), d4, s4, b4, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CIN == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (mode == 1) {
     const cuuint64_t d4[4] = {(cuuint64_t)W * 8, (cuuint64_t)(Cin / 8), (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t s4[3] = {(cuuint64_t)W * 16, (cuuint64_t)(Cin / 8) * W * 16, (cuuint64_t)H * (Cin / 8) * W * 16};
     const cuuint32_t b4[4] = {(cuuint32_t)(TC_TW + 2 * HALO) * 8, (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
@@ -945,14 +1103,38 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   if (per_sm > 512 / pcols) per_sm = 512 / pcols;
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
+  if (pre_scale) {
+    if constexpr (CIN > 0) {
+      if (!swz) return TTG_OK;                 // (*used stays false: the caller takes another path)
+      static int smem_set_pre = 0;
+      if (smem > smem_set_pre) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: smem attribute: %s", cudaGetErrorString(e));
+        smem_set_pre = smem;
+      }
+      if (per_sm > 6) per_sm = 6;              // 320 threads per CTA
+      long long gridp = (long long)ttg_num_sms() * per_sm;
+      if (gridp > tiles) gridp = tiles;
+      if (stats)
+        conv_tc_tma_kernel<K, NBUF, CIN, true, true><<<(unsigned)gridp, 320, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
+                                                                             (int)tiles, pcols, mode, cstore, stats, swz, pre_scale, pre_shift, slope);
+      else
+        conv_tc_tma_kernel<K, NBUF, CIN, false, true><<<(unsigned)gridp, 320, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
+                                                                              (int)tiles, pcols, mode, cstore, stats, swz, pre_scale, pre_shift, slope);
+      TTG_CHECK_LAUNCH("conv2d_tc_tma_pre");
+      *used = true;
+    }
+    return TTG_OK;
+  }
   long long grid = (long long)ttg_num_sms() * per_sm;
   if (grid > tiles) grid = tiles;
   if (stats)
     conv_tc_tma_kernel<K, NBUF, CIN, true><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
-                                                                        (int)tiles, pcols, mode, cstore, stats);
+                                                                        (int)tiles, pcols, mode, cstore, stats, swz);
   else
     conv_tc_tma_kernel<K, NBUF, CIN, false><<<(unsigned)grid, 192, smem, st>>>(tmap, (const bf16*)wp, bias, y, out_f32, H, W, Cin, Cout,
-                                                                         (int)tiles, pcols, mode, cstore, stats);
+                                                                         (int)tiles, pcols, mode, cstore, stats, swz);
   TTG_CHECK_LAUNCH("conv2d_tc_tma");
   *used = true;
   return TTG_OK;
@@ -1498,6 +1680,278 @@ static int launch_conv_tc_fold(const void* x, const void* wp, const float* bias,
   return TTG_OK;
 }
 
+// ------------------------------------------------------------------ fprop / dgrad, bulk-row loads + transform stage
+// The tensor-map loads above fetch an NHWC halo tile as 16-byte "rows" (8 channels of one pixel), and the TMA engine
+// delivers about ONE such row per clock per SM (measured, round 2: clock64 traces of the wgrad kernel: a tile of 1056
+// rows takes 3170 cycles at three CTAs per SM), i.e. <= 16 B / clk / SM = 4.6 TB/s over the chip before any other
+// cost -- below the HBM roofline of the small-channel layers.  Here the producer warp copies whole pixel ROWS of the
+// halo tile with cp.async.bulk (contiguous (TW+2) * Cin * 2 bytes each, no tensor map) into a raw staging slot, and
+// four transform warps re-lay it out into the [halo row][channel group][halo col] x 16 B UMMA operand image.  The
+// transform stage is where everything that used to be a separate pass over the tensor happens for free:
+//   * the BatchNorm + LeakyReLU that precedes the conv (generator.py:38-47, discriminator.py:60-66):
+//     a = lrelu(x * scale[c] + shift[c]), zero padding applied AFTER the activation like the reference;
+//   * the nearest x2 upsample of the generator blocks (generator.py:58): the raw slot holds the LOW resolution
+//     tile (10 x 6 pixels) and is replicated while it is re-laid out;
+//   * the zero fill of the conv padding and of the missing channel group of 8-channel (RGB staging) tensors.
+// warps 0-3 epilogue, warp 4 MMA issuer, warp 5 row producer, warps 6-9 transform.
+template <int K, int CIN, bool UP, bool PRE, bool STATS>
+__global__ void __launch_bounds__(320) conv_tc_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ wp,
+                                                          const float* __restrict__ bias, void* __restrict__ y, int out_f32,
+                                                          int H, int W, int Cout, int total_tiles, int tmem_cols, int cin_mem,
+                                                          int cstore, int nraw, int nbuf, const float* __restrict__ pre_scale,
+                                                          const float* __restrict__ pre_shift, float slope,
+                                                          double* __restrict__ stats) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  constexpr int RH = UP ? TC_TH / 2 + 2 * HALO : HH, RW = UP ? TC_TW / 2 + 2 * HALO : WH;   // raw tile (low resolution when UP)
+  constexpr int NACC = 4, C8N = CIN / 8, K16N = CIN / 16;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t slice_bytes = (uint32_t)Cout * 32;
+  const uint32_t w_bytes = (uint32_t)(K * K * K16N) * slice_bytes;
+  constexpr uint32_t a_bytes = (uint32_t)C8N * HP * 16;
+  const int c8n_mem = cin_mem >> 3;                                          // channel groups present in memory
+  const uint32_t pix_bytes = (uint32_t)cin_mem * 2;
+  const uint32_t raw_bytes = ((uint32_t)(RH * RW) * pix_bytes + 127) & ~127u;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + ((w_bytes + 127) & ~127u);
+  uint8_t* sR = sA + (size_t)nbuf * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (size_t)nraw * raw_bytes);
+  uint64_t* raw_full = bars;              // [nraw]  bytes of the tile's rows have landed (tx count)
+  uint64_t* raw_empty = raw_full + 4;     // [nraw]  transform warps are done reading the slot (128 arrivals)
+  uint64_t* ready = raw_empty + 4;        // [nbuf]  operand image written and fenced (128 arrivals)
+  uint64_t* empty = ready + 4;            // [nbuf]  MMAs have consumed the operand image (commit)
+  uint64_t* acc_full = empty + 4;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+  uint8_t* sE = reinterpret_cast<uint8_t*>(bars) + 256;
+  float* s_stats = reinterpret_cast<float*>(sE + tc_epi_strip_bytes_dev(Cout));
+
+  const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
+  const int T = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto tile_coords = [&](int j, int& n, int& y0, int& x0) {
+    const int tile = blockIdx.x + j * gridDim.x;
+    n = tile / tiles_img;
+    const int t2 = tile - n * tiles_img;
+    y0 = (t2 / tiles_x) * TC_TH;
+    x0 = (t2 % tiles_x) * TC_TW;
+  };
+
+  if constexpr (STATS)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < nraw; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], 128); }
+    for (int i = 0; i < nbuf; ++i) { mbar_init(&ready[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_fence_init();
+  }
+  if (warp < 4)
+    for (int i = tid; i < (int)(w_bytes / 16); i += 128)
+      reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(wp) + i);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ epilogue
+    EpiStats est;
+    if constexpr (STATS) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) est.s[k] = est.q[k] = 0.f;
+    }
+    const bool reg_stats = STATS && epi_stats_in_regs(Cout) && cstore == Cout;
+    for (int j = 0; j < T; ++j) {
+      const int acc = j & (NACC - 1);
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      { TTG_T0(); if (warp == 0) mbar_wait(&acc_full[acc], (uint32_t)(j / NACC) & 1u);
+        asm volatile("bar.sync 1, 128;" ::: "memory"); if (tid == 0) { TTG_T1(5, j); } }
+      tc_fence_after_sync();
+      TTG_T0();
+      if (!out_f32)
+        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), sE, warp, lane, n, y0, x0, H, W, cstore, bias,
+                                   reinterpret_cast<bf16*>(y), STATS ? s_stats : nullptr, (STATS && reg_stats) ? &est : nullptr);
+      else
+        conv_tc_epilogue<HALO>(tmem_base + (uint32_t)(acc * Cout), warp, tid, n, y0, x0, H, W, Cout, bias, y, out_f32,
+                               cstore == Cout ? 0 : cstore);
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[acc]);
+      if (tid == 0) { TTG_T1(6, j); }
+    }
+    if constexpr (STATS) { if (reg_stats) epi_stats_flush(est, lane, Cout, s_stats); }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(128, Cout, 0, 0);
+    const uint64_t b0 = umma_desc(smem_u32(sW), (uint32_t)Cout * 16, 128);
+    const uint32_t b_step = slice_bytes >> 4;
+    int s = 0;
+    uint32_t sph = 0;
+    for (int it = 0; it < T; ++it) {
+      const int acc = it & (NACC - 1);
+      { TTG_T0(); mbar_wait(&ready[s], sph); if (lane == 0) { TTG_T1(2, it); } }
+      { TTG_T0(); if (it >= NACC) mbar_wait(&acc_empty[acc], (uint32_t)((it / NACC) - 1) & 1u); if (lane == 0) { TTG_T1(3, it); } }
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint64_t a0 = umma_desc(smem_u32(sA + (size_t)s * a_bytes), WH * 16, C8N * WH * 16);
+        resident_issue_tile<K, CIN>(tmem_base + (uint32_t)(acc * Cout), a0, b0, b_step, idesc);
+        umma_commit(&empty[s]);
+        umma_commit(&acc_full[acc]);
+      }
+      __syncwarp();
+      if (++s == nbuf) { s = 0; sph ^= 1u; }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ row producer: one bulk copy per pixel row of the raw tile
+    const int Hs = H >> (UP ? 1 : 0), Ws = W >> (UP ? 1 : 0);
+    int r = 0;
+    uint32_t rph = 0;
+    for (int j = 0; j < T; ++j) {
+      { TTG_T0(); if (j >= nraw) mbar_wait(&raw_empty[r], rph ^ 1u); if (lane == 0) { TTG_T1(1, j); } }
+      TTG_T0();
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      const int ylo = (y0 - HALO) >> (UP ? 1 : 0), xlo = (x0 - HALO) >> (UP ? 1 : 0);    // arithmetic shifts: -1 >> 1 == -1
+      const int c0 = max(xlo, 0), c1 = min(xlo + RW, Ws);
+      const int r0 = max(ylo, 0), r1 = min(ylo + RH, Hs);
+      const uint32_t row_bytes = (uint32_t)(c1 - c0) * pix_bytes;
+      const uint32_t bar = smem_u32(&raw_full[r]);
+      // (one elected lane walks the rows: UBLKCP is a uniform-datapath instruction, and 18 lanes with different
+      //  addresses made ptxas serialise them in a ~100-cycle-per-copy waterfall loop: 1900 cycles per tile, measured)
+      if (elect_one()) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(r1 - r0) * row_bytes) : "memory");
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + (((long long)n * Hs + r0) * Ws + c0) * (long long)pix_bytes;
+        uint32_t dst = smem_u32(sR + (size_t)r * raw_bytes) + (uint32_t)((r0 - ylo) * RW + (c0 - xlo)) * pix_bytes;
+        const long long src_step = (long long)Ws * pix_bytes;
+        const uint32_t dst_step = (uint32_t)RW * pix_bytes;
+        for (int ry = r0; ry < r1; ++ry, src += src_step, dst += dst_step)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) { TTG_T1(9, j); }
+      if (++r == nraw) { r = 0; rph ^= 1u; }
+    }
+  } else {
+    // ------------------------------------------------------------ transform: raw rows -> UMMA operand image
+    const int tt = tid - 192;                       // 0..127
+    const int c8 = tt % C8N, p0 = tt / C8N;         // this thread's channel group (fixed) and first halo pixel
+    constexpr int PSTEP = 128 / C8N;
+    float sc[8], sh[8];
+    if constexpr (PRE) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {        // (arrays of cin_mem entries; padded channels must carry scale = shift = 0)
+        sc[k] = c8 < c8n_mem ? __ldg(pre_scale + c8 * 8 + k) : 0.f;
+        sh[k] = c8 < c8n_mem ? __ldg(pre_shift + c8 * 8 + k) : 0.f;
+      }
+    }
+    const bool have_c8 = c8 < c8n_mem;
+    int r = 0, s = 0;
+    uint32_t rph = 0, sph = 0;
+    for (int j = 0; j < T; ++j) {
+      int n, y0, x0;
+      tile_coords(j, n, y0, x0);
+      const int ylo = (y0 - HALO) >> (UP ? 1 : 0), xlo = (x0 - HALO) >> (UP ? 1 : 0);
+      { TTG_T0();
+        if (warp == 6) { mbar_wait(&raw_full[r], rph); if (j >= nbuf) mbar_wait(&empty[s], sph ^ 1u); }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (tt == 0) { TTG_T1(4, j); } }
+      TTG_T0();
+      const uint8_t* raw = sR + (size_t)r * raw_bytes;
+      const uint32_t dst0 = smem_u32(sA + (size_t)s * a_bytes);
+      for (int p = p0; p < HP; p += PSTEP) {
+        const int hy = p / WH, hx = p - hy * WH;
+        const int gy = y0 + hy - HALO, gx = x0 + hx - HALO;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (have_c8 && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          const int ry = (gy >> (UP ? 1 : 0)) - ylo, rx = (gx >> (UP ? 1 : 0)) - xlo;
+          v = *reinterpret_cast<const uint4*>(raw + (size_t)(ry * RW + rx) * pix_bytes + c8 * 16);
+          if constexpr (PRE) {
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 f = __bfloat1622float2(h[q]);
+              f.x = lrelu(f.x * sc[2 * q] + sh[2 * q], slope);
+              f.y = lrelu(f.y * sc[2 * q + 1] + sh[2 * q + 1], slope);
+              h[q] = __floats2bfloat162_rn(f.x, f.y);
+            }
+          }
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst0 + (uint32_t)((hy * C8N + c8) * WH + hx) * 16), "r"(v.x), "r"(v.y),
+                     "r"(v.z), "r"(v.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&ready[s]);
+      mbar_arrive(&raw_empty[r]);
+      if (tt == 0) { TTG_T1(7, j); }
+      if (++r == nraw) { r = 0; rph ^= 1u; }
+      if (++s == nbuf) { s = 0; sph ^= 1u; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if constexpr (STATS)
+    for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
+}
+
+static int g_use_rows = 0;       // A/B switch: bulk-row + transform kernel for resident-filter layers (0: tensor-map tiles)
+extern "C" int ttg_set_use_rows(int on) { g_use_rows = on ? 1 : 0; return TTG_OK; }
+
+template <int K, int CIN, bool UP, bool PRE>
+static int launch_conv_tc_rows(const void* x, const void* wp, const float* bias, void* y, int out_f32, int N, int H, int W,
+                               int Cout, int cin_mem, int cstore, long long tiles, const float* pre_scale,
+                               const float* pre_shift, float slope, double* stats, cudaStream_t st) {
+  constexpr int HALO = K / 2, WH = TC_TW + 2 * HALO, HH = TC_TH + 2 * HALO, HP = WH * HH;
+  constexpr int RH = UP ? TC_TH / 2 + 2 * HALO : HH, RW = UP ? TC_TW / 2 + 2 * HALO : WH;
+  const int w_bytes = K * K * (CIN / 16) * Cout * 32;
+  const int a_bytes = (CIN / 8) * HP * 16;
+  const int raw_bytes = (RH * RW * cin_mem * 2 + 127) & ~127;
+  const int fixed = ((w_bytes + 127) & ~127) + 256 + tc_epi_bytes(Cout) + 64;
+  // slots: as deep as fits, at most 3 operand + 3 raw slots
+  int nbuf = 3, nraw = 3;
+  while (nbuf > 2 && fixed + nbuf * a_bytes + nraw * raw_bytes > 200 * 1024) --nbuf;
+  while (nraw > 2 && fixed + nbuf * a_bytes + nraw * raw_bytes > 200 * 1024) --nraw;
+  const int smem = fixed + nbuf * a_bytes + nraw * raw_bytes;
+  if (smem > 227 * 1024) return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_tc_rows: layer does not fit shared memory");
+  const int pcols = (int)tmem_cols_for(4 * Cout);
+  auto kern_s = conv_tc_rows_kernel<K, CIN, UP, PRE, true>;
+  auto kern_n = conv_tc_rows_kernel<K, CIN, UP, PRE, false>;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern_n, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc_rows: smem attribute: %s", cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  int per_sm = (220 * 1024) / smem;
+  if (per_sm > 512 / pcols) per_sm = 512 / pcols;
+  if (per_sm > 2048 / 320) per_sm = 2048 / 320;
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)ttg_num_sms() * per_sm;
+  if (grid > tiles) grid = tiles;
+  if (stats)
+    kern_s<<<(unsigned)grid, 320, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cout, (int)tiles, pcols, cin_mem,
+                                              cstore, nraw, nbuf, pre_scale, pre_shift, slope, stats);
+  else
+    kern_n<<<(unsigned)grid, 320, smem, st>>>((const bf16*)x, (const bf16*)wp, bias, y, out_f32, H, W, Cout, (int)tiles, pcols, cin_mem,
+                                              cstore, nraw, nbuf, pre_scale, pre_shift, slope, stats);
+  TTG_CHECK_LAUNCH("conv2d_tc_rows");
+  return TTG_OK;
+}
+
+template <int K, int CIN>
+static int dispatch_conv_tc_rows(int up, bool pre, const void* x, const void* wp, const float* bias, void* y, int out_f32, int N,
+                                 int H, int W, int Cout, int cin_mem, int cstore, long long tiles, const float* pre_scale,
+                                 const float* pre_shift, float slope, double* stats, cudaStream_t st) {
+#define TTG_ROWS(UPF, PREF) launch_conv_tc_rows<K, CIN, UPF, PREF>(x, wp, bias, y, out_f32, N, H, W, Cout, cin_mem, cstore, tiles, \
+                                                                  pre_scale, pre_shift, slope, stats, st)
+  if (up) return pre ? TTG_ROWS(true, true) : TTG_ROWS(true, false);
+  return pre ? TTG_ROWS(false, true) : TTG_ROWS(false, false);
+#undef TTG_ROWS
+}
+
 // Cin / Cout are the (padded, multiple-of-16) GEMM channel counts; cin_real / cout_real the channel counts of the
 // tensors in memory (equal to Cin / Cout except for the RGB layers).
 // stats (optional): double[2 * Cout], zeroed by the caller; receives sum / sum of squares per output channel of the
@@ -1506,6 +1960,27 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
                           int Cout, int cin_real, int cout_real, int ksize, int up, int dtype_out,
                           const float* pre_scale, const float* pre_shift, float slope, double* stats, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  // (taken for the cases the tensor-map kernel has no variant for: fused upsample, prologue on an 8-channel tensor;
+  //  for plain layers the pixel-major swizzled TMA kernel below is faster: 83 vs 116 us on 16->16 @128^2)
+  if ((g_use_rows || up == 1 || (pre_scale != nullptr && cin_real != Cin)) && (ksize == 1 || ksize == 3) &&
+      (Cin == 16 || Cin == 32 || Cin == 64) && Cout % 16 == 0 && Cout >= 16 &&
+      Cout <= 256 && ksize * ksize * (Cin / 16) * Cout * 32 <= TC_RESIDENT_W_BYTES && (up == 0 || (H % 2 == 0 && W % 2 == 0)) &&
+      (dtype_out == TTG_BF16 || dtype_out == TTG_F32)) {
+    // bulk-row loads + transform stage (fused BatchNorm/LeakyReLU prologue, fused nearest upsample, 8-channel inputs)
+    const bool in8r = cin_real == 8 && Cin == 16, out8r = cout_real == 8 && Cout == 16 && dtype_out == TTG_BF16;
+    const bool okc = (cin_real == Cin || in8r) && (cout_real == Cout || out8r);
+    const bool ok_stats = stats == nullptr || (dtype_out == TTG_BF16 && cout_real == Cout);
+    const long long tiles_r = (long long)N * ((H + TC_TH - 1) / TC_TH) * ((W + TC_TW - 1) / TC_TW);
+    if (okc && ok_stats && tiles_r > 0 && tiles_r < (1ll << 31) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(wp) & 15) == 0) {
+      const int of32 = dtype_out == TTG_F32;
+#define TTG_ROWS_K(KK, CI) dispatch_conv_tc_rows<KK, CI>(up, pre_scale != nullptr, x, wp, bias, y, of32, N, H, W, Cout, cin_real, cout_real, \
+                                                      tiles_r, pre_scale, pre_shift, slope, stats, st)
+      if (ksize == 3) return Cin == 16 ? TTG_ROWS_K(3, 16) : Cin == 32 ? TTG_ROWS_K(3, 32) : TTG_ROWS_K(3, 64);
+      return Cin == 16 ? TTG_ROWS_K(1, 16) : Cin == 32 ? TTG_ROWS_K(1, 32) : TTG_ROWS_K(1, 64);
+#undef TTG_ROWS_K
+    }
+  }
   // 8-channel staging tensors (ttg_pad_channels8) ride the TMA path: not "padded" in the scalar-access sense
   // (genuine 8-channel layers of the '512thin' config look the same; with an upsample, a prologue or an fp32 output
   // they take the scalar-access padded path below instead)
@@ -1553,11 +2028,11 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
     if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     const int of32 = dtype_out == TTG_F32;
-    if (!padded && !pre_scale && up == 0 && g_use_tma) {
+    if (!padded && up == 0 && g_use_tma && (!pre_scale || (g_use_swz && cin_real == Cin && (Cin == 16 || Cin == 32 || Cin == 64)))) {
       bool used = false;
       const int tcols = (int)tmem_cols_for(4 * Cout);
       const bool deep = a_bytes <= 12 * 1024;       // small tiles: 4 slots, else 3
-#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, stats, st, &used)
+#define TTG_TMA(KK, NB, CI) launch_conv_tc_tma<KK, NB, CI>(x, wp, bias, y, dtype_out == TTG_F32, N, H, W, Cin, Cout, cin_real, cout_real, tiles, w_bytes, a_bytes, tcols, stats, st, &used, pre_scale, pre_shift, slope)
       int rc;
       // activation slots that fit next to the resident filter (256 -> 128 1x1: 64 KB filter + 64 KB tiles -> 2 slots)
       const bool three = ((w_bytes + 127) & ~127) + 3 * a_bytes + 256 + tc_epi_bytes(Cout) <= 227 * 1024;
@@ -1764,7 +2239,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c8n = Cin >> 3;
-  const uint32_t x_bytes = (uint32_t)c8n * HP * 16;
+  // fuse == 3 ("mfold", TMA only): the filter column kx is folded into M and the filter row ky into N, so a tile
+  // costs 8 MMAs instead of 24:  D[(kx, co), (ky, ci)] = sum_q gy[q - (kx-1)][co] * x[q + (ky-1) rows][ci].
+  // A = three copies of the gy tile fetched with column offsets +1, 0, -1 (stacked along M: [kx][co/8][128 px]),
+  // B = the x tile WITHOUT horizontal halo (whx = 8 columns), vertical taps reached through the N-group stride.
+  const bool mfold = fuse == 3;
+  const int whx = mfold ? TC_TW : WH;                   // columns of the staged x tile
+  const uint32_t x_bytes = (uint32_t)c8n * HH * whx * 16;
   uint8_t* sG = smem;                                   // NBUF gy tiles, [co/8][128 pixels] x 16 B
   uint8_t* sX = smem + (size_t)NBUF * g_bytes;          // NBUF x halo tiles
   // barriers live at the end of the allocation (the host pads so that an A descriptor that starts in
@@ -1778,14 +2259,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
   // B = gy^T with N = Cout, one unit per filter column kx.  The 128-row MMA floor is then filled with
   // 3*Cin useful rows instead of Cout, which cuts the tensor-pipe time of the 16/32-channel layers 3x.
   const bool swapped = fuse == 2;
-  const int units_total = fuse ? K : K * K;
+  const int units_total = mfold ? 1 : (fuse ? K : K * K);
   const int NU = swapped ? Cout : (fuse ? K * Cin : Cin);     // accumulator columns per unit
   const int unit0 = blockIdx.y * units_per_group;
   const int nunits = min(units_per_group, units_total - unit0);
   const int n_issuers = min(3, nunits);
   const int co_base = blockIdx.z * 128;
   const int co_cnt = min(128, Cout - co_base);
-  const bool m64 = swapped ? (K * Cin <= 64) : (Cout <= 64);
+  const bool m64 = swapped ? (K * Cin <= 64) : mfold ? (K * co_cnt <= 64) : (Cout <= 64);
   const int g8n = co_cnt >> 3;
   const int tiles_x = (W + TC_TW - 1) / TC_TW, tiles_y = (H + TC_TH - 1) / TC_TH, tiles_img = tiles_x * tiles_y;
   const int total_tiles = N * tiles_img;
@@ -1872,7 +2353,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       for (int it = 0; it < T; ++it) {
         const int s = it % NBUF;
         mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
-        const uint8_t* gt = sG + (size_t)s * g_bytes + (size_t)g8 * NPIX * 16;
+        // (mfold: the un-shifted copy of the gy tile is the middle one)
+        const uint8_t* gt = sG + (size_t)s * g_bytes + (size_t)((mfold ? g8n : 0) + g8) * NPIX * 16;
         for (int p = p0; p < NPIX; p += ppg) {
           const uint4 v = *reinterpret_cast<const uint4*>(gt + (size_t)p * 16);
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
@@ -1896,7 +2378,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       //   swapped        : gwp[tap][ci][co]      (columns = co)
       // ttg_wgrad_unpack_kernel turns it into OIHW.
       const int row = m64 ? (warp * 16 + lane) : tid;
-      const bool valid = (m64 ? lane < 16 : true) && row < (swapped ? K * Cin : co_cnt);
+      const bool valid = (m64 ? lane < 16 : true) && row < (swapped ? K * Cin : mfold ? K * co_cnt : co_cnt);
       const int co = co_base + row;
       for (int t = 0; t < nunits; ++t) {
         const int u = unit0 + t;
@@ -1909,6 +2391,10 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
           if (swapped) {                              // row = ky*Cin + ci, column = output channel, unit = kx
             const int ky = row / Cin, ci = row - ky * Cin;
             dst = gw + ((long long)(ky * K + u) * Cin + ci) * Cout + co_base + c0;
+          } else if (mfold) {                         // row = kx*Cout + co, column = ky*Cin + ci
+            const int kxi = row / co_cnt, cc = row - kxi * co_cnt;
+            const int ky = c0 / Cin, ci0 = c0 - ky * Cin;
+            dst = gw + ((long long)(ky * K + kxi) * Cout + cc) * Cin + ci0;
           } else {
             const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
             const int tap = fuse ? ky * K + u : u;
@@ -1935,7 +2421,17 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       tile_coords(it, n_, y0_, x0_);
       const int rmax = min(TC_TH / 2, (H - y0_ + 1) >> 1);
       const bool leader = elect_one();
-      if (leader && swapped) {
+      if (leader && mfold) {
+        const uint64_t a0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
+        const uint64_t b0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * whx) * 16, (uint32_t)whx * 16);
+#pragma unroll
+        for (int r = 0; r < TC_TH / 2; ++r)
+          if (r < rmax)
+            umma_bf16(tmem_base, a0 + (uint64_t)(2 * r * TC_TW), b0 + (uint64_t)(2 * r * c8n * whx), idesc,
+                      (it == 0 && r == 0) ? 0u : 1u);
+        umma_commit(&empty[s]);
+        if (it == T - 1) umma_commit(done);
+      } else if (leader && swapped) {
         // A = shifted x (MN-major): M groups = (ky, c8) WH units apart; B = gy^T (MN-major): N groups = co/8
         const uint64_t a0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * WH) * 16, WH * 16);
         const uint64_t b0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
@@ -1981,11 +2477,20 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       tile_coords(j, n, y0, x0);
       const uint32_t bar = smem_u32(&full[s]);
       const uint32_t gbytes_tile = (uint32_t)g8n * NPIX * 16;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + gbytes_tile) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + (mfold ? 3u : 1u) * gbytes_tile) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-          ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
+          ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(mfold ? x0 : x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
           : "memory");
+      if (mfold) {
+#pragma unroll
+        for (int kxi = 0; kxi < 3; ++kxi)       // copy kxi holds gy[q - (kxi - 1)] for the pixels q of the tile
+          asm volatile(
+              "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+              ::"r"(smem_u32(sG + (size_t)s * g_bytes) + (uint32_t)kxi * gbytes_tile), "l"(&tmap_g), "r"(0), "r"(x0 + 1 - kxi), "r"(y0),
+                "r"(co_base >> 3), "r"(n), "r"(bar)
+              : "memory");
+      } else
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
           ::"r"(smem_u32(sG + (size_t)s * g_bytes)), "l"(&tmap_g), "r"(0), "r"(x0), "r"(y0), "r"(co_base >> 3), "r"(n), "r"(bar)
@@ -2009,11 +2514,12 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
   bool tma = g_use_tma && up == 0 && (cin_real == Cin || in8) && (cout_real == Cout || out8);
   ttg_encode_tiled_fn enc = tma ? ttg_get_encode_tiled() : nullptr;
   if (!enc) tma = false;
+  if (fuse == 3 && !tma) return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_wgrad_tc: the kx-folded variant needs the TMA path");
   if (tma) {
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const cuuint64_t xd[5] = {8, (cuuint64_t)W, (cuuint64_t)(cin_real / 8), (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t xs[4] = {(cuuint64_t)cin_real * 2, 16, (cuuint64_t)W * cin_real * 2, (cuuint64_t)H * W * cin_real * 2};
-    const cuuint32_t xb[5] = {8, (cuuint32_t)(TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    const cuuint32_t xb[5] = {8, (cuuint32_t)(fuse == 3 ? TC_TW : TC_TW + 2 * HALO), (cuuint32_t)(Cin / 8), (cuuint32_t)(TC_TH + 2 * HALO), 1};
     const int g8n = (Cout < 128 ? Cout : 128) / 8;
     const cuuint64_t gd[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(cout_real / 8), (cuuint64_t)N};
     const cuuint64_t gs[4] = {(cuuint64_t)cout_real * 2, (cuuint64_t)W * cout_real * 2, 16, (cuuint64_t)H * W * cout_real * 2};
@@ -2044,6 +2550,8 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
 }
 
 static int g_wgrad_tc_smem[2] = {0, 0};
+static int g_use_mfold = 1;
+extern "C" int ttg_set_wgrad_mfold(int on) { g_use_mfold = on ? 1 : 0; return TTG_OK; }   // A/B switch (tools/kbench.py)
 
 // packed partial-sum image -> OIHW fp32 (layout 0: gwp[tap][co][ci], 1: gwp[tap][ci][co]; padded sizes CoutP x CinP)
 // acc != 0: added to gw (a view of the flat .grad buffer) instead of overwriting it
@@ -2122,18 +2630,24 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
     // persistent warp-specialised variant when at least two (x, gy) slots fit in shared memory
     // measured: the swapped orientation only pays when the input is wider than the output (32->16: 204 -> 175 us);
     // for Cin <= Cout the MMA count, not the MMA shape, is what bounds these narrow layers
-    const bool swap_ok = ksize == 3 && 3 * Cin <= 128 && Cout <= 128 && Cin > Cout;
-    const int fuse = swap_ok ? 2 : ((ksize == 3 && 3 * Cin <= 256) ? 1 : 0);
-    const int units_total = fuse ? 3 : taps;
+    // kx folded into M and ky into N (fuse 3, TMA-fed tiles only): 8 MMAs per tile instead of 24 for the narrow
+    // layers, which are bound by the MMA count (16->16 @128^2: 131 us with 24 small MMAs per 128 pixels)
+    const bool in8_ = cin_real == 8 && Cin == 16, out8_ = cout_real == 8 && Cout == 16;
+    const bool tma_ok = g_use_tma && up == 0 && (cin_real == Cin || in8_) && (cout_real == Cout || out8_) &&
+                        ttg_get_encode_tiled() != nullptr;
+    const bool mfold = g_use_mfold && tma_ok && ksize == 3 && 3 * Cout <= 128 && 3 * Cin <= 256;
+    const bool swap_ok = !mfold && ksize == 3 && 3 * Cin <= 128 && Cout <= 128 && Cin > Cout;
+    const int fuse = mfold ? 3 : swap_ok ? 2 : ((ksize == 3 && 3 * Cin <= 256) ? 1 : 0);
+    const int units_total = mfold ? 1 : fuse ? 3 : taps;
     const int NU = swap_ok ? Cout : (fuse ? 3 * Cin : Cin);
     int upg = 512 / NU;
     if (upg > units_total) upg = units_total;
     const int wgroups = (units_total + upg - 1) / upg;
     upg = (units_total + wgroups - 1) / wgroups;                 // balance units over the groups
     const int wcols = (int)tmem_cols_for(upg * NU);
-    const int x_bytes = (Cin / 8) * HP * 16;
-    const int g_bytes = ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
-    const int reach = swap_ok ? 0 : (Cout <= 64 ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
+    const int x_bytes = mfold ? (Cin / 8) * (TC_TH + 2) * TC_TW * 16 : (Cin / 8) * HP * 16;
+    const int g_bytes = (mfold ? 3 : 1) * ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
+    const int reach = swap_ok ? 0 : ((mfold ? 3 * Cout <= 64 : Cout <= 64) ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
     // swapped orientation: the padding rows of the A operand (ky = 3) reach one halo row past the last x slot
     const int xpad = swap_ok ? 2 * (Cin / 8) * (TC_TW + 2 * halo) * 16 : 0;
     int nbuf = (200 * 1024 - reach) / (x_bytes + g_bytes);

@@ -27,7 +27,13 @@ def main():
     if os.environ.get('TTG_FOLD'):
         _lib.lib.ttg_set_use_fold(int(os.environ['TTG_FOLD']))
     if os.environ.get('TTG_TMA_MODE'):
-        _lib.lib.ttg_set_use_tma(int(os.environ["TTG_TMA_MODE"]), None)
+        _lib.lib.ttg_set_use_tma(int(os.environ["TTG_TMA_MODE"]))
+    if os.environ.get('TTG_ROWS'):
+        _lib.lib.ttg_set_use_rows(int(os.environ['TTG_ROWS']))
+    if os.environ.get('TTG_SWZ'):
+        _lib.lib.ttg_set_use_swz(int(os.environ['TTG_SWZ']))
+    if os.environ.get('TTG_MFOLD'):
+        _lib.lib.ttg_set_wgrad_mfold(int(os.environ['TTG_MFOLD']))
     a = [int(v) for v in sys.argv[2:]]
     bf = torch.bfloat16
     if kind in ('conv', 'wgrad', 'convd'):
