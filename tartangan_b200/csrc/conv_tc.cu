@@ -832,6 +832,11 @@ __device__ __forceinline__ uint64_t umma_desc_swz(uint32_t smem_addr, uint32_t s
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) |
          ((uint64_t)layout_type << 61);
 }
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+__host__ __device__ __forceinline__ uint32_t umma_swz_layout_for(int channels) { return channels == 16 ? 6u : channels == 32 ? 4u : 2u; }
 template <int K, int CIN, int SL = 0>
 __device__ __forceinline__ void resident_issue_tile_swz(uint32_t dacc, uint64_t a0, uint64_t b, uint32_t b_step, uint32_t idesc) {
   constexpr int K16N = CIN / 16, WH = TC_TW + 2 * (K / 2);
@@ -881,7 +886,7 @@ __global__ void __launch_bounds__(PRE ? 320 : 192) conv_tc_tma_kernel(const __gr
     x0 = (t2 % tiles_x) * TC_TW;
   };
 
-  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256 + tc_epi_strip_bytes_dev(Cout));
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512 + tc_epi_strip_bytes_dev(Cout));
   if constexpr (STATS)
     for (int i = tid; i < 2 * Cout; i += blockDim.x) s_stats[i] = 0.f;
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)tmem_cols);
@@ -932,7 +937,7 @@ __global__ void __launch_bounds__(PRE ? 320 : 192) conv_tc_tma_kernel(const __gr
           }
         }
       } else if (!out_f32)
-        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 256, warp, lane, n, y0, x0, H, W,
+        conv_tc_epilogue_coalesced(tmem_base + (uint32_t)(acc * Cout), reinterpret_cast<uint8_t*>(full) + 512, warp, lane, n, y0, x0, H, W,
                                    cstore, bias, reinterpret_cast<bf16*>(y), STATS ? s_stats : nullptr,
                                    (STATS && reg_stats) ? &est : nullptr);
       else
@@ -1044,6 +1049,10 @@ __global__ void __launch_bounds__(PRE ? 320 : 192) conv_tc_tma_kernel(const __gr
     for (int i = tid; i < 2 * Cout; i += blockDim.x) atomicAdd(&stats[i], (double)s_stats[i]);
 }
 
+static int g_persm_cap = 0;     // experiment: cap on resident CTAs per SM of the TMA conv kernel (0 = none)
+extern "C" int ttg_set_persm_cap(int n) { g_persm_cap = n; return TTG_OK; }
+static int g_nbuf_exp = 0;      // experiment: deeper activation rings (8 / 6 slots) for the 16 / 32-channel layers
+extern "C" int ttg_set_nbuf_exp(int on) { g_nbuf_exp = on; return TTG_OK; }
 static int g_use_swz = 1;       // A/B switch: pixel-major swizzled activation tiles in the TMA-fed conv kernel
 extern "C" int ttg_set_use_swz(int on) { g_use_swz = on ? 1 : 0; return TTG_OK; }
 static int g_use_tma = 1;       // 1: NHWC rank-5 map; 2/3: TIMING EXPERIMENTS (blocked layout / pixel-major rows; results are not a convolution)
@@ -1091,7 +1100,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ttg_set_error(TTG_ERR_CUDA, "conv2d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-  const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 256 + tc_epi_bytes(Cout);
+  const int smem = ((w_bytes + 127) & ~127) + NBUF * a_bytes + 512 + tc_epi_bytes(Cout);     // 512: mbarriers (up to 8 slots) + TMEM slot
   static int smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_tma_kernel<K, NBUF, CIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1102,6 +1111,7 @@ static int launch_conv_tc_tma(const void* x, const void* wp, const float* bias, 
   int per_sm = (200 * 1024) / smem;
   if (per_sm > 512 / pcols) per_sm = 512 / pcols;
   if (per_sm > 8) per_sm = 8;
+  if (g_persm_cap > 0 && per_sm > g_persm_cap) per_sm = g_persm_cap;
   if (per_sm < 1) per_sm = 1;
   if (pre_scale) {
     if constexpr (CIN > 0) {
@@ -2036,9 +2046,12 @@ static int conv2d_tc_core(const void* x, const void* wp, const float* bias, void
       int rc;
       // activation slots that fit next to the resident filter (256 -> 128 1x1: 64 KB filter + 64 KB tiles -> 2 slots)
       const bool three = ((w_bytes + 127) & ~127) + 3 * a_bytes + 256 + tc_epi_bytes(Cout) <= 227 * 1024;
-      if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 4, 16) : Cin == 32 ? TTG_TMA(3, 4, 32) : Cin == 64 ? TTG_TMA(3, 3, 64)
+      // ring depth: the pipeline of one CTA is latency bound (one CTA per SM reaches half the throughput of three), so the
+      // small tiles get 8 / 6 slots: 16->16 @128^2 80 -> 66 us, 32->32 @64^2 39 -> 37 us (round 2 sweep, tools/kb2.sh)
+      const bool four64 = ((w_bytes + 127) & ~127) + 4 * a_bytes + 256 + tc_epi_bytes(Cout) <= 200 * 1024;
+      if (ksize == 3) rc = Cin == 16 ? TTG_TMA(3, 8, 16) : Cin == 32 ? TTG_TMA(3, 6, 32) : Cin == 64 ? (four64 ? TTG_TMA(3, 4, 64) : TTG_TMA(3, 3, 64))
                                      : (deep ? TTG_TMA(3, 4, 0) : three ? TTG_TMA(3, 3, 0) : TTG_TMA(3, 2, 0));
-      else rc = Cin == 16 ? TTG_TMA(1, 4, 16) : Cin == 32 ? TTG_TMA(1, 4, 32) : Cin == 64 ? TTG_TMA(1, 3, 64)
+      else rc = Cin == 16 ? TTG_TMA(1, 8, 16) : Cin == 32 ? TTG_TMA(1, 8, 32) : Cin == 64 ? (four64 ? TTG_TMA(1, 4, 64) : TTG_TMA(1, 3, 64))
                           : (deep ? TTG_TMA(1, 4, 0) : three ? TTG_TMA(1, 3, 0) : TTG_TMA(1, 2, 0));
 #undef TTG_TMA
       if (rc != TTG_OK || used) return rc;
@@ -2240,9 +2253,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c8n = Cin >> 3;
   // fuse == 3 ("mfold", TMA only): the filter column kx is folded into M and the filter row ky into N, so a tile
-  // costs 8 MMAs instead of 24:  D[(kx, co), (ky, ci)] = sum_q gy[q - (kx-1)][co] * x[q + (ky-1) rows][ci].
-  // A = three copies of the gy tile fetched with column offsets +1, 0, -1 (stacked along M: [kx][co/8][128 px]),
-  // B = the x tile WITHOUT horizontal halo (whx = 8 columns), vertical taps reached through the N-group stride.
+  // costs 8 MMAs instead of 24:  D[(j, co), (ky, ci)] = sum_q gy[q + j - 1][co] * x[q + (ky-1) rows][ci],  kx = 2 - j.
+  // Both tiles are PIXEL-MAJOR (NHWC as in memory: one TMA request per pixel, SWIZZLE_32B/64B/128B by channel count),
+  // which is the MN-major canonical layout with one swizzle row per pixel:
+  //   A = gy^T: the gy tile with a one-column halo, [16 rows][10 cols][Cout]; the M block j is the same tile one pixel
+  //       further on (LBO = one pixel), K = the 8 pixels of a tile row (k-blocks SBO = one tile row apart);
+  //   B = x without horizontal halo, [18 rows][8 cols][Cin]; N block ky = one row further down (LBO = one row).
   const bool mfold = fuse == 3;
   const int whx = mfold ? TC_TW : WH;                   // columns of the staged x tile
   const uint32_t x_bytes = (uint32_t)c8n * HH * whx * 16;
@@ -2353,13 +2369,26 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       for (int it = 0; it < T; ++it) {
         const int s = it % NBUF;
         mbar_wait(&full[s], (uint32_t)(it / NBUF) & 1u);
-        // (mfold: the un-shifted copy of the gy tile is the middle one)
-        const uint8_t* gt = sG + (size_t)s * g_bytes + (size_t)((mfold ? g8n : 0) + g8) * NPIX * 16;
+        if (mfold) {
+          // pixel-major swizzled tile with a one-column halo: pixel (row, col) at halo index row * 10 + col + 1
+          const uint32_t gs = smem_u32(sG + (size_t)s * g_bytes);
+          for (int p = p0; p < NPIX; p += ppg) {
+            const uint32_t pa = gs + (uint32_t)(((p >> 3) * (TC_TW + 2) + (p & 7) + 1) * co_cnt * 2);
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(pa + (uint32_t)((g8 ^ (int)((pa >> 7) & (uint32_t)(g8n - 1))) << 4)));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { bs[2 * k] += __uint_as_float(w4[k] << 16); bs[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u); }
+          }
+        } else {
+        const uint8_t* gt = sG + (size_t)s * g_bytes + (size_t)g8 * NPIX * 16;
         for (int p = p0; p < NPIX; p += ppg) {
           const uint4 v = *reinterpret_cast<const uint4*>(gt + (size_t)p * 16);
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) { bs[2 * k] += __uint_as_float(w4[k] << 16); bs[2 * k + 1] += __uint_as_float(w4[k] & 0xffff0000u); }
+        }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -2392,9 +2421,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
             const int ky = row / Cin, ci = row - ky * Cin;
             dst = gw + ((long long)(ky * K + u) * Cin + ci) * Cout + co_base + c0;
           } else if (mfold) {                         // row = kx*Cout + co, column = ky*Cin + ci
-            const int kxi = row / co_cnt, cc = row - kxi * co_cnt;
+            const int jb = row / co_cnt, cc = row - jb * co_cnt;           // M block j <-> filter column kx = 2 - j
             const int ky = c0 / Cin, ci0 = c0 - ky * Cin;
-            dst = gw + ((long long)(ky * K + kxi) * Cout + cc) * Cin + ci0;
+            dst = gw + ((long long)(ky * K + (2 - jb)) * Cout + cc) * Cin + ci0;
           } else {
             const int ky = fuse ? c0 / Cin : 0, ci0 = fuse ? c0 - ky * Cin : c0;
             const int tap = fuse ? ky * K + u : u;
@@ -2422,12 +2451,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       const int rmax = min(TC_TH / 2, (H - y0_ + 1) >> 1);
       const bool leader = elect_one();
       if (leader && mfold) {
-        const uint64_t a0 = umma_desc(smem_u32(sG + (size_t)s * g_bytes), TC_TW * 16, NPIX * 16);
-        const uint64_t b0 = umma_desc(smem_u32(sX + (size_t)s * x_bytes), (uint32_t)(c8n * whx) * 16, (uint32_t)whx * 16);
+        const uint32_t gpix = (uint32_t)co_cnt * 2, grow = (uint32_t)(TC_TW + 2) * gpix;       // bytes per gy pixel / tile row
+        const uint32_t xrow = (uint32_t)TC_TW * (uint32_t)Cin * 2;                             // bytes per x tile row
+        const uint64_t a0 = umma_desc_sw(smem_u32(sG + (size_t)s * g_bytes), gpix, grow, umma_swz_layout_for(co_cnt));
+        const uint64_t b0 = umma_desc_sw(smem_u32(sX + (size_t)s * x_bytes), xrow, xrow, umma_swz_layout_for(Cin));
 #pragma unroll
         for (int r = 0; r < TC_TH / 2; ++r)
           if (r < rmax)
-            umma_bf16(tmem_base, a0 + (uint64_t)(2 * r * TC_TW), b0 + (uint64_t)(2 * r * c8n * whx), idesc,
+            umma_bf16(tmem_base, a0 + (uint64_t)((2 * r * grow) >> 4), b0 + (uint64_t)((2 * r * xrow) >> 4), idesc,
                       (it == 0 && r == 0) ? 0u : 1u);
         umma_commit(&empty[s]);
         if (it == T - 1) umma_commit(done);
@@ -2477,20 +2508,22 @@ __global__ void __launch_bounds__(256) conv_wgrad_tc_ws_kernel(const bf16* __res
       tile_coords(j, n, y0, x0);
       const uint32_t bar = smem_u32(&full[s]);
       const uint32_t gbytes_tile = (uint32_t)g8n * NPIX * 16;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + (mfold ? 3u : 1u) * gbytes_tile) : "memory");
+      if (mfold) {
+        const uint32_t gtile = (uint32_t)(TC_TH * (TC_TW + 2) * co_cnt * 2);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + gtile) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(x0), "r"(y0 - HALO), "r"(n), "r"(bar) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(sG + (size_t)s * g_bytes)), "l"(&tmap_g), "r"(0), "r"(x0 - 1), "r"(y0), "r"(n), "r"(bar) : "memory");
+        continue;
+      }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(x_bytes + gbytes_tile) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-          ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(mfold ? x0 : x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
+          ::"r"(smem_u32(sX + (size_t)s * x_bytes)), "l"(&tmap_x), "r"(0), "r"(x0 - HALO), "r"(0), "r"(y0 - HALO), "r"(n), "r"(bar)
           : "memory");
-      if (mfold) {
-#pragma unroll
-        for (int kxi = 0; kxi < 3; ++kxi)       // copy kxi holds gy[q - (kxi - 1)] for the pixels q of the tile
-          asm volatile(
-              "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-              ::"r"(smem_u32(sG + (size_t)s * g_bytes) + (uint32_t)kxi * gbytes_tile), "l"(&tmap_g), "r"(0), "r"(x0 + 1 - kxi), "r"(y0),
-                "r"(co_base >> 3), "r"(n), "r"(bar)
-              : "memory");
-      } else
       asm volatile(
           "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
           ::"r"(smem_u32(sG + (size_t)s * g_bytes)), "l"(&tmap_g), "r"(0), "r"(x0), "r"(y0), "r"(co_base >> 3), "r"(n), "r"(bar)
@@ -2515,7 +2548,22 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
   ttg_encode_tiled_fn enc = tma ? ttg_get_encode_tiled() : nullptr;
   if (!enc) tma = false;
   if (fuse == 3 && !tma) return ttg_set_error(TTG_ERR_UNSUPPORTED, "conv2d_wgrad_tc: the kx-folded variant needs the TMA path");
-  if (tma) {
+  if (tma && fuse == 3) {
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint64_t xd[4] = {(cuuint64_t)cin_real, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t xs[3] = {(cuuint64_t)cin_real * 2, (cuuint64_t)W * cin_real * 2, (cuuint64_t)H * W * cin_real * 2};
+    const cuuint32_t xb[4] = {(cuuint32_t)Cin, TC_TW, (cuuint32_t)(TC_TH + 2 * HALO), 1};
+    const cuuint64_t gd[4] = {(cuuint64_t)cout_real, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gs[3] = {(cuuint64_t)cout_real * 2, (cuuint64_t)W * cout_real * 2, (cuuint64_t)H * W * cout_real * 2};
+    const cuuint32_t gb[4] = {(cuuint32_t)Cout, TC_TW + 2, TC_TH, 1};
+    auto swz_of = [](int c) { return c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B; };
+    CUresult r1 = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), xd, xs, xb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swz_of(Cin), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gy), gd, gs, gb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      swz_of(Cout), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+      return ttg_set_error(TTG_ERR_CUDA, "conv2d_wgrad_tc: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+  } else if (tma) {
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const cuuint64_t xd[5] = {8, (cuuint64_t)W, (cuuint64_t)(cin_real / 8), (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t xs[4] = {(cuuint64_t)cin_real * 2, 16, (cuuint64_t)W * cin_real * 2, (cuuint64_t)H * W * cin_real * 2};
@@ -2550,6 +2598,8 @@ static int launch_wgrad_ws(const void* x, const void* gy, float* gw, int N, int 
 }
 
 static int g_wgrad_tc_smem[2] = {0, 0};
+static int g_wg_nbuf = 0, g_wg_persm = 0;     // experiments: ring depth / resident CTAs of the folded wgrad variant
+extern "C" int ttg_set_wgrad_tuning(int nbuf, int persm) { g_wg_nbuf = nbuf; g_wg_persm = persm; return TTG_OK; }
 static int g_use_mfold = 1;
 extern "C" int ttg_set_wgrad_mfold(int on) { g_use_mfold = on ? 1 : 0; return TTG_OK; }   // A/B switch (tools/kbench.py)
 
@@ -2635,7 +2685,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
     const bool in8_ = cin_real == 8 && Cin == 16, out8_ = cout_real == 8 && Cout == 16;
     const bool tma_ok = g_use_tma && up == 0 && (cin_real == Cin || in8_) && (cout_real == Cout || out8_) &&
                         ttg_get_encode_tiled() != nullptr;
-    const bool mfold = g_use_mfold && tma_ok && ksize == 3 && 3 * Cout <= 128 && 3 * Cin <= 256;
+    const bool mfold = g_use_mfold && tma_ok && ksize == 3 && (Cout == 16 || Cout == 32) && (Cin == 16 || Cin == 32 || Cin == 64);
     const bool swap_ok = !mfold && ksize == 3 && 3 * Cin <= 128 && Cout <= 128 && Cin > Cout;
     const int fuse = mfold ? 3 : swap_ok ? 2 : ((ksize == 3 && 3 * Cin <= 256) ? 1 : 0);
     const int units_total = mfold ? 1 : fuse ? 3 : taps;
@@ -2646,12 +2696,17 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
     upg = (units_total + wgroups - 1) / wgroups;                 // balance units over the groups
     const int wcols = (int)tmem_cols_for(upg * NU);
     const int x_bytes = mfold ? (Cin / 8) * (TC_TH + 2) * TC_TW * 16 : (Cin / 8) * HP * 16;
-    const int g_bytes = (mfold ? 3 : 1) * ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
-    const int reach = swap_ok ? 0 : ((mfold ? 3 * Cout <= 64 : Cout <= 64) ? 8 : 16) * TC_TH * TC_TW * 16;  // bytes an M=64 / M=128 A descriptor spans
+    const int g_bytes = mfold ? TC_TH * (TC_TW + 2) * Cout * 2 : ((Cout < 128 ? Cout : 128) / 8) * TC_TH * TC_TW * 16;
+    // bytes an M=64 / M=128 A descriptor spans from the start of a gy slot (mfold: the tile plus the three extra pixels
+    // the padding M block reaches past its end)
+    const int reach = swap_ok ? 0 : mfold ? g_bytes + 4 * Cout * 2 : (Cout <= 64 ? 8 : 16) * TC_TH * TC_TW * 16;
     // swapped orientation: the padding rows of the A operand (ky = 3) reach one halo row past the last x slot
     const int xpad = swap_ok ? 2 * (Cin / 8) * (TC_TW + 2 * halo) * 16 : 0;
     int nbuf = (200 * 1024 - reach) / (x_bytes + g_bytes);
-    if (nbuf > 4) nbuf = 4;
+    const int nbuf_cap = mfold ? (g_wg_nbuf > 0 ? g_wg_nbuf : 8) : 4;     // the folded variant's pipeline is latency bound: deeper ring
+    if (nbuf > nbuf_cap) nbuf = nbuf_cap;
+    if (nbuf == 5) nbuf = 4;
+    if (nbuf == 7) nbuf = 6;
     if (nbuf >= 2) {
       int wper_sm = 512 / wcols;
       int body = nbuf * (x_bytes + g_bytes);
@@ -2660,6 +2715,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
       const int wsmem = body + xpad + 1024;          // barriers + the bias partial sums
       if (wper_sm > (220 * 1024) / wsmem) wper_sm = (220 * 1024) / wsmem;
       if (wper_sm > 4) wper_sm = 4;
+      if (g_wg_persm > 0 && wper_sm > g_wg_persm) wper_sm = g_wg_persm;
       if (wper_sm < 1) wper_sm = 1;
       long long wsplits = (long long)ttg_num_sms() * wper_sm / (wgroups * halves);
       if (wsplits < 1) wsplits = 1;
@@ -2670,7 +2726,7 @@ static int wgrad_tc_core(const void* x, const void* gy, float* gw, float* gbias,
       dim3 wgrid((unsigned)wsplits, wgroups, halves);
 #define TTG_WG(KK, NB) launch_wgrad_ws<KK, NB>(x, gy, gwp, N, H, W, Cin, Cout, up, upg, fuse, wcols, g_bytes, wsmem, wgrid, cin_real, cout_real, gbias, &bias_done, st)
       int rc;
-      if (ksize == 3) rc = nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
+      if (ksize == 3) rc = nbuf == 8 ? TTG_WG(3, 8) : nbuf == 6 ? TTG_WG(3, 6) : nbuf == 4 ? TTG_WG(3, 4) : nbuf == 3 ? TTG_WG(3, 3) : TTG_WG(3, 2);
       else rc = nbuf == 4 ? TTG_WG(1, 4) : nbuf == 3 ? TTG_WG(1, 3) : TTG_WG(1, 2);
 #undef TTG_WG
       if (rc != TTG_OK) return rc;

@@ -47,6 +47,14 @@ def main():
             wp = ops._packed(wt, 0, 'tc')
             y = ops.empty_nhwc(n, cout, h, w, bf, 'cuda')
             fn = lambda: call('ttg_conv2d_tc', ptr(x), ptr(wp), None, ptr(y), n, h, w, cin, cout, k, 0, _lib.BF16)
+            if os.environ.get('KB_PRE'):        # fused BatchNorm + LeakyReLU prologue (and KB_UP=1: fused nearest upsample)
+                up = int(os.environ.get('KB_UP', '0'))
+                xs = ops.empty_nhwc(n, cin, h >> up, w >> up, bf, 'cuda'); xs.normal_()
+                sc = torch.rand(cin, device='cuda') + 0.5; sh = torch.randn(cin, device='cuda') * 0.3
+                pre = os.environ['KB_PRE'] == '1'
+                fn = lambda: call('ttg_conv2d_tc_pre', ptr(xs), ptr(wp), None, ptr(y), n, h, w, cin, cout, k, up, _lib.BF16,
+                                  ptr(sc) if pre else None, ptr(sh) if pre else None, 0.2)
+                nbytes = n * h * w * cout * 2 + n * (h >> up) * (w >> up) * cin * 2
         elif kind == 'convd':
             wp = ops._packed(wt, 0, 'direct')
             y = ops.empty_nhwc(n, cout, h, w, bf, 'cuda')
