@@ -251,7 +251,13 @@ def main():
                            'ms_per_step': ms / args.steps}, f, indent=1)
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # the step graphs hold captured NCCL collectives: release them before the communicator, never hang on teardown
+        from tartangan_b200.parallel import shutdown
+        sys.stdout.flush()
+        torch.distributed.barrier()
+        clean = shutdown([trainer])
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

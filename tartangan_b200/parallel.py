@@ -88,6 +88,22 @@ class BucketedAllReduce:
             h.remove()
 
 
+def shutdown(trainers=(), timeout_s=10.0):
+    """Leave a data-parallel job without hanging: release the trainers' CUDA graphs (they hold captured NCCL kernels),
+    then destroy the process group from a helper thread and give up on it after `timeout_s` (the caller is expected to
+    exit the process next; a communicator that refuses to die must not keep a finished job alive)."""
+    import threading
+    for t in trainers:
+        if hasattr(t, 'release_graphs'):
+            t.release_graphs()
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    th.start()
+    th.join(timeout_s)
+    return not th.is_alive()
+
+
 def shard_batch(global_batch, world, rank):
     """Contiguous per-rank slice of a global batch (strong-scaling helper)."""
     per = global_batch // world

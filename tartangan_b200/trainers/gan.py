@@ -305,12 +305,21 @@ class GanTrainer(Trainer):
             pool = g.pool()
             graphs.append(g)
 
-        overlap = False                           # exchanges happen between graphs
+        # Data parallel: the bucketed NCCL all-reduces are captured INSIDE the graph.  They are launched from the
+        # post-accumulate-grad hooks while backward is being captured; ProcessGroupNCCL forks its own stream off the
+        # capture stream at that point and `finish()` joins it back, so in the instantiated graph each bucket's
+        # exchange is a side branch that runs concurrently with the rest of backward (D: the R1 double backward and
+        # the trunk below the bucket; G: the blocks below the bucket).  One graph per step on any world size.
+        # TTG_DP_BLOCKING=1 keeps round 1's scheme (blocking all-reduce of the whole buffer between graph segments).
+        blocking = self.world_size > 1 and os.environ.get('TTG_DP_BLOCKING', '0') == '1'
+        overlap = not blocking
         def gen():
             with torch.no_grad():
                 out['fake'] = self.sample_g(b)
         seg(gen)                                  # needs no images: runs while the host batch is still in flight
-        if self.world_size == 1:
+        if not blocking:
+            if self.world_size > 1:               # build the reducers (and their hooks) before capturing
+                self._reducer(self.optimizer_d); self._reducer(self.optimizer_g)
             def rest():
                 out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
                 self.d_update()
@@ -360,6 +369,17 @@ class GanTrainer(Trainer):
         ops.state.pack_generation += 1
         o = self._graph_out
         return o['d_loss'], o['gp'], o['g_loss']
+
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (the next graphed step re-captures).  Call before
+        torch.distributed.destroy_process_group(): tearing the NCCL communicator down while instantiated graphs still
+        hold its captured collectives hangs (measured on torch 2.11 / NCCL 2.28)."""
+        torch.cuda.synchronize()
+        self._segments = None
+        self._graph_out = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
 
     def parameters_changed(self):
         """Call after parameters were modified outside the optimiser (load_state_dict, manual edits): drops every
