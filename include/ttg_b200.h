@@ -208,6 +208,17 @@ int ttg_iqn_head_fwd(const float* feats, const float* taus, const float* We, con
 int ttg_iqn_head_bwd(const float* g, const float* feats, const float* taus, const float* We, const float* be,
                      const float* wo, float* gf, float* gWe, float* gbe, float* gwo, float* gbo, int B, int nq,
                      int C, int E, void* stream);
+/* The whole IQN head in ONE forward and ONE backward kernel (blocks/discriminator.py:164-178): embedding + mix +
+ * Linear(C->1) (p_tau, rows r = q*B + b), the mean over quantiles p_mean [B] (:174-175) and iqn_loss (:111-130) against
+ * target [B] (NULL: no loss).  Backward: cotangents of p_mean and of the loss (either may be NULL) -> gradients of
+ * feats, We, be, wo, bo.  C <= 256, E <= 32. */
+int ttg_iqn_head_loss_fwd(const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                          const float* bo, const float* target, float* p_tau, float* p_mean, float* loss, int B, int nq,
+                          int C, int E, float k, void* stream);
+int ttg_iqn_head_loss_bwd(const float* g_pmean, const float* gloss, const float* p_tau, const float* target,
+                          const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                          float* gf, float* gWe, float* gbe, float* gwo, float* gbo, int B, int nq, int C, int E, float k,
+                          void* stream);
 int ttg_quantile_huber_fwd(const float* p_tau, const float* target, const float* taus, float* loss, int B, int nq,
                            float k, void* stream);
 int ttg_quantile_huber_bwd(const float* p_tau, const float* target, const float* taus, const float* gloss,

@@ -75,15 +75,141 @@ extern "C" int ttg_iqn_head_fwd(const float* feats, const float* taus, const flo
   return TTG_OK;
 }
 
+// ---------------------------------------------------------------- IQN head + quantile mean + quantile-Huber loss: ONE kernel
+// (blocks/discriminator.py:164-178 in one launch: models/iqn.py:91-103 embedding + mix, Linear(C->1), the mean over
+// quantiles p_target (:174-175) and iqn_loss (:111-130)).  One warp owns a batch row b and walks its nq quantile rows
+// r = q*B + b: the pooled features are read ONCE per batch row (registers), p_target needs no second pass over
+// p_tau and the loss terms of the row are summed in the same registers.  loss must be zero on entry.
+// Per batch row the cos(tau pi k) table of a chunk of <= 8 quantiles is written to a per-warp strip of shared memory
+// once and read back as broadcast LDS.128, the embedding row We[c][:] of a lane's channel lives in registers while the
+// lane walks the chunk: 5 vector loads per 20 FMAs (the first version shuffled every cosine to every lane for every
+// row and re-read We per row: LDS / SHFL bound at 10 % of the fp32 rate, 940 us per 2^20 quantile rows).
+#define IQN_QC 8
+#define IQN_EP 20            // embedding dims of the table rows (E <= 20 takes the fast path; E = 20 in the reference)
+template <int CPL>        // channels per lane = ceil(C / 32)
+__global__ void __launch_bounds__(256) iqn_head_loss_fwd_kernel(
+    const float* __restrict__ feats, const float* __restrict__ taus, const float* __restrict__ We,
+    const float* __restrict__ be, const float* __restrict__ wo, const float* __restrict__ bo,
+    const float* __restrict__ target, float* __restrict__ p_tau, float* __restrict__ p_mean,
+    float* __restrict__ loss, int B, int nq, int C, int E, float k) {
+  extern __shared__ __align__(16) float s_dyn[];   // cos tables [8 warps][IQN_QC][IQN_EP] + We [C][E+1] + be[C] + wo[C]
+  float* s_cs_all = s_dyn;
+  float* s_we = s_dyn + 8 * IQN_QC * IQN_EP;
+  const int ES = E + 1;
+  float* s_be = s_we + C * ES; float* s_wo = s_be + C;
+  for (int i = threadIdx.x; i < C * E; i += blockDim.x) s_we[(i / E) * ES + (i % E)] = We[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_be[i] = be[i]; s_wo[i] = wo[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float* s_cs = s_cs_all + warp * (IQN_QC * IQN_EP);
+  const float bias_o = bo ? bo[0] : 0.f;
+  float lacc = 0.f;
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    float f[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { const int c = lane + 32 * j; f[j] = c < C ? feats[(long long)b * C + c] * s_wo[c] : 0.f; }
+    const float tgt = target ? target[b] : 0.f;
+    float msum = 0.f;
+    for (int q0 = 0; q0 < nq; q0 += IQN_QC) {
+      const int nqc = min(IQN_QC, nq - q0);
+      __syncwarp();
+      for (int i = lane; i < nqc * IQN_EP; i += 32) {
+        const int q = i / IQN_EP, kk = i - q * IQN_EP;
+        s_cs[i] = kk < E ? cosf(taus[(q0 + q) * B + b] * 3.14159265358979323846f * (float)(kk + 1)) : 0.f;
+      }
+      __syncwarp();
+      float acc[IQN_QC];
+#pragma unroll
+      for (int q = 0; q < IQN_QC; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          float we[IQN_EP];
+#pragma unroll
+          for (int kk = 0; kk < IQN_EP; ++kk) we[kk] = kk < E ? s_we[c * ES + kk] : 0.f;
+          const float bec = s_be[c];
+#pragma unroll
+          for (int q = 0; q < IQN_QC; ++q) {
+            if (q < nqc) {
+              float pre = bec;
+              const float4* cs4 = reinterpret_cast<const float4*>(s_cs + q * IQN_EP);
+#pragma unroll
+              for (int v = 0; v < IQN_EP / 4; ++v) {
+                const float4 cv = cs4[v];
+                pre += cv.x * we[4 * v] + cv.y * we[4 * v + 1] + cv.z * we[4 * v + 2] + cv.w * we[4 * v + 3];
+              }
+              acc[q] += f[j] * fast_tanh(pre);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < IQN_QC; ++q) {
+        if (q < nqc) {
+          const float p = warp_sum(acc[q]) + bias_o;
+          msum += p;
+          if (lane == 0) {
+            const int r = (q0 + q) * B + b;
+            p_tau[r] = p;
+            if (target) {
+              const float err = tgt - p, mag = fabsf(err);
+              const float h = mag <= k ? 0.5f * err * err : k * (mag - 0.5f * k);
+              lacc += fabsf(taus[r] - (err < 0.f ? 1.f : 0.f)) * h;
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0 && p_mean) p_mean[b] = msum / (float)nq;
+  }
+  if (target && loss) {
+    __shared__ float s_l[8];
+    if (lane == 0) s_l[warp] = lacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < nwarp; ++w) t += s_l[w];
+      atomicAdd(loss, t / (float)B);
+    }
+  }
+}
+extern "C" int ttg_iqn_head_loss_fwd(const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                                     const float* bo, const float* target, float* p_tau, float* p_mean, float* loss, int B,
+                                     int nq, int C, int E, float k, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(E <= IQN_EP, "iqn_head_loss: embedding dims %d > %d", E, IQN_EP);
+  TTG_REQUIRE(C >= 1 && C <= 256, "iqn_head_loss: feature dims %d outside [1, 256]", C);
+  TTG_REQUIRE(p_tau != nullptr, "iqn_head_loss: p_tau is required (saved for backward)");
+  const size_t smem = sizeof(float) * (8 * IQN_QC * IQN_EP + (size_t)C * (E + 1) + 2 * C);
+  if (target && loss) cudaMemsetAsync(loss, 0, sizeof(float), st);
+  int grid = (B + 7) / 8;
+  if (grid > ttg_num_sms() * 8) grid = ttg_num_sms() * 8;
+#define TTG_IQN(CPL)                                                                                                    \
+  do {                                                                                                                  \
+    cudaFuncSetAttribute(iqn_head_loss_fwd_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    iqn_head_loss_fwd_kernel<CPL><<<grid, 256, smem, st>>>(feats, taus, We, be, wo, bo, target, p_tau, p_mean, loss, B, nq, C, E, k); \
+  } while (0)
+  if (C <= 32) TTG_IQN(1); else if (C <= 64) TTG_IQN(2); else if (C <= 128) TTG_IQN(4); else TTG_IQN(8);
+#undef TTG_IQN
+  TTG_CHECK_LAUNCH("iqn_head_loss_fwd");
+  return TTG_OK;
+}
+
 // ---------------------------------------------------------------- IQN head backward
 // g[r] = cotangent of p_tau[r] (the mean-over-quantiles cotangent is folded in by the caller).
 // Lane = channel; each warp walks a slice of the batch; per-channel partials reduced through
 // shared memory then fp32 atomics (outputs zeroed here).
+// g == nullptr: the cotangent of p_tau[r] is rebuilt on the fly from the cotangents of the head's two outputs,
+//   g[r] = g_pmean[b] / nq  +  gloss * d iqn_loss / d p_tau[r]          (either may be null)
+// which folds quantile_huber_bwd, the broadcast of the quantile mean's cotangent and their sum into this kernel.
 __global__ void __launch_bounds__(256) iqn_head_bwd_kernel(
     const float* __restrict__ g, const float* __restrict__ feats, const float* __restrict__ taus,
     const float* __restrict__ We, const float* __restrict__ be, const float* __restrict__ wo,
     float* __restrict__ gf, float* __restrict__ gWe, float* __restrict__ gbe, float* __restrict__ gwo,
-    float* __restrict__ gbo, int B, int nq, int C, int E) {
+    float* __restrict__ gbo, int B, int nq, int C, int E, const float* __restrict__ g_pmean = nullptr,
+    const float* __restrict__ gloss = nullptr, const float* __restrict__ p_tau = nullptr,
+    const float* __restrict__ target = nullptr, float hk = 1.f) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const bool live = c < C;
@@ -97,7 +223,18 @@ __global__ void __launch_bounds__(256) iqn_head_bwd_kernel(
     float a_gf = 0.f;
     for (int q = 0; q < nq; ++q) {
       const int r = q * B + b;
-      const float gr = g[r], tau = taus[r];
+      const float tau = taus[r];
+      float gr;
+      if (g) gr = g[r];
+      else {
+        gr = g_pmean ? g_pmean[b] / (float)nq : 0.f;
+        if (gloss) {
+          const float err = target[b] - p_tau[r];
+          const float w = fabsf(tau - (err < 0.f ? 1.f : 0.f));
+          const float dh = fabsf(err) <= hk ? err : (err > 0.f ? hk : -hk);
+          gr -= gloss[0] / (float)B * w * dh;
+        }
+      }
       float pre = bec, cs[IQN_MAX_E];
       iqn_cosines(tau, E, lane, cs);
 #pragma unroll
@@ -136,6 +273,26 @@ extern "C" int ttg_iqn_head_bwd(const float* g, const float* feats, const float*
   dim3 grid((C + 31) / 32, gy);
   iqn_head_bwd_kernel<<<grid, 256, 0, st>>>(g, feats, taus, We, be, wo, gf, gWe, gbe, gwo, gbo, B, nq, C, E);
   TTG_CHECK_LAUNCH("iqn_head_bwd");
+  return TTG_OK;
+}
+
+// backward of ttg_iqn_head_loss_fwd in ONE kernel: cotangents g_pmean [B] and gloss [1] (either may be NULL)
+extern "C" int ttg_iqn_head_loss_bwd(const float* g_pmean, const float* gloss, const float* p_tau, const float* target,
+                                     const float* feats, const float* taus, const float* We, const float* be, const float* wo,
+                                     float* gf, float* gWe, float* gbe, float* gwo, float* gbo, int B, int nq, int C, int E,
+                                     float k, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(E <= IQN_MAX_E, "iqn_head_loss: embedding dims %d > %d", E, IQN_MAX_E);
+  TTG_REQUIRE(gloss == nullptr || (p_tau != nullptr && target != nullptr), "iqn_head_loss_bwd: the loss cotangent needs p_tau and target");
+  if (gWe) cudaMemsetAsync(gWe, 0, sizeof(float) * (size_t)C * E, st);
+  if (gbe) cudaMemsetAsync(gbe, 0, sizeof(float) * C, st);
+  if (gwo) cudaMemsetAsync(gwo, 0, sizeof(float) * C, st);
+  if (gbo) cudaMemsetAsync(gbo, 0, sizeof(float), st);
+  int gy = (B + 7) / 8; if (gy > 64) gy = 64;
+  dim3 grid((C + 31) / 32, gy);
+  iqn_head_bwd_kernel<<<grid, 256, 0, st>>>(nullptr, feats, taus, We, be, wo, gf, gWe, gbe, gwo, gbo, B, nq, C, E, g_pmean, gloss, p_tau,
+                                            target, k);
+  TTG_CHECK_LAUNCH("iqn_head_loss_bwd");
   return TTG_OK;
 }
 

@@ -100,7 +100,7 @@ class DiscriminatorOutput(nn.Module):
 class IQNDiscriminatorOutput(nn.Module):
     """discriminator.py:149-178: BN -> act -> sum over H,W -> IQN mix -> Linear(C -> 1);
     returns the mean over quantiles and, when targets are given, the quantile-Huber loss.
-    The tau embedding, the mix and the Linear are ONE kernel (ops.IqnHeadFn)."""
+    The tau embedding, the mix, the Linear, the quantile mean and the loss are ONE kernel (ops.IqnHeadLossFn)."""
 
     def __init__(self, in_dims, out_dims, norm_factory=BatchNorm2d,
                  activation_factory=functools.partial(LeakyReLU, 0.2)):
@@ -120,11 +120,11 @@ class IQNDiscriminatorOutput(nn.Module):
         taus = self.iqn.sample_quantiles(batch)               # (nq*B, 1), CPU generator (Appendix B.10)
         emb = self.iqn.quantile_embedding.to_state[0]
         out = self.to_output[0]
-        p_tau = ops.IqnHeadFn.apply(feats, taus, emb.weight, emb.bias, out.weight, out.bias, nq)
-        p_target = ops.ColsumFn.apply(p_tau.view(nq, batch), 1.0 / nq).view(batch, 1)
+        # embedding + mix + Linear(C -> 1) + mean over quantiles + quantile-Huber loss: ONE kernel forward, ONE backward
         if targets is not None:
-            return p_target, iqn_loss(p_tau.view(-1, 1), targets, taus)
-        return p_target
+            assert not targets.requires_grad
+            return ops.IqnHeadLossFn.apply(feats, taus, emb.weight, emb.bias, out.weight, out.bias, targets, nq, 1.0)
+        return ops.IqnHeadLossFn.apply(feats, taus, emb.weight, emb.bias, out.weight, out.bias, None, nq, 1.0)
 
 
 class _Unsupported(nn.Module):

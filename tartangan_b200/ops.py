@@ -1117,6 +1117,93 @@ class IqnHeadBwdFn(Function):
         return cot_g, None, None, gwe, gbe, gwo, None
 
 
+class IqnHeadLossFn(Function):
+    """The whole IQN head in one launch (blocks/discriminator.py:164-178): (feats, taus, head parameters, target) ->
+    (p_target = mean over quantiles [B], quantile-Huber loss).  target=None: no loss (returned as None)."""
+
+    @staticmethod
+    def forward(ctx, feats, taus, we, be, wo, bo, target, nq, k):
+        feats, taus = _flat(feats), _flat(taus).reshape(-1)
+        b, c = feats.shape
+        e = we.shape[1]
+        dev = feats.device
+        p_tau = torch.empty(b * nq, dtype=torch.float32, device=dev)
+        p_mean = torch.empty(b, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev) if target is not None else None
+        tgt = _flat(target).reshape(-1).float() if target is not None else None
+        call('ttg_iqn_head_loss_fwd', ptr(feats), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), ptr(bo), ptr(tgt),
+             ptr(p_tau), ptr(p_mean), ptr(loss), b, nq, c, e, float(k))
+        ctx.save_for_backward(feats, taus, we, be, wo, tgt, p_tau)
+        ctx.nq, ctx.k, ctx.has_loss = nq, float(k), target is not None
+        ctx.set_materialize_grads(False)
+        if loss is None:
+            return p_mean.view(b, 1)
+        return p_mean.view(b, 1), loss
+
+    @staticmethod
+    def backward(ctx, g_pmean, g_loss=None):
+        feats, taus, we, be, wo, tgt, p_tau = ctx.saved_tensors
+        gf, gwe, gbe, gwo, gbo = IqnHeadLossBwdFn.apply(g_pmean, g_loss, feats, taus, we, be, wo, tgt, p_tau, ctx.nq, ctx.k)
+        if state.inputs_only:
+            gwe = gbe = gwo = gbo = None
+        return gf, None, gwe, gbe, gwo, gbo, None, None, None
+
+
+class IqnHeadLossBwdFn(Function):
+    """One kernel: cotangents of (p_target, loss) -> gradients of feats and the head parameters.  Differentiable once
+    more w.r.t. the p_target path (the R1 penalty, models/losses.py:23-26): d p_target / d feats does not depend on
+    feats, so the second backward re-uses the forward (feats := cotangent) and this kernel."""
+
+    @staticmethod
+    def forward(ctx, g_pmean, g_loss, feats, taus, we, be, wo, tgt, p_tau, nq, k):
+        b, c = feats.shape
+        e = we.shape[1]
+        dev = feats.device
+        gp = _flat(g_pmean).reshape(-1).float() if g_pmean is not None else None
+        gl = _flat(g_loss).reshape(-1).float() if g_loss is not None else None
+        gf = torch.empty((b, c), dtype=torch.float32, device=dev)
+        gwe = torch.empty((c, e), dtype=torch.float32, device=dev)
+        gbe = torch.empty(c, dtype=torch.float32, device=dev)
+        gwo = torch.empty(wo.shape, dtype=torch.float32, device=dev)
+        gbo = torch.empty(1, dtype=torch.float32, device=dev)
+        call('ttg_iqn_head_loss_bwd', ptr(gp), ptr(gl), ptr(p_tau), ptr(tgt), ptr(feats), ptr(taus), ptr(_flat(we)), ptr(be),
+             ptr(_flat(wo)), ptr(gf), ptr(gwe), ptr(gbe), ptr(gwo), ptr(gbo), b, nq, c, e, float(k))
+        ctx.save_for_backward(gp, taus, we, be, wo)
+        ctx.nq, ctx.loss_path = nq, g_loss is not None
+        ctx.set_materialize_grads(False)
+        return gf, gwe, gbe, gwo, gbo
+
+    @staticmethod
+    def backward(ctx, ggf, ggwe, ggbe, ggwo, ggbo):
+        if any(t is not None for t in (ggwe, ggbe, ggwo, ggbo)):
+            raise NotImplementedError('tartangan_b200: second derivatives of IQN-head parameter gradients are '
+                                      'not supported (the R1 penalty only differentiates d p / d feats)')
+        if ggf is None:
+            return (None,) * 11
+        if ctx.loss_path:
+            raise NotImplementedError('tartangan_b200: differentiating the IQN loss gradient a second time is not on the '
+                                      'reference path (the R1 penalty differentiates p_target only)')
+        gp, taus, we, be, wo = ctx.saved_tensors
+        ggf = _flat(ggf)
+        b, c = ggf.shape
+        e = we.shape[1]
+        dev = ggf.device
+        # gf[b, :] = (gp[b] / nq) * sum_q e(tau_qb) * wo  is linear in gp and independent of feats:
+        #   cot(gp)[b] = mean_q <ggf[b], e(tau_qb) * wo>  = the forward's quantile mean with feats := ggf (no bias, no loss)
+        scratch = torch.empty(b * ctx.nq, dtype=torch.float32, device=dev)
+        cot_gp = torch.empty(b, dtype=torch.float32, device=dev)
+        call('ttg_iqn_head_loss_fwd', ptr(ggf), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)), None, None, ptr(scratch),
+             ptr(cot_gp), None, b, ctx.nq, c, e, 1.0)
+        gwe = gbe = gwo = None
+        if not state.inputs_only:
+            gwe = torch.empty((c, e), dtype=torch.float32, device=dev)
+            gbe = torch.empty(c, dtype=torch.float32, device=dev)
+            gwo = torch.empty(wo.shape, dtype=torch.float32, device=dev)
+            call('ttg_iqn_head_loss_bwd', ptr(gp), None, None, None, ptr(ggf), ptr(taus), ptr(_flat(we)), ptr(be), ptr(_flat(wo)),
+                 None, ptr(gwe), ptr(gbe), ptr(gwo), None, b, ctx.nq, c, e, 1.0)
+        return cot_gp.view(-1, 1) if gp is not None else None, None, None, None, gwe, gbe, gwo, None, None, None, None
+
+
 class QuantileHuberFn(Function):
     """iqn_loss (models/iqn.py:111-130)."""
 

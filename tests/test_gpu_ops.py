@@ -162,6 +162,53 @@ def test_iqn_head_and_losses():
         assert rel(a, b_) < 2e-4
 
 
+def test_iqn_head_loss_single_kernel():
+    """ops.IqnHeadLossFn: the whole head (embedding, mix, Linear, quantile mean, quantile-Huber loss) as ONE forward
+    and ONE backward kernel, against torch autograd on the un-fused formula, incl. the R1 second-order path and
+    the no-target call (reference blocks/discriminator.py:164-178, models/iqn.py:91-130)."""
+    from tartangan_b200 import ops, _lib
+    from oracle.tartan_oracle import quantile_huber
+    for B, C, nq in ((6, 24, 8), (33, 128, 8), (5, 256, 64), (9, 16, 3)):
+        torch.manual_seed(3 + B)
+        E = 20
+        feats = torch.randn(B, C, requires_grad=True)
+        taus = torch.rand(B * nq, 1)
+        we = (torch.randn(C, E) * 0.3).requires_grad_()
+        be = (torch.randn(C) * 0.1).requires_grad_()
+        wo = (torch.randn(1, C) * 0.3).requires_grad_()
+        bo = torch.randn(1, requires_grad=True)
+        rng = torch.arange(1, E + 1).float()
+        emb = torch.tanh(F.linear(torch.cos(taus.repeat(1, E) * math.pi * rng), we, be))
+        p_tau = F.linear(feats.repeat(nq, 1) * emb, wo, bo)
+        targets = (torch.rand(B, 1) > 0.5).float()
+        loss = quantile_huber(p_tau, targets, taus)
+        p = p_tau.reshape(nq, -1, 1).mean(0)
+        coef = torch.randn(B, 1)
+        ref_g = torch.autograd.grad(1.7 * loss + (p * coef).sum(), (feats, we, be, wo, bo), retain_graph=True)
+        gfeat, = torch.autograd.grad(p.sum(), feats, create_graph=True)
+        ref2 = torch.autograd.grad((gfeat ** 2).sum(), (we, be, wo))
+
+        d = lambda t: t.detach().cuda().requires_grad_()
+        fd, wed, bed, wod, bod = d(feats), d(we), d(be), d(wo), d(bo)
+        td = taus.cuda()
+        k0 = _lib.Counters.kernels
+        p_d, loss_d = ops.IqnHeadLossFn.apply(fd, td, wed, bed, wod, bod, targets.cuda(), nq, 1.0)
+        assert _lib.Counters.kernels - k0 == 1
+        assert p_d.shape == (B, 1) and rel(p_d, p) < 1e-4 and rel(loss_d, loss) < 1e-4, (B, C, nq)
+        k0 = _lib.Counters.kernels
+        got = torch.autograd.grad((p_d, loss_d), (fd, wed, bed, wod, bod), (coef.cuda(), torch.tensor(1.7, device='cuda')),
+                                  retain_graph=True)
+        assert _lib.Counters.kernels - k0 == 1
+        for a, b_ in zip(got, ref_g):
+            assert rel(a, b_) < 2e-4, (B, C, nq)
+        gfeat_d, = torch.autograd.grad(p_d, fd, torch.ones_like(p_d), create_graph=True)
+        got2 = torch.autograd.grad(ops.SqsumFn.apply(gfeat_d, 1.0), (wed, bed, wod))
+        for a, b_ in zip(got2, ref2):
+            assert rel(a, b_) < 2e-4, (B, C, nq)
+        p_only = ops.IqnHeadLossFn.apply(fd, td, wed, bed, wod, bod, None, nq, 1.0)
+        assert rel(p_only, p) < 1e-4
+
+
 def test_bce_linear_adam():
     from tartangan_b200 import ops
     from tartangan_b200.optim import FusedAdam

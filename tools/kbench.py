@@ -118,7 +118,28 @@ def iqn(rows_b, c=128, nq=8):
     print(f'iqn_head bwd B={b}: {med*1e3:.1f} us  {nb/med/1e6:.0f} GB/s (fused bytes)')
 
 
-if sys.argv[1] == 'iqn':
+def iqn_fused(b, c=128, nq=8):
+    """The single-kernel IQN head (+ quantile mean + quantile-Huber loss) forward and backward at B batch rows
+    (B * nq quantile rows).  Algorithmic bytes: feats B*C*4 + taus / p_tau 2*B*nq*4 + p_mean / target 2*B*4 (forward);
+    feats + gf 2*B*C*4 + taus / p_tau (backward).  Arithmetic: B*nq*C*(2*E + ~12) fp32 flop + B*nq*C tanh (MUFU)."""
+    feats = torch.randn(b, c, device='cuda'); taus = torch.rand(b * nq, device='cuda')
+    we = torch.randn(c, 20, device='cuda') * .3; be = torch.zeros(c, device='cuda'); wo = torch.randn(c, device='cuda'); bo = torch.zeros(1, device='cuda')
+    p = torch.empty(b * nq, device='cuda'); pm = torch.empty(b, device='cuda'); tgt = torch.ones(b, device='cuda'); loss = torch.empty((), device='cuda')
+    gpm = torch.randn(b, device='cuda'); gl = torch.ones(1, device='cuda'); gf = torch.empty(b, c, device='cuda')
+    gwe = torch.empty(c, 20, device='cuda'); gbe = torch.empty(c, device='cuda'); gwo = torch.empty(c, device='cuda'); gbo = torch.empty(1, device='cuda')
+    fwd = lambda: call('ttg_iqn_head_loss_fwd', ptr(feats), ptr(taus), ptr(we), ptr(be), ptr(wo), ptr(bo), ptr(tgt), ptr(p), ptr(pm), ptr(loss), b, nq, c, 20, 1.0)
+    bwd = lambda: call('ttg_iqn_head_loss_bwd', ptr(gpm), ptr(gl), ptr(p), ptr(tgt), ptr(feats), ptr(taus), ptr(we), ptr(be), ptr(wo), ptr(gf), ptr(gwe), ptr(gbe), ptr(gwo), ptr(gbo), b, nq, c, 20, 1.0)
+    flop = b * nq * c * (2 * 20 + 12.0)
+    for name, fn, nb in (('fwd', fwd, b * c * 4 + 2 * b * nq * 4 + 2 * b * 4), ('bwd', bwd, 2 * b * c * 4 + 2 * b * nq * 4 + b * 4)):
+        med, best = timeit(fn)
+        print(f'iqn_head_loss {name} B={b} nq={nq} C={c} ({b*nq} quantile rows): median {med*1e3:.1f} us  algorithmic {nb/1e6:.2f} MB -> '
+              f'{nb/med/1e6:.0f} GB/s ({nb/med/1e6/6473.9*100:.1f} % of 6473.9)  fp32 {flop*(1 if name == "fwd" else 2.5)/med/1e9:.1f} TFLOP/s  '
+              f'tanh {b*nq*c/med/1e6:.0f} G/s')
+
+
+if sys.argv[1] == 'iqnf':
+    iqn_fused(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128, int(sys.argv[4]) if len(sys.argv) > 4 else 8)
+elif sys.argv[1] == 'iqn':
     iqn(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128)
 else:
     main()
