@@ -71,6 +71,57 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=s[len(s) // 2] if s else None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
 
 
+def _roof_time_ms(r, hbm, tflops):
+    """Roofline time of a profiler row: max(algorithmic bytes / HBM peak, flops / tensor peak), in ms."""
+    return max(r['bytes'] / (hbm * 1e9), r['flops'] / (tflops * 1e12)) * 1e3
+
+
+def _roofline(rows, by_name, step_ms_events, step_ms, img_s_per_gpu, hbm, tflops, which):
+    """The `roofline` object.  Leads with the STEP (images/s against the mixed roofline of SURVEY.md 8d), then the
+    dominant kernel FAMILY (the entry point with the largest share of device time) as a TIME-WEIGHTED fraction over
+    all its shapes: frac = sum(roofline time of each launch) / sum(measured time of each launch), where the
+    roofline time of a launch is max(algorithmic bytes / HBM peak, flops / tensor peak).  `achieved` is the family's
+    algorithmic bytes (or flops) divided by its measured time.  Every family with a cost model is listed the same
+    way under `families`; `top_shape` is the single (entry point, shape) with the most device time.
+    Per-launch durations: CUDA events around each launch of one EAGER step on the launching stream; the graphed step
+    that `value` reports is shorter than their sum (no launch gaps), which `events_vs_graph` states."""
+    fams = []
+    for f in by_name:
+        frows = [r for r in rows if r['name'] == f['name']]
+        modelled = [r for r in frows if r['bytes'] > 0]
+        t_meas = sum(r['ms'] for r in modelled)
+        entry = dict(name=f['name'], calls=f['calls'], ms=f['ms'], share_of_step=f['ms'] / max(step_ms_events, 1e-9))
+        if modelled and t_meas > 0:
+            t_roof = sum(_roof_time_ms(r, hbm, tflops) for r in modelled)
+            nbytes, flops = sum(r['bytes'] for r in modelled), sum(r['flops'] for r in modelled)
+            bound = 'tensor' if flops / (tflops * 1e12) > nbytes / (hbm * 1e9) else 'hbm'
+            entry.update(frac=t_roof / t_meas, bound=bound, gbs=nbytes / t_meas / 1e6, tflops=flops / t_meas / 1e9)
+        fams.append(entry)
+    lead = next((f for f in fams if 'frac' in f), None)
+    top = max((r for r in rows if r['bytes'] > 0), key=lambda r: r['ms'], default=None)
+    roof = dict(step_frac_of_mixed_roofline=img_s_per_gpu / ROOFLINE_IMG_S,
+                step_hbm_gbs=img_s_per_gpu * MB_PER_IMG / 1e3, step_tflops=img_s_per_gpu * GFLOP_PER_IMG / 1e3)
+    if lead is not None:
+        peak, unit = (tflops, 'TFLOP/s') if lead['bound'] == 'tensor' else (hbm, 'GB/s')
+        roof.update(bound=lead['bound'], achieved=lead['tflops'] if lead['bound'] == 'tensor' else lead['gbs'],
+                    peak=peak, unit=unit, frac=lead['frac'],
+                    traffic=None,        # DRAM bytes need ncu; the per-kernel captures are under profiles/ (r2_ncu_*.txt)
+                    kernel=lead['name'], share_of_step=lead['share_of_step'], launches_per_step=lead['calls'],
+                    frac_definition='time-weighted over every shape of the family: sum(max(bytes/HBM, flops/tensor '
+                                    'peak)) / sum(measured time); achieved = family bytes (or flops) / family time')
+    roof.update(peak_source=which, peak_hbm_gbs=hbm, peak_bf16_tflops=tflops,
+                events_vs_graph=dict(sum_of_eager_launch_events_ms=step_ms_events, graphed_step_ms=step_ms),
+                families=[{k: (round(v, 4) if isinstance(v, float) else v) for k, v in f.items()} for f in fams[:10]])
+    if top is not None:
+        per = top['ms'] / max(top['calls'], 1)
+        roof['top_shape'] = dict(kernel=top['name'], shape=top.get('key', ''), launches_per_step=top['calls'],
+                                 us_per_launch=per * 1e3, share_of_step=top['ms'] / max(step_ms_events, 1e-9),
+                                 algorithmic_bytes_per_launch=top['bytes'] / max(top['calls'], 1),
+                                 gbs=top['bytes'] / top['ms'] / 1e6, tflops=top['flops'] / top['ms'] / 1e9,
+                                 frac=_roof_time_ms(top, hbm, tflops) / top['ms'])
+    return roof
+
+
 def _oracle_step_time(batch, steps, warmup, threads):
     from oracle import tartan_oracle as O
     torch.set_num_threads(threads)
@@ -104,6 +155,8 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     batch = 8
+    # bounded sample: a CPU step of batch 8 takes ~0.15 s per image, so --steps / --warmup are clamped to 5 / 2 and
+    # the batch to 8 images (the line says so: `steps`, `warmup`, `config.note`)
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     sec = _oracle_step_time(batch, steps, warmup, threads)
     val = batch / sec
@@ -111,7 +164,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'SA-GAN-IQN G+D train images/sec at 128x128', 'value': val,
         'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f"trainers.iqn SA-GAN-IQN config '{CONFIG}' 128x128, CPU sample batch {batch}"},
+        'config': {'workload': f"trainers.iqn SA-GAN-IQN config '{CONFIG}' 128x128, CPU sample batch {batch}",
+                   'note': f'CPU arm: oracle port (torch CPU fp32, {threads} threads); requested --steps {args.steps} '
+                           f'--warmup {args.warmup} clamped to {steps} / {warmup} and the batch to {batch} images so the '
+                           'run stays within minutes; images/sec is per image, so the batch size does not scale it'},
         'cpu_baseline': {'value': val, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
                          'sample': f'{steps} train steps of batch {batch} (of the 256/GPU workload), torch CPU fp32'},
         'e2e': {'value': val, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -151,8 +207,7 @@ def main():
     trainer = make_trainer(IQNTrainer, config=CONFIG, batch_size=args.batch, precision=args.precision,
                            cuda_graph=not args.eager)
     torch.manual_seed(1000 + rank)           # z / tau stream
-    base = tartan_batch(1234 + rank, 32, SIZE)
-    host = base.repeat((args.batch + 31) // 32, 1, 1, 1)[:args.batch].contiguous().pin_memory()
+    host = tartan_batch(1234 + rank, args.batch, SIZE).contiguous().pin_memory()      # `batch` DISTINCT images
     dev = host.cuda()
 
     def barrier():
@@ -202,28 +257,7 @@ def main():
         hbm, tflops, which = _peaks()
         value = args.batch * world * args.steps / (ms / 1e3)
         e2e_val = args.batch * world * args.steps / e2e_s
-        # dominant kernel = the (entry point, shape) with the largest share of device time
-        fam = by_name[0]
-        cands = [r for r in rows if r['name'] == fam['name'] and r['bytes'] > 0] or [fam]
-        top = max(cands, key=lambda r: r['ms'])
-        per_launch_ms = top['ms'] / max(top['calls'], 1)
-        ai = top['flops'] / max(top['bytes'], 1)
-        if ai > (tflops * 1e12) / (hbm * 1e9):
-            achieved = top['flops'] / (top['ms'] / 1e3) / 1e12
-            roof = dict(bound='tensor', achieved=achieved, peak=tflops, unit='TFLOP/s', frac=achieved / tflops)
-        else:
-            achieved = top['bytes'] / (top['ms'] / 1e3) / 1e9
-            roof = dict(bound='hbm', achieved=achieved, peak=hbm, unit='GB/s', frac=achieved / hbm)
-        # DRAM traffic per launch from the committed `ncu --set full` capture of this kernel+shape (profiles/)
-        ncu_traffic = {('ttg_conv2d_tc', 'N256 128x128 16->16 k3 up0'): 229.6e6,       # profiles/r1_ncu_f_conv16.txt
-                       ('ttg_bn_act_bwd', 'M4194304 C16'): 637.6e6}                      # profiles/r1_ncu_f_bn_bwd.txt
-        roof.update(traffic=ncu_traffic.get((top['name'], top.get('key', ''))), kernel=top['name'], shape=top.get('key', ''),
-                    algorithmic_bytes_per_launch=top['bytes'] / max(top['calls'], 1), us_per_launch=per_launch_ms * 1e3,
-                    peak_source=which, launches_per_step=top['calls'],
-                    share_of_step=top['ms'] / max(step_ms_prof, 1e-9),
-                    family_share_of_step=fam['ms'] / max(step_ms_prof, 1e-9),
-                    step_frac_of_mixed_roofline=(value / world) / ROOFLINE_IMG_S,
-                    step_hbm_gbs=(value / world) * MB_PER_IMG / 1e3, step_tflops=(value / world) * GFLOP_PER_IMG / 1e3)
+        roof = _roofline(rows, by_name, step_ms_prof, ms / args.steps, value / world, hbm, tflops, which)
         line = {
             'metric': 'SA-GAN-IQN G+D train images/sec at 128x128', 'value': value, 'unit': 'images/sec',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,

@@ -42,6 +42,12 @@ int ttg_conv2d_direct(const void* x, const float* wp, const float* bias, void* y
                       int Cout, int ksize, int up, int dtype_in, int dtype_out, void* stream);
 int ttg_conv2d_wgrad_direct(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                             int ksize, int up, int dtype_x, int dtype_gy, void* stream);
+/* same, bitwise repeatable: every split of the pixel range writes its partial sums to its own slab of `workspace`
+ * (ttg_conv2d_wgrad_direct_workspace_bytes) and the slabs are added in a fixed order — the reference's CPU
+ * convolution_backward is run-to-run deterministic and so is the fp32 parity path. */
+size_t ttg_conv2d_wgrad_direct_workspace_bytes(int N, int H, int W, int Cin, int Cout, int ksize);
+int ttg_conv2d_wgrad_direct_det(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                                int ksize, int up, int dtype_x, int dtype_gy, void* workspace, void* stream);
 
 /* ---- tensor-core convolution (bf16 operands, fp32 accumulate in TMEM, tcgen05.mma)
  * same reference call sites as above; Cin, Cout multiples of 16.
@@ -137,6 +143,13 @@ int ttg_bn_act_bwd2(const void* x, const void* ga, const void* u, void* g_ga, vo
                     float* ggamma, void* workspace, int dtype, void* stream);
 int ttg_lrelu_fwd(const void* x, void* y, long long n, float slope, int dtype, void* stream);
 int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n, float slope, int dtype, void* stream);
+/* nn.ELU / nn.SELU (--activation elu|selu: trainers/cnn.py:41-45, trainers/iqn.py:42-45):
+ * f(x) = scale * (x > 0 ? x : alpha * (exp(x) - 1)).  _bwd: gx = g * f'(x);  _bwd2: out = g * u * f''(x), the cotangent
+ * of x through _bwd that the R1 penalty (models/losses.py:23-26) needs. */
+int ttg_elu_fwd(const void* x, void* y, long long n, float alpha, float scale, int dtype, void* stream);
+int ttg_elu_bwd(const void* x, const void* g, void* gx, long long n, float alpha, float scale, int dtype, void* stream);
+int ttg_elu_bwd2(const void* x, const void* g, const void* u, void* out, long long n, float alpha, float scale, int dtype,
+                 void* stream);
 /* conv bias gradient: out[c] = sum over rows of x[M,C] */
 int ttg_channel_sum(const void* x, long long M, int C, float* out, void* workspace, int dtype, void* stream);
 

@@ -82,8 +82,26 @@ def _bn(sd, key, x, norm):
     return out
 
 
+ACTIVATION = 'relu'   # --activation of trainers/cnn.py:41-45: 'relu' = LeakyReLU(0.2), 'selu' = nn.SELU, 'elu' = nn.ELU
+
+
 def _act(x):
+    if ACTIVATION == 'selu':
+        return F.selu(x)
+    if ACTIVATION == 'elu':
+        return F.elu(x)
     return F.leaky_relu(x, SLOPE)
+
+
+def init_params_selu(sd, names):
+    """trainers/cnn.py:96-105: vectors zeroed, everything else N(0, 1/fan_in), in parameter order (CPU generator)."""
+    for k in names:
+        d = sd[k]
+        if d.dim() == 1:
+            d.zero_()
+        else:
+            fan_in = d[0].numel()
+            d.normal_(std=math.sqrt(1. / fan_in))
 
 
 # Optional activation trace for the per-layer parity tests: set ``TRACE`` to a dict and every conv /
@@ -97,8 +115,22 @@ def _trace(key, out):
     return out
 
 
+def _sn_weight(sd, key):
+    """torch.nn.utils.spectral_norm semantics (the hooks tartangan/prep4web.py:33-51 strips; seam: conv_factory,
+    generator.py:34, discriminator.py:28,52): ONE power-iteration step per training forward updating u, v in place,
+    sigma = u^T W v with u, v treated as constants.  Pinned against torch itself in tests/test_oracle_golden.py."""
+    w, u, v = sd[key + '.weight_orig'], sd[key + '.weight_u'], sd[key + '.weight_v']
+    wm = w.reshape(w.shape[0], -1)
+    with torch.no_grad():
+        v.copy_(F.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+        u.copy_(F.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+    sigma = torch.dot(u.clone(), torch.mv(wm, v.clone()))
+    return w / sigma
+
+
 def _conv(sd, key, x, pad):
-    return _trace(key, F.conv2d(x, sd[key + '.weight'], sd.get(key + '.bias'), padding=pad))
+    w = _sn_weight(sd, key) if key + '.weight_orig' in sd else sd[key + '.weight']
+    return _trace(key, F.conv2d(x, w, sd.get(key + '.bias'), padding=pad))
 
 
 def _attention(sd, key, x):
@@ -131,7 +163,7 @@ def _g_block(sd, key, x, first, norm):
     projection at the upsampled resolution."""
     x = F.interpolate(x, scale_factor=2, mode='nearest')
     h = _residual_convs(sd, key, x, first, norm)
-    if key + '.project_input.0.weight' in sd:
+    if key + '.project_input.0.weight' in sd or key + '.project_input.0.weight_orig' in sd:
         x = _conv(sd, key + '.project_input.0', x, 0)
     return _trace(key, x + h)
 
@@ -141,7 +173,7 @@ def _d_block(sd, key, x, first, norm):
     align_corners=True) skip, projection after the down-sampling."""
     h = F.avg_pool2d(_residual_convs(sd, key, x, first, norm), 2)
     x = F.interpolate(x, scale_factor=0.5, mode='bilinear', align_corners=True)
-    if key + '.project_input.0.weight' in sd:
+    if key + '.project_input.0.weight' in sd or key + '.project_input.0.weight_orig' in sd:
         x = _conv(sd, key + '.project_input.0', x, 0)
     return _trace(key, x + h)
 
@@ -224,7 +256,7 @@ def iqn_discriminator(sd, spec, x, targets=None, norm='bn', taus=None,
     x, _ = _d_trunk(sd, spec, x, norm, 0, False)
     feats = _act(_bn(sd, 'to_output.activation.0', x, norm)).sum((2, 3))
     if taus is None:
-        taus = torch.rand(feats.shape[0] * num_quantiles, 1)
+        taus = torch.rand(feats.shape[0] * num_quantiles, 1).to(feats.device)
     return _iqn_head(sd, feats, taus, targets)
 
 
@@ -246,7 +278,8 @@ def _split(state_dict):
 
 def _is_param(name):
     return not (name.endswith('running_mean') or name.endswith('running_var')
-                or name.endswith('num_batches_tracked') or name.endswith('embedding_range'))
+                or name.endswith('num_batches_tracked') or name.endswith('embedding_range')
+                or name.endswith('weight_u') or name.endswith('weight_v'))
 
 
 class OracleTrainer:
@@ -256,8 +289,14 @@ class OracleTrainer:
 
     def __init__(self, kind, spec, g_state, target_g_state, d_state, batch_size,
                  lr_g=1e-4, lr_d=4e-4, lr_target_g=1e-3, grad_penalty=5.0,
-                 norm='bn', g_base='mlp', num_quantiles=NUM_QUANTILES):
+                 norm='bn', g_base='mlp', num_quantiles=NUM_QUANTILES, activation='relu', device='cpu'):
         self.kind, self.spec, self.batch_size = kind, spec, batch_size
+        self.activation = activation
+        # device != 'cpu' is used by tools/bench_eager_gpu.py only (the same composition through stock cuDNN / cuBLAS
+        # kernels, as a same-box library bar); z / tau are still drawn on the CPU like the reference does
+        self.device = torch.device(device)
+        g_state, target_g_state, d_state = ({k: v.to(self.device) for k, v in sd.items()}
+                                            for sd in (g_state, target_g_state, d_state))
         self.norm, self.g_base, self.nq = norm, g_base, num_quantiles
         self.grad_penalty, self.lr_target_g = grad_penalty, lr_target_g
         self.g, self.target_g, self.d = _split(g_state), _split(target_g_state), _split(d_state)
@@ -272,7 +311,7 @@ class OracleTrainer:
             sd[k].requires_grad_(on)
 
     def _fake(self, n):
-        z = torch.randn(n, self.spec.latent_dims)           # trainer.py:153-156
+        z = torch.randn(n, self.spec.latent_dims).to(self.device)           # trainer.py:153-156
         return generator(self.g, self.spec, z, self.norm, self.g_base)
 
     def _d(self, x, targets):
@@ -282,6 +321,14 @@ class OracleTrainer:
         return discriminator(self.d, self.spec, x, self.norm)
 
     def train_batch(self, imgs):
+        global ACTIVATION
+        prev, ACTIVATION = ACTIVATION, self.activation
+        try:
+            return self._train_batch(imgs)
+        finally:
+            ACTIVATION = prev
+
+    def _train_batch(self, imgs):
         b = self.batch_size
         # ---- D step
         self._toggle(self.g, self.g_params, False)
@@ -289,7 +336,7 @@ class OracleTrainer:
         self.opt_d.zero_grad()
         fake = self._fake(len(imgs))
         real = imgs.clone()
-        labels = torch.zeros(2 * len(imgs), 1)
+        labels = torch.zeros(2 * len(imgs), 1, device=self.device)
         labels[:len(imgs)] = 1
         if self.grad_penalty:
             real.requires_grad_()
@@ -314,7 +361,7 @@ class OracleTrainer:
         self._toggle(self.d, self.d_params, False)
         self.opt_g.zero_grad()
         fake = self._fake(len(imgs))
-        ones = torch.ones(len(fake), 1)
+        ones = torch.ones(len(fake), 1, device=self.device)
         if self.kind == 'iqn':
             _, g_loss = self._d(fake, ones)
         else:

@@ -227,104 +227,112 @@ extern "C" int ttg_dot_f32out(const void* a, const void* b, float* out, long lon
 }
 
 // ---------------------------------------------------------------- spectral norm power iteration
-// W is [rows, cols] fp32 row-major (conv weight viewed (Cout, Cin*k*k)).  Per iteration:
-//   v = normalize(W^T u)   (thread per column, coalesced across the warp)
-//   u = normalize(W v)     (warp per row, float4 loads, shuffle reduction)
-// then sigma = u^T W v and w_out = W / sigma.  workspace: 4 floats + rows + cols floats.
-__global__ void sn_wtu_kernel(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ vraw,
-                              float* __restrict__ norms, int rows, int cols) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  float s = 0.f;
-  if (c < cols) { for (int r = 0; r < rows; ++r) s += w[(long long)r * cols + c] * u[r]; vraw[c] = s; }
-  float sq = warp_sum(c < cols ? s * s : 0.f);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&norms[0], sq);
+// W is [rows, cols] fp32 row-major (conv weight viewed (Cout, Cin*k*k), at most 256 x 2304 = 2.4 MB, L2 resident).
+// ONE launch of ONE 1024-thread CTA per call (the matrices are tiny; a launch costs more than the arithmetic):
+//   per iteration  v = normalize(W^T u)   (thread per column, coalesced across the warp)
+//                  u = normalize(W v)     (warp per row, shuffle reduction)
+//   then sigma = u^T W v and w_out = W / sigma.  Fixed summation order: bitwise repeatable from run to run.
+// u / v live in shared memory between the phases; `workspace` is unused (kept in the ABI).
+__device__ __forceinline__ float sn_block_sum(float x, float* red) {      // all threads get the total
+  x = warp_sum(x);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();                       // (red may still be read from the previous call)
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];
+  return t;
 }
-__global__ void sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ vraw, float* __restrict__ v,
-                             float* __restrict__ uraw, float* __restrict__ norms, int rows, int cols, float eps) {
-  const int lane = threadIdx.x & 31; const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const float inv = 1.f / fmaxf(sqrtf(norms[0]), eps);
-  if (blockIdx.x == 0) for (int c = threadIdx.x; c < cols; c += blockDim.x) v[c] = vraw[c] * inv;
-  if (warp < rows) {
-    float s = 0.f;
-    const float* wr = w + (long long)warp * cols;
-    for (int c = lane; c < cols; c += 32) s += wr[c] * vraw[c];
-    s = warp_sum(s) * inv;
-    if (lane == 0) { uraw[warp] = s; atomicAdd(&norms[1], s * s); }
+// n_iter == 0: eval mode, sigma from the stored u, v without updating them
+__global__ void __launch_bounds__(1024) sn_fused_kernel(const float* __restrict__ w, float* __restrict__ u_g, float* __restrict__ v_g,
+                                                        float* __restrict__ w_out, float* __restrict__ sigma_g, int rows, int cols,
+                                                        int n_iter, float eps) {
+  extern __shared__ float sn_smem[];
+  float* u = sn_smem; float* v = u + rows; float* wv = v + cols; float* red = wv + rows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int r = tid; r < rows; r += blockDim.x) u[r] = u_g[r];
+  for (int c = tid; c < cols; c += blockDim.x) v[c] = v_g[c];
+  __syncthreads();
+  for (int it = 0; it < n_iter; ++it) {
+    float sq = 0.f;
+    for (int c = tid; c < cols; c += blockDim.x) {
+      float a = 0.f;
+      for (int r = 0; r < rows; ++r) a += w[(long long)r * cols + c] * u[r];
+      v[c] = a; sq += a * a;
+    }
+    const float inv_v = 1.f / fmaxf(sqrtf(sn_block_sum(sq, red)), eps);
+    for (int c = tid; c < cols; c += blockDim.x) v[c] *= inv_v;
+    __syncthreads();
+    sq = 0.f;
+    for (int r = warp; r < rows; r += nw) {
+      const float* wr = w + (long long)r * cols;
+      float a = 0.f;
+      for (int c = lane; c < cols; c += 32) a += wr[c] * v[c];
+      a = warp_sum(a);
+      if (lane == 0) { u[r] = a; sq += a * a; }
+    }
+    const float inv_u = 1.f / fmaxf(sqrtf(sn_block_sum(sq, red)), eps);
+    for (int r = tid; r < rows; r += blockDim.x) u[r] *= inv_u;
+    __syncthreads();
   }
+  // sigma = u^T (W v)
+  float part = 0.f;
+  for (int r = warp; r < rows; r += nw) {
+    const float* wr = w + (long long)r * cols;
+    float a = 0.f;
+    for (int c = lane; c < cols; c += 32) a += wr[c] * v[c];
+    a = warp_sum(a);
+    if (lane == 0) part += a * u[r];
+  }
+  const float sigma = sn_block_sum(part, red);
+  const float inv = 1.f / sigma;
+  const long long n = (long long)rows * cols;
+  for (long long i = tid; i < n; i += blockDim.x) w_out[i] = w[i] * inv;
+  if (n_iter > 0) {
+    for (int r = tid; r < rows; r += blockDim.x) u_g[r] = u[r];
+    for (int c = tid; c < cols; c += blockDim.x) v_g[c] = v[c];
+  }
+  if (tid == 0) sigma_g[0] = sigma;
 }
-__global__ void sn_u_kernel(const float* __restrict__ uraw, float* __restrict__ u, float* __restrict__ norms,
-                            float* __restrict__ sigma, int rows, float eps, int last) {
-  const float n = sqrtf(norms[1]);
-  const float inv = 1.f / fmaxf(n, eps);
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) u[r] = uraw[r] * inv;
-  if (r == 0) { sigma[0] = norms[1] * inv; }   // u^T W v with the normalised u
-  (void)last;
-}
-__global__ void sn_reset_kernel(float* norms) { norms[0] = 0.f; norms[1] = 0.f; }
-__global__ void sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ sigma, float* __restrict__ o, long long n) {
-  const float inv = 1.f / sigma[0];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = w[i] * inv;
+static int sn_launch(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols, int n_iter, float eps,
+                     cudaStream_t st, const char* name) {
+  TTG_REQUIRE(rows > 0 && cols > 0 && rows + cols <= 8192, "spectral_norm: matrix too large for the single-CTA kernel");
+  const size_t smem = sizeof(float) * (size_t)(2 * rows + cols + 32);
+  sn_fused_kernel<<<1, 1024, smem, st>>>(w, u, v, w_out, sigma, rows, cols, n_iter, eps);
+  TTG_CHECK_LAUNCH(name);
+  return TTG_OK;
 }
 extern "C" int ttg_spectral_norm(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
                                  int n_iter, float eps, void* workspace, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+  (void)workspace;
   TTG_REQUIRE(n_iter >= 1, "spectral_norm: n_iter must be >= 1");
-  float* norms = (float*)workspace; float* vraw = norms + 4; float* uraw = vraw + cols;
-  for (int it = 0; it < n_iter; ++it) {
-    sn_reset_kernel<<<1, 1, 0, st>>>(norms);
-    sn_wtu_kernel<<<(cols + 127) / 128, 128, 0, st>>>(w, u, vraw, norms, rows, cols);
-    sn_wv_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, vraw, v, uraw, norms, rows, cols, eps);
-    sn_u_kernel<<<(rows + 127) / 128, 128, 0, st>>>(uraw, u, norms, sigma, rows, eps, it == n_iter - 1);
-  }
-  TTG_CHECK_LAUNCH("spectral_norm_iter");
-  sn_scale_kernel<<<ttg_grid_for((long long)rows * cols, 1024), 256, 0, st>>>(w, sigma, w_out, (long long)rows * cols);
-  TTG_CHECK_LAUNCH("spectral_norm_scale");
-  return TTG_OK;
+  return sn_launch(w, u, v, w_out, sigma, rows, cols, n_iter, eps, (cudaStream_t)stream, "spectral_norm");
 }
 // eval mode: sigma = u^T W v with the given (already normalised) u, v; no update
-__global__ void sn_sigma_kernel(const float* __restrict__ w, const float* __restrict__ u, const float* __restrict__ v,
-                                float* __restrict__ norms, int rows, int cols) {
-  const int lane = threadIdx.x & 31; const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (warp < rows) {
-    float s = 0.f;
-    const float* wr = w + (long long)warp * cols;
-    for (int c = lane; c < cols; c += 32) s += wr[c] * v[c];
-    s = warp_sum(s);
-    if (lane == 0) atomicAdd(&norms[0], s * u[warp]);
-  }
-}
-__global__ void sn_copy_sigma_kernel(const float* norms, float* sigma) { sigma[0] = norms[0]; }
 extern "C" int ttg_spectral_norm_sigma(const float* w, const float* u, const float* v, float* w_out, float* sigma, int rows,
                                        int cols, void* workspace, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  float* norms = (float*)workspace;
-  sn_reset_kernel<<<1, 1, 0, st>>>(norms);
-  sn_sigma_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, u, v, norms, rows, cols);
-  sn_copy_sigma_kernel<<<1, 1, 0, st>>>(norms, sigma);
-  sn_scale_kernel<<<ttg_grid_for((long long)rows * cols, 1024), 256, 0, st>>>(w, sigma, w_out, (long long)rows * cols);
-  TTG_CHECK_LAUNCH("spectral_norm_sigma");
-  return TTG_OK;
+  (void)workspace;
+  return sn_launch(w, (float*)u, (float*)v, w_out, sigma, rows, cols, 0, 0.f, (cudaStream_t)stream, "spectral_norm_sigma");
 }
-// g_w = (g - dot(g, w_out) * u v^T) / sigma
-__global__ void sn_bwd_kernel(const float* __restrict__ g, const float* __restrict__ u, const float* __restrict__ v,
-                              const float* __restrict__ sigma, const double* __restrict__ dot, float* __restrict__ gw, int rows, int cols) {
-  const float inv = 1.f / sigma[0]; const float d = (float)dot[0];
+// g_w = (g - dot(g, w_out) * u v^T) / sigma   (u, v constants: torch.nn.utils.spectral_norm detaches them); one launch
+__global__ void __launch_bounds__(1024) sn_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ w_out,
+                                                            const float* __restrict__ u, const float* __restrict__ v,
+                                                            const float* __restrict__ sigma, float* __restrict__ gw, int rows, int cols) {
+  __shared__ float red[32];
   const long long n = (long long)rows * cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    int r = (int)(i / cols), c = (int)(i % cols);
+  float part = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) part += g[i] * w_out[i];
+  const float d = sn_block_sum(part, red);
+  const float inv = 1.f / sigma[0];
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
     gw[i] = (g[i] - d * u[r] * v[c]) * inv;
   }
 }
 extern "C" int ttg_spectral_norm_bwd(const float* g, const float* w_out, const float* u, const float* v, const float* sigma,
                                      float* gw, int rows, int cols, void* workspace, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  double* ws = (double*)workspace;
-  long long n = (long long)rows * cols;
-  cudaMemsetAsync(ws, 0, sizeof(double), st);
-  dot_kernel<float><<<ttg_grid_for(n, 2048, 4), 256, 0, st>>>(g, w_out, ws, n);
-  TTG_CHECK_LAUNCH("spectral_norm_bwd_dot");
-  sn_bwd_kernel<<<ttg_grid_for(n, 1024), 256, 0, st>>>(g, u, v, sigma, ws, gw, rows, cols);
+  (void)workspace;
+  sn_bwd_fused_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, w_out, u, v, sigma, gw, rows, cols);
   TTG_CHECK_LAUNCH("spectral_norm_bwd");
   return TTG_OK;
 }

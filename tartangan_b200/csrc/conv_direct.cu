@@ -121,11 +121,13 @@ extern "C" int ttg_conv2d_direct(const void* x, const float* wp, const float* bi
 
 // ------------------------------------------------------------------ wgrad
 // Block = 16 output channels x 16 input channels (x K*K taps in registers), looping over the
-// pixel tiles of its slice; partial sums are added with fp32 atomics into gw (OIHW, zeroed here).
+// pixel tiles of its slice.  Split-K over blockIdx.z: with a workspace every split writes its partial sums to its own
+// slab and a second kernel adds the slabs in a FIXED order (bitwise repeatable, like the reference's CPU path);
+// without one (legacy entry point) the partial sums are added with fp32 atomics into gw (OIHW, zeroed here).
 #define WG_C 16
 template <typename TX, typename TG, int K>
 __global__ void __launch_bounds__(WG_C * WG_C) conv_wgrad_direct_kernel(
-    const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw,
+    const TX* __restrict__ x, const TG* __restrict__ gy, float* __restrict__ gw, float* __restrict__ partial,
     int N, int H, int W, int Cin, int Cout, int up, int tiles_per_img, int nsplit) {
   constexpr int HALO = K / 2;
   constexpr int SH = CD_TH + 2 * HALO, SW = CD_TW + 2 * HALO;
@@ -171,15 +173,27 @@ __global__ void __launch_bounds__(WG_C * WG_C) conv_wgrad_direct_kernel(
     __syncthreads();
   }
   if (ci0 + ci < Cin && co0 + co < Cout) {
-    float* dst = gw + ((long long)(co0 + co) * Cin + ci0 + ci) * K * K;
+    const long long off = ((long long)(co0 + co) * Cin + ci0 + ci) * K * K;
+    if (partial) {
+      float* dst = partial + (long long)blockIdx.z * Cout * Cin * K * K + off;
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) atomicAdd(dst + t, acc[t]);
+      for (int t = 0; t < K * K; ++t) dst[t] = acc[t];
+    } else {
+      float* dst = gw + off;
+#pragma unroll
+      for (int t = 0; t < K * K; ++t) atomicAdd(dst + t, acc[t]);
+    }
   }
 }
-
-template <typename TX, typename TG>
-static int launch_wgrad_direct(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int k,
-                               int up, cudaStream_t st) {
+// gw[i] = sum over the splits, in split order (fixed summation order)
+__global__ void wgrad_direct_reduce_kernel(const float* __restrict__ partial, float* __restrict__ gw, long long n, int nsplit) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int s = 0; s < nsplit; ++s) a += partial[(long long)s * n + i];
+  gw[i] = a;
+}
+static int wgrad_direct_nsplit(int N, int H, int W, int Cin, int Cout) {
   int tiles = ((W + CD_TW - 1) / CD_TW) * ((H + CD_TH - 1) / CD_TH);
   int gx = (Cin + WG_C - 1) / WG_C, gyb = (Cout + WG_C - 1) / WG_C;
   long long total_tiles = (long long)N * tiles;
@@ -187,22 +201,45 @@ static int launch_wgrad_direct(const void* x, const void* gy, float* gw, int N, 
   if (nsplit > total_tiles) nsplit = (int)total_tiles;
   if (nsplit > 65535) nsplit = 65535;
   if (nsplit < 1) nsplit = 1;
+  return nsplit;
+}
+
+template <typename TX, typename TG>
+static int launch_wgrad_direct(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout, int k,
+                               int up, float* partial, cudaStream_t st) {
+  int tiles = ((W + CD_TW - 1) / CD_TW) * ((H + CD_TH - 1) / CD_TH);
+  int gx = (Cin + WG_C - 1) / WG_C, gyb = (Cout + WG_C - 1) / WG_C;
+  const int nsplit = wgrad_direct_nsplit(N, H, W, Cin, Cout);
   dim3 grid(gx, gyb, nsplit);
-  cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)Cout * Cin * k * k, st);
-  if (k == 3) conv_wgrad_direct_kernel<TX, TG, 3><<<grid, WG_C * WG_C, 0, st>>>((const TX*)x, (const TG*)gy, gw, N, H, W, Cin, Cout, up, tiles, nsplit);
-  else conv_wgrad_direct_kernel<TX, TG, 1><<<grid, WG_C * WG_C, 0, st>>>((const TX*)x, (const TG*)gy, gw, N, H, W, Cin, Cout, up, tiles, nsplit);
+  const long long n = (long long)Cout * Cin * k * k;
+  if (!partial) cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)n, st);
+  if (k == 3) conv_wgrad_direct_kernel<TX, TG, 3><<<grid, WG_C * WG_C, 0, st>>>((const TX*)x, (const TG*)gy, gw, partial, N, H, W, Cin, Cout, up, tiles, nsplit);
+  else conv_wgrad_direct_kernel<TX, TG, 1><<<grid, WG_C * WG_C, 0, st>>>((const TX*)x, (const TG*)gy, gw, partial, N, H, W, Cin, Cout, up, tiles, nsplit);
   TTG_CHECK_LAUNCH("conv2d_wgrad_direct");
+  if (partial) {
+    wgrad_direct_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, gw, n, nsplit);
+    TTG_CHECK_LAUNCH("conv2d_wgrad_direct_reduce");
+  }
   return TTG_OK;
 }
 
 // x: [N, H>>up, W>>up, Cin], gy: [N,H,W,Cout]; gw: fp32 [Cout][Cin][k][k] (overwritten).
+extern "C" size_t ttg_conv2d_wgrad_direct_workspace_bytes(int N, int H, int W, int Cin, int Cout, int ksize) {
+  return sizeof(float) * (size_t)wgrad_direct_nsplit(N, H, W, Cin, Cout) * Cout * Cin * ksize * ksize;
+}
+// workspace != NULL (ttg_conv2d_wgrad_direct_workspace_bytes): deterministic fixed-order split-K reduction
+extern "C" int ttg_conv2d_wgrad_direct_det(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
+                                           int ksize, int up, int dtype_x, int dtype_gy, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  float* ws = (float*)workspace;
+  TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad_direct: ksize %d unsupported", ksize);
+  if (dtype_x == TTG_F32 && dtype_gy == TTG_F32) return launch_wgrad_direct<float, float>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, ws, st);
+  if (dtype_x == TTG_BF16 && dtype_gy == TTG_BF16) return launch_wgrad_direct<bf16, bf16>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, ws, st);
+  if (dtype_x == TTG_F32 && dtype_gy == TTG_BF16) return launch_wgrad_direct<float, bf16>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, ws, st);
+  if (dtype_x == TTG_BF16 && dtype_gy == TTG_F32) return launch_wgrad_direct<bf16, float>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, ws, st);
+  return ttg_set_error(TTG_ERR_ARG, "conv2d_wgrad_direct: bad dtypes");
+}
 extern "C" int ttg_conv2d_wgrad_direct(const void* x, const void* gy, float* gw, int N, int H, int W, int Cin, int Cout,
                                        int ksize, int up, int dtype_x, int dtype_gy, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  TTG_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad_direct: ksize %d unsupported", ksize);
-  if (dtype_x == TTG_F32 && dtype_gy == TTG_F32) return launch_wgrad_direct<float, float>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, st);
-  if (dtype_x == TTG_BF16 && dtype_gy == TTG_BF16) return launch_wgrad_direct<bf16, bf16>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, st);
-  if (dtype_x == TTG_F32 && dtype_gy == TTG_BF16) return launch_wgrad_direct<float, bf16>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, st);
-  if (dtype_x == TTG_BF16 && dtype_gy == TTG_F32) return launch_wgrad_direct<bf16, float>(x, gy, gw, N, H, W, Cin, Cout, ksize, up, st);
-  return ttg_set_error(TTG_ERR_ARG, "conv2d_wgrad_direct: bad dtypes");
+  return ttg_conv2d_wgrad_direct_det(x, gy, gw, N, H, W, Cin, Cout, ksize, up, dtype_x, dtype_gy, nullptr, stream);
 }

@@ -381,6 +381,43 @@ extern "C" int ttg_lrelu_bwd(const void* x, const void* g, void* gx, long long n
   return TTG_OK;
 }
 
+// ---------------------------------------------------------------- ELU / SELU (--activation elu|selu, trainers/cnn.py:41-45)
+// f(x) = scale * (x > 0 ? x : alpha * (exp(x) - 1));  nn.ELU: alpha 1, scale 1;  nn.SELU: alpha 1.6732632..., scale 1.0507009...
+// order 0: y = f(x);  order 1: out = g * f'(x);  order 2: out = g * u * f''(x)  (the x-cotangent of the order-1 op under R1)
+template <typename T, int ORDER> struct EluOp : NoParams {
+  static constexpr int NIN = ORDER + 1, NOUT = 1;
+  const T* in[ORDER + 1]; T* out[1]; float alpha, scale;
+  template <int V> __device__ __forceinline__ void apply(const float* v, int, const P<V>&, float* o) const {
+    const float x = v[0];
+    const float e = scale * alpha * __expf(fminf(x, 0.f));        // = f'(x) = f''(x) for x <= 0
+    if constexpr (ORDER == 0) o[0] = x > 0.f ? scale * x : scale * alpha * expm1f(x);
+    else if constexpr (ORDER == 1) o[0] = v[1] * (x > 0.f ? scale : e);
+    else o[0] = x > 0.f ? 0.f : v[1] * v[2] * e;
+  }
+};
+template <int ORDER>
+static int elu_launch(const char* name, const void* x, const void* a, const void* b, void* out, long long n, float alpha,
+                      float scale, int dtype, void* stream) {
+  TTG_DISPATCH(dtype, {
+    EluOp<T, ORDER> op; op.in[0] = (const T*)x;
+    if constexpr (ORDER >= 1) op.in[1] = (const T*)a;
+    if constexpr (ORDER >= 2) op.in[2] = (const T*)b;
+    op.out[0] = (T*)out; op.alpha = alpha; op.scale = scale;
+    return launch_chan_map<T>(name, op, n, (n % 8 == 0) ? 8 : 1, (cudaStream_t)stream);
+  });
+  return TTG_OK;
+}
+extern "C" int ttg_elu_fwd(const void* x, void* y, long long n, float alpha, float scale, int dtype, void* stream) {
+  return elu_launch<0>("elu_fwd", x, nullptr, nullptr, y, n, alpha, scale, dtype, stream);
+}
+extern "C" int ttg_elu_bwd(const void* x, const void* g, void* gx, long long n, float alpha, float scale, int dtype, void* stream) {
+  return elu_launch<1>("elu_bwd", x, g, nullptr, gx, n, alpha, scale, dtype, stream);
+}
+extern "C" int ttg_elu_bwd2(const void* x, const void* g, const void* u, void* out, long long n, float alpha, float scale,
+                            int dtype, void* stream) {
+  return elu_launch<2>("elu_bwd2", x, g, u, out, n, alpha, scale, dtype, stream);
+}
+
 // ---------------------------------------------------------------- per-channel sum (conv bias gradient)
 template <typename T> struct SumOp : NoParams {
   static constexpr int NIN = 1, NACC = 1;

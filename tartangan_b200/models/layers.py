@@ -38,6 +38,20 @@ class LeakyReLU(nn.LeakyReLU):
         return ops.leaky_relu(x, self.negative_slope)
 
 
+class ELU(nn.ELU):
+    """nn.ELU (--activation elu, reference trainers/cnn.py:44)."""
+
+    def forward(self, x):
+        return ops.elu(x, self.alpha)
+
+
+class SELU(nn.SELU):
+    """nn.SELU (--activation selu, reference trainers/cnn.py:43, trainers/iqn.py:44)."""
+
+    def forward(self, x):
+        return ops.selu(x)
+
+
 class AvgPool2d(nn.AvgPool2d):
     def __init__(self, kernel_size=2, **kw):
         super().__init__(kernel_size, **kw)
@@ -92,14 +106,12 @@ class PixelNorm(nn.Module):
 
 def native(factory):
     """Map a torch.nn factory handed to a block constructor onto the kernel-backed twin."""
-    table = {nn.Conv2d: Conv2d, nn.BatchNorm2d: BatchNorm2d, nn.LeakyReLU: LeakyReLU,
+    table = {nn.Conv2d: Conv2d, nn.BatchNorm2d: BatchNorm2d, nn.LeakyReLU: LeakyReLU, nn.SELU: SELU, nn.ELU: ELU,
              nn.AvgPool2d: AvgPool2d, nn.Linear: Linear, nn.Tanh: Tanh}
     if isinstance(factory, functools.partial):
         return functools.partial(native(factory.func), *factory.args, **factory.keywords)
     if factory in table:
         return table[factory]
-    if factory in (nn.SELU, nn.ELU):
-        raise NotImplementedError('tartangan_b200: --activation selu/elu has no kernel yet; use relu (LeakyReLU 0.2)')
     return factory
 
 
@@ -119,6 +131,10 @@ def run_layers(layers, x, up_first=False):
         if isinstance(m, BatchNorm2d) and isinstance(nxt, LeakyReLU):
             x = ops.bn_act(ops.ensure_internal(x), m, nxt.negative_slope, 4 if pending_up else 1)
             i += 2
+        elif isinstance(m, BatchNorm2d):
+            # followed by ELU / SELU (--activation elu|selu): plain BatchNorm (slope 1), the activation is its own kernel
+            x = ops.bn_act(ops.ensure_internal(x), m, 1.0, 4 if pending_up else 1)
+            i += 1
         elif isinstance(m, nn.Identity):
             i += 1
         elif isinstance(m, Conv2d):
@@ -127,7 +143,7 @@ def run_layers(layers, x, up_first=False):
             x = m(x, up=1 if pending_up else 0, stats=feeds_bn)
             pending_up = False
             i += 1
-        elif pending_up and not isinstance(m, LeakyReLU):
+        elif pending_up and not isinstance(m, (LeakyReLU, ELU, SELU)):
             x = m(ops.upsample2(x))          # unknown layer type: materialise the upsample first
             pending_up = False
             i += 1

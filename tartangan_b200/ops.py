@@ -435,8 +435,9 @@ class ConvWgradFn(Function):
                 call('ttg_conv2d_wgrad_tc_ex', ptr(x), ptr(gy), ptr(gw), n, h, w, _pad16(cin), _pad16(cout), cin, cout, k,
                      up, ptr(ws))
         else:
-            call('ttg_conv2d_wgrad_direct', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up,
-                 dtype_code(x.dtype), dtype_code(gy.dtype))
+            ws = _ws(_lib.lib.ttg_conv2d_wgrad_direct_workspace_bytes(n, h, w, cin, cout, k), x.device)
+            call('ttg_conv2d_wgrad_direct_det', ptr(x), ptr(gy), ptr(gw), n, h, w, cin, cout, k, up,
+                 dtype_code(x.dtype), dtype_code(gy.dtype), ptr(ws))
         return gw
 
     @staticmethod
@@ -687,6 +688,61 @@ class LeakyReluMaskFn(Function):
 
 def leaky_relu(x, slope=SLOPE):
     return LeakyReluFn.apply(x, slope)
+
+
+SELU_ALPHA, SELU_SCALE = 1.6732632423543772848170429916717, 1.0507009873554804934193349852946
+
+
+class EluFn(Function):
+    """scale * (x > 0 ? x : alpha * (exp(x) - 1)): nn.ELU (alpha, 1) / nn.SELU (SELU_ALPHA, SELU_SCALE) — the other two
+    choices of --activation (reference trainers/cnn.py:41-45)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, scale):
+        x = nhwc(x) if x.dim() == 4 else _flat(x)
+        ctx.save_for_backward(x)
+        ctx.alpha, ctx.scale = alpha, scale
+        y = _empty_like(x)
+        call('ttg_elu_fwd', ptr(x), ptr(y), x.numel(), alpha, scale, dtype_code(x.dtype))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return EluBwdFn.apply(x, g, ctx.alpha, ctx.scale), None, None
+
+
+class EluBwdFn(Function):
+    """out = g * f'(x).  Linear in g; its x-cotangent g * u * f''(x) is what the R1 penalty differentiates through."""
+
+    @staticmethod
+    def forward(ctx, x, g, alpha, scale):
+        g = nhwc(g) if g.dim() == 4 else _flat(g)
+        ctx.save_for_backward(x, g)
+        ctx.alpha, ctx.scale = alpha, scale
+        out = _empty_like(x)
+        call('ttg_elu_bwd', ptr(x), ptr(g), ptr(out), x.numel(), alpha, scale, dtype_code(x.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, u):
+        x, g = ctx.saved_tensors
+        gx = gg = None
+        u = nhwc(u) if u.dim() == 4 else _flat(u)
+        if ctx.needs_input_grad[0]:
+            gx = _empty_like(x)
+            call('ttg_elu_bwd2', ptr(x), ptr(g), ptr(u), ptr(gx), x.numel(), ctx.alpha, ctx.scale, dtype_code(x.dtype))
+        if ctx.needs_input_grad[1]:
+            gg = EluBwdFn.apply(x, u, ctx.alpha, ctx.scale)
+        return gx, gg, None, None
+
+
+def elu(x, alpha=1.0, scale=1.0):
+    return EluFn.apply(x, float(alpha), float(scale))
+
+
+def selu(x):
+    return EluFn.apply(x, SELU_ALPHA, SELU_SCALE)
 
 
 # --------------------------------------------------------------------------- resampling

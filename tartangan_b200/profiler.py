@@ -35,6 +35,40 @@ def _wgrad_bytes_flops(args, elt=2):
     return ((pix_out >> (2 * up)) * cin + pix_out * cout) * elt, 2.0 * pix_out * cin * cout * k * k
 
 
+def _elt(code):
+    return 2 if code == _lib.BF16 else 4
+
+
+# algorithmic HBM bytes of the streaming kernels (each tensor read or written once), keyed by entry point
+_STREAM_MODELS = {
+    # (x, y, N, Hi, Wi, C, scale, dtype): 1 low-res read + 4 writes
+    'ttg_upsample2': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', a[2] * a[3] * a[4] * a[5] * _elt(a[7]) * 5),
+    # (x, y, N, Ho, Wo, C, scale, dtype): 4 reads + 1 write
+    'ttg_pool2_sum': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', a[2] * a[3] * a[4] * a[5] * _elt(a[7]) * 5),
+    # (h, s, y, N, Ho, Wo, C, [sums,] dtype): h + y at full resolution, s at a quarter
+    'ttg_add_up2': lambda a: (f'N{a[3]} {a[4]}x{a[5]} C{a[6]}', int(a[3] * a[4] * a[5] * a[6] * _elt(a[7]) * 2.25)),
+    'ttg_add_up2_stats': lambda a: (f'N{a[3]} {a[4]}x{a[5]} C{a[6]}', int(a[3] * a[4] * a[5] * a[6] * _elt(a[8]) * 2.25)),
+    # (h, s, y, N, Ho, Wo, C, scale, [sums,] dtype): h at 4x the output resolution, s + y at the output resolution
+    'ttg_pool2_add': lambda a: (f'N{a[3]} {a[4]}x{a[5]} C{a[6]}', a[3] * a[4] * a[5] * a[6] * _elt(a[8]) * 6),
+    'ttg_pool2_add_stats': lambda a: (f'N{a[3]} {a[4]}x{a[5]} C{a[6]}', a[3] * a[4] * a[5] * a[6] * _elt(a[9]) * 6),
+    # (x, y, N, Hi, Wi, C, dtype): full-resolution tensor + quarter-resolution tensor
+    'ttg_bilinear_down_fwd': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', int(a[2] * a[3] * a[4] * a[5] * _elt(a[6]) * 1.25)),
+    'ttg_bilinear_down_bwd': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', int(a[2] * a[3] * a[4] * a[5] * _elt(a[6]) * 1.25)),
+    # (a, b, out, n, alpha, beta, dtype)
+    'ttg_axpby': lambda a: (f'n{a[3]}', a[3] * _elt(a[6]) * (2 if a[0] == a[1] else 3)),
+    # (x, y8, npix, c_real): bf16
+    'ttg_pad_channels8': lambda a: (f'npix{a[2]} c{a[3]}', a[2] * (a[3] + 8) * 2),
+    'ttg_unpad_channels8': lambda a: (f'npix{a[2]} c{a[3]}', a[2] * (a[3] + 8) * 2),
+    # (x, y, N, C, HW, dtype): fp32 on the NCHW side
+    'ttg_nchw_to_nhwc': lambda a: (f'N{a[2]} C{a[3]} HW{a[4]}', a[2] * a[3] * a[4] * (4 + _elt(a[5]))),
+    'ttg_nhwc_to_nchw': lambda a: (f'N{a[2]} C{a[3]} HW{a[4]}', a[2] * a[3] * a[4] * (4 + _elt(a[5]))),
+    # (p, g, m, v, ema, n, ...): p, m, v read + written, g read, ema read + written when present
+    'ttg_adam_flat': lambda a: (f'n{a[5]}', a[5] * 4 * (7 + (2 if a[4] else 0))),
+    # (x, src_dtype, y, dst_dtype, n)
+    'ttg_cast': lambda a: (f'n{a[4]}', a[4] * (_elt(a[1]) + _elt(a[3]))),
+}
+
+
 class KernelProfiler:
     def __init__(self):
         self.events = []
@@ -61,7 +95,7 @@ class KernelProfiler:
             key = _wgrad_key(a)
             nbytes, flops = _wgrad_bytes_flops(a)
             name = 'ttg_conv2d_wgrad_tc'
-        elif name in ('ttg_conv2d_wgrad_tc', 'ttg_conv2d_wgrad_direct'):
+        elif name in ('ttg_conv2d_wgrad_tc', 'ttg_conv2d_wgrad_direct', 'ttg_conv2d_wgrad_direct_det'):
             key = _wgrad_key(args)
             nbytes, flops = _wgrad_bytes_flops(args)
         elif name in ('ttg_bn_stats',):
@@ -93,6 +127,13 @@ class KernelProfiler:
         elif name == 'ttg_bn_act_bwd2':
             key = f'M{args[5]} C{args[6]}'
             nbytes = args[5] * args[6] * 2 * 8          # reduce reads 3; apply reads 3 writes 2
+        elif name == 'ttg_conv2d_tc_stats':      # (x, wp, bias, y, N, H, W, Cin, Cout, k, sums): conv + statistics epilogue
+            a = list(args[:10]) + [0]
+            key = _conv_key(a)
+            nbytes, flops = _conv_bytes_flops(a)
+            name = 'ttg_conv2d_tc'
+        elif name in _STREAM_MODELS:              # resampling / joins / layout / optimiser: bytes in + bytes out
+            key, nbytes = _STREAM_MODELS[name](args)
         self.events.append((name, key, nbytes, flops, e0, e1))
 
     def summary(self):

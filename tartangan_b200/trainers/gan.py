@@ -4,13 +4,14 @@ D-step / G-step / EMA schedule of reference trainers/cnn.py:29-165 and trainers/
 import functools
 import os
 
+import numpy as np
 import torch
 from torch import nn
 
 from .. import ops
 from ..models.blocks import (GeneratorInputMLP, GeneratorOutput, ResidualDiscriminatorBlock,
                              ResidualGeneratorBlock, TiledZGeneratorInput)
-from ..models.layers import BatchNorm2d, LeakyReLU
+from ..models.layers import ELU, SELU, BatchNorm2d, LeakyReLU, SpectralNormConv2d
 from ..models.losses import gradient_penalty
 from ..models.pluggan import GAN_CONFIGS, Generator
 from ..optim import FlatParams, FusedAdam
@@ -34,28 +35,35 @@ class GanTrainer(Trainer):
         self.gan_config = cfg.scale_model(args.model_scale)
         norm_factory = {'id': nn.Identity, 'bn': BatchNorm2d}[args.norm]
         g_input_factory = {'mlp': GeneratorInputMLP, 'tiledz': TiledZGeneratorInput}[args.g_base]
-        if args.activation != 'relu':
-            raise NotImplementedError(f'--activation {args.activation}: only "relu" (LeakyReLU 0.2, the default) '
-                                      'has kernels; selu/elu are not implemented')
-        activation_factory = functools.partial(LeakyReLU, 0.2)
+        activation_factory = {'relu': functools.partial(LeakyReLU, 0.2), 'selu': SELU, 'elu': ELU}[args.activation]
+        # additive flag --spectral-norm {none,d,g,gd}: binds the blocks' conv_factory seam (reference generator.py:34,
+        # discriminator.py:28,52 — never bound by the reference trainers) to the power-iteration conv
+        sn = getattr(args, 'spectral_norm', 'none') or 'none'
+        g_conv = dict(conv_factory=SpectralNormConv2d) if 'g' in sn and sn != 'none' else {}
+        d_conv = dict(conv_factory=SpectralNormConv2d) if 'd' in sn and sn != 'none' else {}
         g_factories = dict(
             input_factory=functools.partial(g_input_factory, activation_factory=activation_factory),
             block_factory=functools.partial(ResidualGeneratorBlock, norm_factory=norm_factory,
-                                            activation_factory=activation_factory),
+                                            activation_factory=activation_factory, **g_conv),
             output_factory=functools.partial(GeneratorOutput, norm_factory=norm_factory,
-                                             activation_factory=activation_factory))
+                                             activation_factory=activation_factory, **g_conv))
         self.g = Generator(self.gan_config, **g_factories).to(self.device)
         self.target_g = Generator(self.gan_config, **g_factories).to(self.device)
         self.d = self.discriminator_cls(
             self.gan_config,
             block_factory=functools.partial(ResidualDiscriminatorBlock, norm_factory=norm_factory,
-                                            activation_factory=activation_factory),
+                                            activation_factory=activation_factory, **d_conv),
             output_factory=functools.partial(self.d_output_cls, norm_factory=norm_factory,
                                              activation_factory=activation_factory),
+            **(dict(input_factory=functools.partial(self.discriminator_cls.default_input, **d_conv))
+               if d_conv and getattr(self.discriminator_cls, 'default_input', None) is not None else {}),
         ).to(self.device)
         nq = getattr(args, 'num_quantiles', None)
         if nq and hasattr(self.d, 'to_output') and hasattr(self.d.to_output, 'iqn'):
             self.d.to_output.iqn.num_quantiles = nq
+        if args.activation == 'selu':
+            self.init_params_selu(self.g.parameters())
+            self.init_params_selu(self.d.parameters())
         self.optimizer_g = FusedAdam(self.g.parameters(), lr=args.lr_g, betas=(0., 0.999))
         self.optimizer_d = FusedAdam(self.d.parameters(), lr=args.lr_d, betas=(0., 0.999))
         self.update_target_generator(1.)       # NB: like the reference this is an EMA step, not a copy (B.1)
@@ -64,6 +72,18 @@ class GanTrainer(Trainer):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world_size, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
             self.broadcast_parameters()
+
+    def init_params_selu(self, params):
+        """trainers/cnn.py:96-105 / trainers/iqn.py:94-102: vectors zeroed, matrices / filters N(0, 1/fan_in).  The draws
+        come from the CPU generator (like the reference, whose models are initialised before .to(device)), in
+        parameter order, so a seed gives the reference's values."""
+        for p in params:
+            d = p.data
+            if d.dim() == 1:
+                d.zero_()
+            else:
+                fan_in, _ = nn.init._calculate_fan_in_and_fan_out(d)
+                d.copy_(torch.empty(d.shape).normal_(std=float(np.sqrt(1. / fan_in))))
 
     def broadcast_parameters(self):
         """Data parallel start-up: every rank adopts rank 0's parameters and buffers."""

@@ -175,6 +175,11 @@ class Trainer:
                                                  drop_last=True)
         logs = defaultdict(list)
         self._maybe_resume()
+        sampler = None
+        if getattr(self.args, 'gen_freq', 0) and not getattr(self.args, 'no_samples', False):
+            from .sampler import ImageSampler
+            sampler = self.sampler = ImageSampler(self)
+            sampler.on_train_begin(self.steps)          # draws the 32 progress latents (image_sampler.py:13-15)
         try:
             while self.epoch <= self.args.epochs:
                 for images in loader:
@@ -186,6 +191,8 @@ class Trainer:
                     if (self.steps and self.steps % self.args.checkpoint_freq == 0
                             and self.steps != getattr(self, '_loaded_from', None)):
                         self.save_checkpoint()
+                    if sampler is not None:
+                        sampler.on_batch_end(self.steps)
                     if not self.args.quiet_logs or self.steps % self.args.log_iters == 0:
                         print(f'step {self.steps} ' + ' '.join(f'{k}={v:.4f}' for k, v in metrics.items()), flush=True)
                     self.steps += 1
@@ -194,6 +201,8 @@ class Trainer:
                 self.epoch += 1
         except KeyboardInterrupt:
             pass
+        if sampler is not None:
+            sampler.on_train_end(self.steps)
         self.save_checkpoint()
         return logs
 
@@ -232,14 +241,28 @@ class Trainer:
         return f'{self.output_root}/checkpoints/{self.steps}'
 
     def save_checkpoint(self):
+        """components/model_checkpoint.py:32-50.  --checkpoint-format reference (default): whole objects that the
+        unmodified reference unpickles into ITS classes (its loader calls .state_dict() on them, :66);
+        state_dict: plain state dicts (smaller; models with --spectral-norm, which have no reference twin)."""
         os.makedirs(self.checkpoint_root, exist_ok=True)
+        fmt = getattr(self.args, 'checkpoint_format', 'reference')
+        if fmt == 'reference' and getattr(self.args, 'spectral_norm', 'none') not in (None, 'none'):
+            fmt = 'state_dict'
         for obj, name in ((self.g, 'g.pt'), (self.target_g, 'g_target.pt'), (self.d, 'd.pt'),
                           (self.optimizer_d, 'opt_d.pt'), (self.optimizer_g, 'opt_g.pt')):
-            torch.save(obj.state_dict(), f'{self.checkpoint_root}/{name}')
+            if fmt == 'reference':
+                from ..checkpoint_compat import save_reference_object
+                save_reference_object(obj, f'{self.checkpoint_root}/{name}')
+            else:
+                torch.save(obj.state_dict(), f'{self.checkpoint_root}/{name}')
         with open(f'{self.checkpoint_root}/trainer.json', 'w') as f:
             json.dump(self.get_state(), f)
 
     def load_checkpoint(self):
+        """model_checkpoint.py:52-74.  Accepts whole objects written by the reference (its class paths resolve to the
+        mirror classes through install_as_tartangan) or by save_checkpoint, and plain state dicts."""
+        from .. import install_as_tartangan
+        install_as_tartangan()
         for attr, name in (('g', 'g.pt'), ('target_g', 'g_target.pt'), ('d', 'd.pt'),
                            ('optimizer_d', 'opt_d.pt'), ('optimizer_g', 'opt_g.pt')):
             obj = torch.load(f'{self.checkpoint_root}/{name}', weights_only=False, map_location=self.device)
@@ -330,7 +353,7 @@ class Trainer:
         p.add_argument('--cache-dataset', action='store_true')
         p.add_argument('--g-base', default='mlp')
         p.add_argument('--norm', default='bn', help='"bn" (batchnorm) or "id" (identity)')
-        p.add_argument('--activation', default='relu', help='"relu" (LeakyReLU 0.2); selu/elu have no kernel')
+        p.add_argument('--activation', default='relu', help='Activation function: "relu" (LeakyReLU 0.2), "selu" or "elu"')
         p.add_argument('--quiet-logs', action='store_true')
         p.add_argument('--log-iters', type=int, default=1000)
         p.add_argument('--log-progress-newlines', action='store_true')
@@ -348,5 +371,11 @@ class Trainer:
                        help='run the training step as CUDA graphs (static shapes; z/tau staged from the CPU generator)')
         p.add_argument('--device-dataset', action='store_true',
                        help='keep the uint8 .npz image stack in GPU memory; crop + normalise batches with one kernel')
+        p.add_argument('--no-samples', action='store_true', help='do not render progress samples (no z draws for them)')
+        p.add_argument('--checkpoint-format', default='reference', choices=('reference', 'state_dict'),
+                       help='reference: whole pickled objects readable by the unmodified reference; state_dict: state dicts')
+        p.add_argument('--spectral-norm', default='none', choices=('none', 'd', 'g', 'gd'),
+                       help='spectral-normalised convolutions (power iteration, torch.nn.utils.spectral_norm '
+                            'semantics) in the discriminator and / or the generator')
         p.add_argument('--attention', type=type_or_none(str), default=None,
                        help='comma-separated block indices with self-attention (overrides the config)')

@@ -8,7 +8,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
-GOLDEN_CASES = ['cnn_tiny', 'iqn_tiny', 'cnn_attn', 'iqn_attn', 'iqn_nonorm']
+GOLDEN_CASES = ['cnn_tiny', 'iqn_tiny', 'cnn_attn', 'iqn_attn', 'iqn_nonorm', 'cnn_selu', 'iqn_selu', 'cnn_elu', 'iqn_tiledz']
 
 
 def pytest_configure(config):

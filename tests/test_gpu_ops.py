@@ -98,6 +98,54 @@ def test_bn_act_fwd_bwd_double(mode, c, hw, n):
     assert rel(x2d, x2) < TOL[mode] * 4 and rel(gam2d, gam2) < TOL[mode] * 4
 
 
+def test_fp32_wgrad_is_bitwise_repeatable():
+    """The fp32 (parity) wgrad path adds its split-K partial sums in a fixed order (ttg_conv2d_wgrad_direct_det): two runs
+    on the same inputs give identical bits, like the reference's CPU convolution_backward."""
+    import tartangan_b200 as tb
+    from tartangan_b200 import ops
+    tb.set_precision('fp32')
+    try:
+        torch.manual_seed(9)
+        for n, cin, cout, hw, k in ((8, 16, 16, 32, 3), (4, 128, 64, 16, 3), (16, 3, 32, 32, 1), (2, 24, 40, 10, 3)):
+            x = ops.to_internal(torch.randn(n, cin, hw, hw, device='cuda'))
+            gy = ops.to_internal(torch.randn(n, cout, hw, hw, device='cuda'))
+            runs = [ops.ConvWgradFn.apply(x, gy, k, 0).clone() for _ in range(4)]
+            assert all(torch.equal(runs[0], r) for r in runs[1:]), (n, cin, cout, hw, k)
+            ref = torch.nn.grad.conv2d_weight(x.float().cpu(), (cout, cin, k, k), gy.float().cpu(), padding=k // 2)
+            assert rel(runs[0], ref) < 2e-4
+    finally:
+        tb.set_precision('bf16')
+
+
+@pytest.mark.parametrize('act', ['selu', 'elu'])
+def test_elu_selu_fwd_bwd_double(mode, act):
+    """nn.SELU / nn.ELU (--activation selu|elu, reference trainers/cnn.py:41-45): value, gradient and the second-order
+    term the R1 penalty needs (cotangent of x through the backward)."""
+    from tartangan_b200 import ops
+    torch.manual_seed(3)
+    ref_fn, fn = (F.selu, ops.selu) if act == 'selu' else (F.elu, ops.elu)
+    for shape in ((2, 16, 8, 8), (3, 5, 6, 6), (7, 33)):
+        x = (torch.randn(*shape) * 2).bfloat16().float().requires_grad_()
+        y = ref_fn(x)
+        gy, v = torch.randn_like(y), torch.randn_like(x)
+        gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+        gyr = gy.clone().requires_grad_()
+        gx_b, = torch.autograd.grad(ref_fn(x), x, gyr, create_graph=True)
+        x2, gy2 = torch.autograd.grad((gx_b * v).sum(), (x, gyr))
+        xd = x.detach().cuda().requires_grad_()
+        four = len(shape) == 4
+        xi = ops.to_internal(xd) if four else xd
+        cast = (lambda t: ops.to_internal(t.cuda())) if four else (lambda t: t.cuda())
+        yd = fn(xi)
+        assert rel(yd, y) < TOL[mode]
+        gyd = cast(gy).detach().requires_grad_()
+        gxd, = torch.autograd.grad(yd, xd, gyd, create_graph=True)
+        assert rel(gxd, gx) < TOL[mode]
+        probe = ops.DotFn.apply(cast(gxd) if four else gxd, cast(v))
+        x2d, gy2d = torch.autograd.grad(probe, (xd, gyd))
+        assert rel(x2d, x2) < TOL[mode] * 2 and rel(gy2d, gy2) < TOL[mode] * 2
+
+
 def test_resample_ops(mode):
     from tartangan_b200 import ops
     torch.manual_seed(2)

@@ -11,6 +11,8 @@ Tolerances: bf16 outputs 2e-2 relative L2; fp32 reductions 2e-3 relative.
 """
 import math
 
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -245,3 +247,12 @@ def test_device_image_stack_matches_host_pipeline(tmp_path):
     t.args.data_path = str(tmp_path / 'imgs.npz')
     logs = t.train(max_steps=2)
     assert len(logs['d_loss']) == 2 and all(v == v for v in logs['d_loss'])
+    # f-2: the progress sampler (image_sampler.py) rendered target_g / g samples and the slerp grid at step 0 and at the end
+    samples = sorted(os.listdir(os.path.join(t.output_root, 'samples')))
+    assert samples == ['grid_sample_0.png', 'grid_sample_2.png', 'sample_0.png', 'sample_2.png'], samples
+    imgs, grid = t.sampler.render()
+    assert imgs.shape == (32, 3, 32, 32) and grid.shape == (25, 3, 32, 32) and float(imgs.abs().max()) <= 1.0
+    g = t.sampler._latent_grid_samples.cpu()
+    assert torch.allclose(g[0], g[0]) and g.shape == (25, t.gan_config.latent_dims)
+    n = g.norm(dim=1)                           # slerp between (almost) equal-norm gaussians keeps the norm in their range
+    assert float(n.min()) > 0.5 * float(n.max())

@@ -42,6 +42,47 @@ def test_spectral_norm_matches_torch():
     tb.set_precision('bf16')
 
 
+@pytest.mark.parametrize('kind,precision', [('cnn', 'fp32'), ('iqn', 'fp32'), ('iqn', 'bf16')])
+def test_spectral_norm_training_step_with_r1(kind, precision):
+    """--spectral-norm gd: spectral-normalised convs in G and D (conv_factory seam) through two full training steps
+    INCLUDING the R1 penalty (the normalised weight is a non-leaf tensor inside the double-backward graph) against
+    the oracle, whose spectral-norm conv is pinned to torch.nn.utils.spectral_norm."""
+    from oracle import tartan_oracle as O
+    from tartangan_b200.models.pluggan import GANConfig
+    from tartangan_b200.trainers.cnn import CNNTrainer
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    cfg = GANConfig(base_size=4, latent_dims=32, data_dims=3, blocks=(32, 16, 16), num_blocks_per_scale=1, attention=())
+    torch.manual_seed(0)
+    t = make_trainer(CNNTrainer if kind == 'cnn' else IQNTrainer, gan_config=cfg, batch_size=8, precision=precision,
+                     spectral_norm='gd')
+    keys = list(t.d.state_dict())
+    assert any(k.endswith('weight_orig') for k in keys) and any(k.endswith('weight_u') for k in keys)
+    assert any(k.endswith('weight_orig') for k in t.g.state_dict())
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer(kind, O.Spec(4, 32, 3, (32, 16, 16), ()), cpu(t.g), cpu(t.target_g), cpu(t.d), 8)
+    tol = (3e-3, 1e-2) if precision == 'fp32' else (6e-2, 1e-1)
+    for s in range(2):
+        imgs = O.tartan_batch(60 + s, 8, 32)
+        torch.manual_seed(400 + s)
+        ref = orc.train_batch(imgs)
+        torch.manual_seed(400 + s)
+        got = t.train_batch(imgs)
+        assert ref['gp'] > 0
+        for k in ref:
+            assert abs(got[k] - ref[k]) <= tol[min(s, 1)] * max(1.0, abs(ref[k])), (s, k, got[k], ref[k])
+        if s == 0 and precision == 'fp32':
+            for net, mod in (('d', t.d), ('g', t.g)):
+                for k, p in mod.named_parameters():
+                    r = orc.last_grads[net].get(k)
+                    if r is None or p.grad is None or float(r.abs().max()) < 1e-5:
+                        continue
+                    assert _rel(p.grad, r) < 2e-2 or (k.endswith('.bias') and float(r.abs().max()) < 1e-4), (net, k)
+    for k, v in orc.d.items():       # the power-iteration vectors walked the same path (two D forwards + one per G step)
+        if k.endswith('weight_u') or k.endswith('weight_v'):
+            assert _rel(t.d.state_dict()[k], v) < (5e-3 if precision == 'fp32' else 5e-2), k
+
+
 def _sync_from_oracle(t, orc):
     """Copy the oracle's parameters, buffers and Adam moments into the CUDA trainer."""
     with torch.no_grad():
@@ -201,10 +242,15 @@ def test_checkpoint_layout_round_trip(tmp_path):
     root = tmp_path / 'run' / 'checkpoints' / '7'
     assert sorted(os.listdir(root)) == ['d.pt', 'g.pt', 'g_target.pt', 'opt_d.pt', 'opt_g.pt', 'trainer.json']
     assert json.load(open(root / 'trainer.json')) == {'epoch': 1, 'steps': 7}
-    sd = torch.load(root / 'd.pt', weights_only=False)
+    import tartangan_b200
+    tartangan_b200.install_as_tartangan()                 # the files name the reference's classes (whole objects)
+    d_obj = torch.load(root / 'd.pt', weights_only=False)
+    assert type(d_obj).__name__ == 'IQNDiscriminator' and not isinstance(d_obj, dict)
+    sd = d_obj.state_dict()
     assert list(sd.keys())[0].startswith('to_output.activation.0')       # head first (pluggan.py:126-127)
     opt = torch.load(root / 'opt_d.pt', weights_only=False)
-    assert set(opt['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
+    assert type(opt) is torch.optim.Adam                                  # what the reference pickles (cnn.py:84-85)
+    assert set(opt.state_dict()['state'][0].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
     torch.manual_seed(0)
     t2 = make_trainer(IQNTrainer, config='32', batch_size=4, precision='fp32', output=str(tmp_path), model_scale=0.25)
     t2.run_id, t2.steps = 'run', 7
@@ -217,3 +263,87 @@ def test_checkpoint_layout_round_trip(tmp_path):
     b = t2.train_batch(imgs)
     for k in a:
         assert abs(a[k] - b[k]) <= 5e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+
+
+def test_load_checkpoint_written_by_the_reference(tmp_path):
+    """f-1, reference -> here: tests/golden/ref_checkpoint was saved by the UNMODIFIED reference
+    (ModelCheckpointComponent.save_checkpoint: whole pickled objects, tools/make_ref_checkpoint.py).  The trainer resumes
+    from it (parameters, BN buffers, Adam moments, step counter) and the next step matches the oracle resumed from the
+    same state."""
+    import shutil
+    from conftest import GOLDEN_DIR
+    from oracle import tartan_oracle as O
+    from tartangan_b200.models.pluggan import GANConfig
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    exp = torch.load(os.path.join(GOLDEN_DIR, 'ref_checkpoint', 'expected_state.pt'), weights_only=False)
+    shutil.copytree(os.path.join(GOLDEN_DIR, 'ref_checkpoint', 'checkpoints'), tmp_path / 'run' / 'checkpoints')
+    cfg = GANConfig(base_size=4, latent_dims=exp['latent'], data_dims=3, blocks=tuple(exp['blocks']),
+                    num_blocks_per_scale=1, attention=())
+    torch.manual_seed(5)
+    t = make_trainer(IQNTrainer, gan_config=cfg, batch_size=exp['batch'], precision='fp32', output=str(tmp_path))
+    t.run_id, t.steps = 'run', 1
+    t.load_checkpoint()
+    assert t.steps == 1 and t.epoch == 1
+    for net in ('g', 'target_g', 'd'):
+        sd = getattr(t, net).state_dict()
+        assert list(sd) == list(exp[net])
+        for k, v in exp[net].items():
+            assert torch.equal(sd[k].cpu(), v), (net, k)
+    for name, opt in (('opt_d', t.optimizer_d), ('opt_g', t.optimizer_g)):
+        got = opt.state_dict()['state']
+        for i, st in exp[name]['state'].items():
+            assert torch.equal(got[i]['exp_avg_sq'].cpu(), st['exp_avg_sq']) and float(got[i]['step']) == float(st['step'])
+    # the resumed trainer continues like the reference would: one more step vs the oracle carrying the same state
+    orc = O.OracleTrainer('iqn', O.Spec(4, exp['latent'], 3, tuple(exp['blocks']), ()), exp['g'], exp['target_g'],
+                          exp['d'], exp['batch'])
+    orc.opt_d.load_state_dict(exp['opt_d'])
+    orc.opt_g.load_state_dict(exp['opt_g'])
+    imgs = O.tartan_batch(4321, exp['batch'], 32)
+    torch.manual_seed(9)
+    ref = orc.train_batch(imgs)
+    torch.manual_seed(9)
+    got = t.train_batch(imgs)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 3e-3 * max(1.0, abs(ref[k])), (k, got[k], ref[k])
+    for k, v in orc.g.items():
+        if v.is_floating_point() and not k.endswith('.bias') and 'running' not in k:
+            d = (t.g.state_dict()[k].cpu() - v).abs()
+            assert float(d.max()) <= 3e-4 + 1e-4 * float(v.abs().max()), k      # at most one sign-flipped Adam step (lr 1e-4, bias-corrected)
+
+
+def test_target_g_sampling_after_graphed_steps():
+    """f-2: sample_g(target_g=True) (components/image_sampler.py:24-45 draws its grids from target_g) after CUDA-graph
+    steps uses the EMA weights the graphs wrote (not a stale packed copy) and equals the oracle generator run on the
+    same state dict; the EMA itself tracks the oracle's target_g."""
+    from oracle import tartan_oracle as O
+    from tartangan_b200.models.pluggan import GAN_CONFIGS
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    from tartangan_b200.trainers.gan import make_trainer
+    cfg = GAN_CONFIGS['32']
+    torch.manual_seed(0)
+    t = make_trainer(IQNTrainer, config='32', batch_size=8, precision='bf16', cuda_graph=True)
+    spec = O.Spec(4, cfg.latent_dims, 3, tuple(cfg.blocks), ())
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    orc = O.OracleTrainer('iqn', spec, cpu(t.g), cpu(t.target_g), cpu(t.d), 8)
+    torch.manual_seed(21)
+    before = t.sample_g(8, target_g=True).float().cpu()
+    for s in range(3):
+        imgs = O.tartan_batch(70 + s, 8, 32)
+        torch.manual_seed(500 + s)
+        orc.train_batch(imgs)
+        torch.manual_seed(500 + s)
+        t.train_batch(imgs)
+    t.target_g.train()
+    torch.manual_seed(21)
+    after = t.sample_g(8, target_g=True).float().cpu()
+    assert after.shape == (8, 3, 32, 32) and float(after.abs().max()) <= 1.0
+    assert float((after - before).abs().max()) > 0            # the EMA moved the target generator
+    sd = cpu(t.target_g)
+    torch.manual_seed(21)
+    with torch.no_grad():
+        want = O.generator({k: v.clone() for k, v in sd.items()}, spec, torch.randn(8, cfg.latent_dims))
+    assert float((after - want).norm() / want.norm()) < 3e-2  # bf16 kernels vs fp32 oracle on the SAME (current) weights
+    for k, v in orc.target_g.items():                         # and the EMA state follows the oracle's
+        if v.is_floating_point() and 'running' not in k:
+            assert float((sd[k] - v).abs().max()) <= 5e-6 + 1e-3 * 4e-4 * 3, k

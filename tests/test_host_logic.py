@@ -31,13 +31,13 @@ def _build(kind, g):
     from tartangan_b200.models import pluggan
     from tartangan_b200.models.blocks import (DiscriminatorOutput, GeneratorInputMLP, GeneratorOutput,
                                                IQNDiscriminatorOutput, ResidualDiscriminatorBlock,
-                                               ResidualGeneratorBlock)
+                                               ResidualGeneratorBlock, TiledZGeneratorInput)
     from tartangan_b200.models.layers import BatchNorm2d
     from torch import nn
     cfg = pluggan.GANConfig(base_size=4, latent_dims=g['latent'], data_dims=3, blocks=tuple(g['blocks']),
                             num_blocks_per_scale=1, attention=tuple(g['attention']))
     norm = {'bn': BatchNorm2d, 'id': nn.Identity}[g['norm']]
-    gf = dict(input_factory=GeneratorInputMLP,
+    gf = dict(input_factory=TiledZGeneratorInput if g.get('g_base') == 'tiledz' else GeneratorInputMLP,
               block_factory=functools.partial(ResidualGeneratorBlock, norm_factory=norm),
               output_factory=functools.partial(GeneratorOutput, norm_factory=norm))
     torch.manual_seed(0)
@@ -53,6 +53,8 @@ def _build(kind, g):
 def test_modules_match_reference_initial_state(golden):
     """Same seed -> same parameter tensors under the same state-dict keys as the reference modules."""
     g = golden
+    if g.get('activation') == 'selu':
+        pytest.skip('init_params_selu re-draws every tensor in the trainer (checked on the GPU: test_golden_fp32)')
     gen, tgt, d = _build(g['kind'], g)
     for name, mod in (('g', gen), ('d', d)):
         ref, sd = g['init'][name], mod.state_dict()
@@ -241,3 +243,72 @@ def test_fused_attention_shape_support():
     for nq, nk, dk, dv in [(64, 16, 2, 8), (4096, 1024, 32, 128), (1000, 256, 8, 32), (1024, 192, 8, 32), (1024, 64, 8, 32)]:
         assert ok(nq, nk, dk, dv) == 0
     assert _lib.lib.ttg_attn_bwd_workspace_bytes(2, 1024, 8) == (2 * 1024 * 8 + 2 * 2 * 1024) * 4
+
+
+def test_reference_written_checkpoint_unpickles_into_mirror_classes():
+    """f-1, reference -> here, without a GPU: the whole-object files of tests/golden/ref_checkpoint (saved by the
+    unmodified reference) unpickle through install_as_tartangan() into this package's classes and give back the
+    reference's state dicts, key order included."""
+    from conftest import GOLDEN_DIR
+    import tartangan_b200
+    tartangan_b200.install_as_tartangan()
+    root = os.path.join(GOLDEN_DIR, 'ref_checkpoint')
+    exp = torch.load(os.path.join(root, 'expected_state.pt'), weights_only=False)
+    for name, key in (('g.pt', 'g'), ('g_target.pt', 'target_g'), ('d.pt', 'd'), ('opt_d.pt', 'opt_d'), ('opt_g.pt', 'opt_g')):
+        obj = torch.load(os.path.join(root, 'checkpoints', '1', name), weights_only=False)
+        sd = obj.state_dict()
+        if key.startswith('opt'):
+            assert sd['param_groups'][0]['betas'] == (0.0, 0.999)
+            for i, st in exp[key]['state'].items():
+                assert torch.equal(sd['state'][i]['exp_avg_sq'], st['exp_avg_sq'])
+        else:
+            assert type(obj).__module__.startswith('tartangan_b200.models')
+            assert list(sd) == list(exp[key]) and all(torch.equal(sd[k], v) for k, v in exp[key].items())
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/tartangan'), reason='needs the reference tree (build container only)')
+def test_reference_loader_reads_our_checkpoints(tmp_path):
+    """f-1, here -> reference: files written by checkpoint_compat.save_reference_object are unpickled by the UNMODIFIED
+    reference (a separate interpreter with only torch + /root/reference on its path: no tartangan_b200) into its own
+    classes; `.state_dict()` (all its loader needs, model_checkpoint.py:66) equals ours and the reference can run the
+    loaded generator / discriminator."""
+    from tartangan_b200.checkpoint_compat import save_reference_object
+    from tartangan_b200.models import pluggan
+    from tartangan_b200.models.blocks import (GeneratorInputMLP, GeneratorOutput, IQNDiscriminatorOutput,
+                                               ResidualDiscriminatorBlock, ResidualGeneratorBlock)
+    from tartangan_b200.optim import FusedAdam
+    torch.manual_seed(3)
+    cfg = pluggan.GANConfig(base_size=4, latent_dims=16, data_dims=3, blocks=(16, 8, 8), num_blocks_per_scale=1, attention=(1,))
+    g = pluggan.Generator(cfg, input_factory=GeneratorInputMLP, block_factory=ResidualGeneratorBlock, output_factory=GeneratorOutput)
+    d = pluggan.IQNDiscriminator(cfg, block_factory=ResidualDiscriminatorBlock, output_factory=IQNDiscriminatorOutput)
+    opt = FusedAdam(g.parameters(), lr=1e-4, betas=(0., 0.999))
+    for p in g.parameters():          # state as after a step (the CUDA step itself is not needed to test the format)
+        opt.state[p] = {'step': torch.tensor(3.), 'exp_avg': torch.zeros_like(p), 'exp_avg_sq': torch.rand_like(p)}
+    for obj, name in ((g, 'g'), (d, 'd'), (opt, 'opt_g')):
+        save_reference_object(obj, str(tmp_path / f'{name}.pt'))
+        torch.save(obj.state_dict(), str(tmp_path / f'{name}_sd.pt'))
+    assert 'tartangan' not in sys.modules or sys.modules['tartangan'].__dict__.get('models') is not None
+    script = f"""
+import sys, types
+sys.path.insert(0, '/root/reference')
+so = types.ModuleType('smart_open'); so.open = open; sys.modules['smart_open'] = so
+b3 = types.ModuleType('boto3'); b3.resource = b3.client = (lambda *a, **k: None); sys.modules['boto3'] = b3
+import torch
+for n in ('g', 'd'):
+    m = torch.load(r'{tmp_path}/' + n + '.pt', weights_only=False)      # what model_checkpoint.py:64 does
+    assert type(m).__module__ == 'tartangan.models.pluggan', type(m)
+    sd, ref = m.state_dict(), torch.load(r'{tmp_path}/' + n + '_sd.pt')
+    assert list(sd) == list(ref) and all(torch.equal(sd[k], ref[k]) for k in ref)
+    m.train()
+    out = m(torch.randn(2, 16)) if n == 'g' else m(torch.randn(2, 3, 32, 32), targets=torch.ones(2, 1))[0]
+    assert torch.isfinite(out).all()
+o = torch.load(r'{tmp_path}/opt_g.pt', weights_only=False)
+assert type(o) is torch.optim.Adam
+sd, ref = o.state_dict(), torch.load(r'{tmp_path}/opt_g_sd.pt', weights_only=False)
+assert sd['param_groups'][0]['lr'] == 1e-4 and tuple(sd['param_groups'][0]['betas']) == (0.0, 0.999)
+assert all(torch.equal(sd['state'][i]['exp_avg_sq'], ref['state'][i]['exp_avg_sq']) for i in ref['state'])
+assert 'tartangan_b200' not in sys.modules
+print('REFERENCE_LOADED_OK')
+"""
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert 'REFERENCE_LOADED_OK' in r.stdout, r.stderr[-2000:]

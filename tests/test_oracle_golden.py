@@ -20,8 +20,16 @@ def test_forward_probe(golden):
     spec, pr = _spec(g), g['probe']
     gsd = {k: v.clone() for k, v in g['init']['g'].items()}
     dsd = {k: v.clone() for k, v in g['init']['d'].items()}
+    O.ACTIVATION = g.get('activation', 'relu')
+    try:
+        _probe(g, spec, pr, gsd, dsd)
+    finally:
+        O.ACTIVATION = 'relu'
+
+
+def _probe(g, spec, pr, gsd, dsd):
     with torch.no_grad():
-        img = O.generator(gsd, spec, pr['z'], g['norm'])
+        img = O.generator(gsd, spec, pr['z'], g['norm'], g.get('g_base', 'mlp'))
         assert _close(img, pr['g_out'])
         if g['kind'] == 'iqn':
             torch.manual_seed(pr['tau_seed'])
@@ -34,7 +42,8 @@ def test_forward_probe(golden):
 def test_train_steps(golden):
     g = golden
     tr = O.OracleTrainer(g['kind'], _spec(g), g['init']['g'], g['init']['target_g'],
-                         g['init']['d'], g['batch'], norm=g['norm'])
+                         g['init']['d'], g['batch'], norm=g['norm'], g_base=g.get('g_base', 'mlp'),
+                         activation=g.get('activation', 'relu'))
     for s in range(g['steps']):
         torch.manual_seed(g['seeds'][s])
         m = tr.train_batch(g['imgs'][s])
@@ -56,3 +65,22 @@ def test_tartan_batch_is_deterministic():
     a, b = O.tartan_batch(5, 3, 32), O.tartan_batch(5, 3, 32)
     assert torch.equal(a, b) and a.shape == (3, 3, 32, 32)
     assert float(a.min()) >= -1 and float(a.max()) <= 1
+
+
+def test_spectral_norm_restatement_matches_torch():
+    """The oracle's spectral-norm conv against torch.nn.utils.spectral_norm itself (forward, u / v updates and the
+    weight_orig gradient over three training forwards)."""
+    torch.manual_seed(4)
+    ref = torch.nn.utils.spectral_norm(torch.nn.Conv2d(6, 10, 3, padding=1))
+    sd = {'c.' + k: v.detach().clone() for k, v in ref.state_dict().items()}
+    sd['c.weight_orig'].requires_grad_()
+    for i in range(3):
+        x = torch.randn(2, 6, 8, 8)
+        y_ref = ref(x)
+        y = O._conv(sd, 'c', x, 1)
+        assert _close(y, y_ref, 1e-5)
+        g = torch.randn_like(y)
+        gw_ref, = torch.autograd.grad(y_ref, ref.weight_orig, g)
+        gw, = torch.autograd.grad(y, sd['c.weight_orig'], g)
+        assert _close(gw, gw_ref, 1e-5)
+        assert _close(sd['c.weight_u'], ref.weight_u, 1e-5) and _close(sd['c.weight_v'], ref.weight_v, 1e-5)

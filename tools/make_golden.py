@@ -5,7 +5,7 @@ imported read-only with three import shims for modules that are outside the
 arithmetic; nothing from it is copied into the repo,
 only the tensors it produces.
 
-    python tools/make_golden.py            # rewrites every case
+    python tools/make_golden.py [case ...]   # rewrites every case (or the named ones)
 """
 import argparse
 import contextlib
@@ -44,6 +44,11 @@ CASES = {
     'cnn_attn': ('cnn', (16, 16, 8), (1,), 16, 2, 2, 'bn'),
     'iqn_attn': ('iqn', (16, 16, 8), (1,), 16, 2, 2, 'bn'),
     'iqn_nonorm': ('iqn', (16, 8), (), 16, 4, 2, 'id'),
+    # round 2: --activation selu|elu (incl. init_params_selu) and --g-base tiledz; optional fields (activation, g_base)
+    'cnn_selu': ('cnn', (16, 8, 8), (), 16, 4, 2, 'id', 'selu', 'mlp'),      # BatchNorm + ELU-family kernels: cnn_elu
+    'iqn_selu': ('iqn', (16, 8), (), 16, 4, 2, 'id', 'selu', 'mlp'),       # (with 'bn' the selu init zeroes gamma: dead path)
+    'cnn_elu': ('cnn', (16, 8, 8), (), 16, 4, 2, 'bn', 'elu', 'mlp'),
+    'iqn_tiledz': ('iqn', (16, 8, 8), (), 16, 4, 2, 'bn', 'relu', 'tiledz'),
 }
 
 
@@ -52,7 +57,8 @@ def _clone_sd(m):
 
 
 def make_case(name, pluggan, cnn, iqn):
-    kind, blocks, attention, latent, batch, steps, norm = CASES[name]
+    kind, blocks, attention, latent, batch, steps, norm = CASES[name][:7]
+    activation, g_base = (CASES[name][7:] + ('relu', 'mlp'))[:2] if len(CASES[name]) > 7 else ('relu', 'mlp')
     cfg_key = f'golden_{name}'
     pluggan.GAN_CONFIGS[cfg_key] = pluggan.GANConfig(
         base_size=4, latent_dims=latent, data_dims=3, attention=attention,
@@ -64,7 +70,7 @@ def make_case(name, pluggan, cnn, iqn):
     for cc in cls.get_component_classes(p.parse_known_args(['/unused'])[0]):
         cc.add_args_to_parser(p)
     args = p.parse_args(['/unused', '--batch-size', str(batch), '--config', cfg_key,
-                         '--norm', norm])
+                         '--norm', norm, '--activation', activation, '--g-base', g_base])
     args.device = 'cpu'
     t = cls.__new__(cls)
     t.args, t.steps, t.epoch = args, 0, 1
@@ -79,6 +85,7 @@ def make_case(name, pluggan, cnn, iqn):
     size = t.g.max_size
     out = dict(case=name, kind=kind, blocks=blocks, attention=attention, latent=latent,
                batch=batch, steps=steps, norm=norm, size=size,
+               **({'activation': activation, 'g_base': g_base} if len(CASES[name]) > 7 else {}),
                init=dict(g=_clone_sd(t.g), target_g=_clone_sd(t.target_g), d=_clone_sd(t.d)))
     # forward-only probes on the initial state (train-mode BN, buffers restored after)
     torch.manual_seed(77)
@@ -123,7 +130,7 @@ def make_case(name, pluggan, cnn, iqn):
 def main():
     pluggan, cnn, iqn = _import_reference()
     os.makedirs(os.path.join(REPO, 'tests', 'golden'), exist_ok=True)
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         out = make_case(name, pluggan, cnn, iqn)
         path = os.path.join(REPO, 'tests', 'golden', f'{name}.pt')
         torch.save(out, path)
