@@ -181,6 +181,10 @@ int ttg_pool2_sum(const void* x, void* y, int N, int Ho, int Wo, int C, float sc
 int ttg_upsample2(const void* x, void* y, int N, int Hi, int Wi, int C, float scale, int dtype, void* stream);
 int ttg_bilinear_down_fwd(const void* x, void* y, int N, int Hi, int Wi, int C, int dtype, void* stream);
 int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream);
+/* gx = add + B^T gy: the gradient fan-in at the input of a residual D block (bilinear skip + conv branch,
+ * discriminator.py:90-95) in one pass instead of a transposed-bilinear pass plus an add pass */
+int ttg_bilinear_down_bwd_add(const void* gy, const void* add, void* gx, int N, int Hi, int Wi, int C, int dtype,
+                              void* stream);
 /* fused residual joins: h + nearest_up2(skip) (generator.py:58-62) and avg_pool2(h) + skip (discriminator.py:67,95) */
 int ttg_add_up2(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, int dtype, void* stream);
 int ttg_pool2_add(const void* h, const void* s, void* y, int N, int Ho, int Wo, int C, float scale, int dtype, void* stream);

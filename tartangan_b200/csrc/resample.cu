@@ -202,8 +202,10 @@ __device__ __forceinline__ int bil_candidates(int i, int in, int out, int* oidx,
 }
 // one thread per input pixel: the (<= 3 x 3) contributing outputs and their weights are found once,
 // then every channel vector of the pixel is gathered with them
+// `add` (optional, same shape as gx): gx = add + B^T gy — the gradient fan-in of a D block's input (skip branch + conv
+// branch, discriminator.py:90-95) without a separate add pass
 template <typename T, int V>
-__global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, int N, int Hi, int Wi, int C) {
+__global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ add, T* __restrict__ gx, int N, int Hi, int Wi, int C) {
   const int cv = C / V; const int Ho = Hi / 2, Wo = Wi / 2;
   const long long total = (long long)N * Hi * Wi;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
@@ -214,8 +216,11 @@ __global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, T* __restrict
     T* dst = gx + p * C;
     for (int v = 0; v < cv; ++v) {
       float acc[V];
+      if (add) Ld<T, V>::ld(add + p * C + v * V, acc);
+      else {
 #pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+      }
       for (int a = 0; a < ny; ++a)
         for (int b = 0; b < nx; ++b) {
           const float w = wys[a] * wxs[b];
@@ -228,15 +233,18 @@ __global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, T* __restrict
     }
   }
 }
-extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream) {
+extern "C" int ttg_bilinear_down_bwd_add(const void* gy, const void* add, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long pixels = (long long)N * Hi * Wi;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, gy, gx)) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, Vec<T>::N>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
-    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, 1>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (T*)gx, N, Hi, Wi, C); }
+    if (vec2_ok<T>(C, gy, gx) && (add == nullptr || vec2_ok<T>(C, add, gx))) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, Vec<T>::N>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C); }
+    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, 1>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C); }
   });
   TTG_CHECK_LAUNCH("bilinear_down_bwd");
   return TTG_OK;
+}
+extern "C" int ttg_bilinear_down_bwd(const void* gy, void* gx, int N, int Hi, int Wi, int C, int dtype, void* stream) {
+  return ttg_bilinear_down_bwd_add(gy, nullptr, gx, N, Hi, Wi, C, dtype, stream);
 }
 
 // BatchNorm statistics of the tensor a join kernel writes (sum / sum of squares per channel of the ROUNDED values):

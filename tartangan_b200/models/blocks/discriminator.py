@@ -72,11 +72,15 @@ class ResidualDiscriminatorBlock(nn.Module):
 
     def forward(self, x):
         x = ops.ensure_internal(x)
-        xs, xh = ops.fork(x)
         layers = list(self.convs)
         fuse_pool = isinstance(layers[-1], AvgPool2d)
-        h = run_layers(layers[:-1] if fuse_pool else layers, xh)
-        xs = self.interpolate(xs)
+        if self.interpolate is _default_interpolate:
+            xh, xs = ops.fork_bilinear_down(x)       # (the gradient fan-in of the two branches is one kernel)
+            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
+        else:
+            xs, xh = ops.fork(x)
+            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
+            xs = self.interpolate(xs)
         if self.project_input is not None:
             xs = run_layers(self.project_input, xs)
         return ops.avg_pool2_add(h, xs) if fuse_pool else ops.add(xs, h)

