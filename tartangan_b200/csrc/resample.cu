@@ -479,12 +479,63 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__
     for (int c = 0; c < C; ++c) d[(long long)c * HW] = to_f(s[c]);
   }
 }
+// RGB images (C == 3, the layout boundary of every training step: real batch in, fake batch out, d/d(real) out): a
+// thread converts 8 pixels -> three coalesced 32-byte reads per plane and three 16-byte stores (bf16) instead of 2-byte
+// stores per element; 41 -> ~15 us for a 256 x 3 x 128 x 128 batch
+__global__ void nchw_to_nhwc_rgb_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int N, int HW) {
+  const long long total = (long long)N * (HW / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / (HW / 8); const int p = (int)(i % (HW / 8)) * 8;
+    const float* s = x + n * 3 * HW + p;
+    float v[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(s + (long long)c * HW), b = *reinterpret_cast<const float4*>(s + (long long)c * HW + 4);
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w; v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+    }
+    float o[24];
+#pragma unroll
+    for (int e = 0; e < 24; ++e) o[e] = v[e % 3][e / 3];
+    bf16* d = y + (n * HW + p) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Vec<bf16> q; q.pack(o + 8 * k); q.store(d + 8 * k); }
+  }
+}
+__global__ void nhwc_to_nchw_rgb_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, int N, int HW) {
+  const long long total = (long long)N * (HW / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / (HW / 8); const int p = (int)(i % (HW / 8)) * 8;
+    const bf16* s = x + (n * HW + p) * 3;
+    float o[24];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { Vec<bf16> q; q.load(s + 8 * k); q.unpack(o + 8 * k); }
+    float* d = y + n * 3 * HW + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      *reinterpret_cast<float4*>(d + (long long)c * HW) = make_float4(o[c], o[3 + c], o[6 + c], o[9 + c]);
+      *reinterpret_cast<float4*>(d + (long long)c * HW + 4) = make_float4(o[12 + c], o[15 + c], o[18 + c], o[21 + c]);
+    }
+  }
+}
+static inline bool rgb_fast_ok(int C, int HW, int dtype, const void* a, const void* b) {
+  return C == 3 && HW % 8 == 0 && dtype == TTG_BF16 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
 extern "C" int ttg_nchw_to_nhwc(const float* x, void* y, int N, int C, int HW, int dtype, void* stream) {
+  if (rgb_fast_ok(C, HW, dtype, x, y)) {
+    nchw_to_nhwc_rgb_bf16_kernel<<<ttg_grid_occ(nchw_to_nhwc_rgb_bf16_kernel, (long long)N * (HW / 8), 256, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, N, HW);
+    TTG_CHECK_LAUNCH("nchw_to_nhwc_rgb");
+    return TTG_OK;
+  }
   TTG_DISPATCH(dtype, { nchw_to_nhwc_kernel<T><<<ttg_grid_occ(nchw_to_nhwc_kernel<T>, (long long)N * HW, 256, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, N, C, HW); });
   TTG_CHECK_LAUNCH("nchw_to_nhwc");
   return TTG_OK;
 }
 extern "C" int ttg_nhwc_to_nchw(const void* x, float* y, int N, int C, int HW, int dtype, void* stream) {
+  if (rgb_fast_ok(C, HW, dtype, x, y)) {
+    nhwc_to_nchw_rgb_bf16_kernel<<<ttg_grid_occ(nhwc_to_nchw_rgb_bf16_kernel, (long long)N * (HW / 8), 256, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, N, HW);
+    TTG_CHECK_LAUNCH("nhwc_to_nchw_rgb");
+    return TTG_OK;
+  }
   TTG_DISPATCH(dtype, { nhwc_to_nchw_kernel<T><<<ttg_grid_occ(nhwc_to_nchw_kernel<T>, (long long)N * HW, 256, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, y, N, C, HW); });
   TTG_CHECK_LAUNCH("nhwc_to_nchw");
   return TTG_OK;
