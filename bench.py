@@ -183,6 +183,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=('b200', 'reference'))
     ap.add_argument('--batch', type=int, default=BATCH, help='per-GPU batch (default: the BASELINE workload)')
     ap.add_argument('--precision', default='bf16')
+    ap.add_argument('--strong', action='store_true',
+                    help='strong scaling (secondary row, SURVEY 8d): the global batch stays at --batch, each rank takes 1/N')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--eager', action='store_true', help='disable CUDA-graph execution of the step')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel event timing table here (JSON)')
@@ -193,6 +195,10 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.strong:
+        if args.batch % world:
+            raise SystemExit(f'--strong: global batch {args.batch} is not divisible by {world} ranks')
+        args.batch //= world                 # per-rank batch; everything below is per rank
     torch.cuda.set_device(local_rank)
     if world > 1:
         torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -261,8 +267,8 @@ def main():
         line = {
             'metric': 'SA-GAN-IQN G+D train images/sec at 128x128', 'value': value, 'unit': 'images/sec',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision,
-            'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None,
+            'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': f"trainers.iqn SA-GAN-IQN config '{CONFIG}' 128x128, batch {args.batch}/GPU, "
                                    f"R1 penalty 5.0, 8 quantiles", 'global_batch': args.batch * world,
                        'parallelism': f'dp{world}',

@@ -61,10 +61,12 @@ size_t ttg_pack_weight_tc_bytes(int Cout, int Cin, int ksize);
 int ttg_pack_weight_tc(const float* w, void* wp, int Cout, int Cin, int ksize, int mode, void* stream);
 int ttg_conv2d_tc(const void* x, const void* wp, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                   int ksize, int up, int dtype_out, void* stream);
-/* tuning switch: 1 (default) = TMA-fed activation tiles where applicable, 0 = cp.async staging everywhere */
+/* tuning switch: 1 (default) = TMA-fed activation tiles where applicable, 0 = cp.async staging everywhere; any other
+ * value is rejected (the layout timing experiments 2 / 3 exist in -DTTG_TRACE development builds only) */
 int ttg_set_use_tma(int on);
 int ttg_set_use_fold(int on);   /* development switch: kx-folded row-tile conv kernel on / off */
-/* A/B switch (default 1): resident-filter layers (Cin in {16, 32, 64}) fetch their halo tiles as whole pixel rows with
+/* A/B switch (default 0: measured slower than the tensor-map tiles; always used for the fused nearest
+ * upsample `up == 1`): resident-filter layers (Cin in {16, 32, 64}) fetch their halo tiles as whole pixel rows with
  * cp.async.bulk and re-lay them out in shared memory (where the fused BatchNorm/LeakyReLU prologue, the fused nearest
  * upsample and the channel padding of 8-channel tensors are applied); 0 = tensor-map (TMA tile) loads. */
 int ttg_set_use_rows(int on);

@@ -1461,7 +1461,15 @@ static int launch_conv_tc_stream_ws(const void* x, const void* wp, const float* 
 }
 
 static int g_conv_tc_smem[2] = {0, 0};
-extern "C" int ttg_set_use_tma(int on) { g_use_tma = on; return TTG_OK; }
+extern "C" int ttg_set_use_tma(int on) {
+#ifdef TTG_TRACE      // development builds only: 2 / 3 are the layout TIMING experiments (results are not a convolution)
+  g_use_tma = on;
+#else
+  if (on != 0 && on != 1) return ttg_set_error(TTG_ERR_ARG, "set_use_tma: %d is a development-build experiment (0 or 1 here)", on);
+  g_use_tma = on;
+#endif
+  return TTG_OK;
+}
 
 
 // ------------------------------------------------------------------ fprop / dgrad, horizontal taps folded into N

@@ -404,29 +404,67 @@ extern "C" int ttg_sqsum_f32(const float* x, long long n, float scale, float* ou
 }
 
 // ---------------------------------------------------------------- small fp32 matmul
-// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]);  row-major, 16x16 tiles.
+// C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]);  row-major.  64x64 output tile per 256-thread block, 4x4 outputs per
+// thread, K in steps of 16 through shared memory (the generator's input Linear 256 x 256 -> 2048 and its two gradient
+// products: 61 us with the one-output-per-thread 16x16 kernel of round 1).  Operand tiles are read along their
+// contiguous dimension whatever the transpose flags are.
+#define MM_BM 64
+#define MM_BN 64
+#define MM_BK 16
 __global__ void __launch_bounds__(256) matmul_f32_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                          const float* __restrict__ bias, float* __restrict__ Cm, int M,
                                                          int N, int K, int ta, int tb) {
-  __shared__ float sa[16][17], sb[16][17];
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
-  float acc = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    int ak = k0 + tx, bk = k0 + ty;
-    sa[ty][tx] = (row < M && ak < K) ? (ta ? A[(long long)ak * M + row] : A[(long long)row * K + ak]) : 0.f;
-    sb[ty][tx] = (bk < K && col < N) ? (tb ? Bm[(long long)col * K + bk] : Bm[(long long)bk * N + col]) : 0.f;
+  __shared__ float sa[MM_BK][MM_BM + 4], sb[MM_BK][MM_BN + 4];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * MM_BM, n0 = blockIdx.x * MM_BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += MM_BK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      int m, k;
+      if (ta) { m = idx % MM_BM; k = idx / MM_BM; } else { k = idx % MM_BK; m = idx / MM_BK; }
+      const int gm = m0 + m, gk = k0 + k;
+      sa[k][m] = (gm < M && gk < K) ? (ta ? A[(long long)gk * M + gm] : A[(long long)gm * K + gk]) : 0.f;
+      int n, kb;
+      if (tb) { kb = idx % MM_BK; n = idx / MM_BK; } else { n = idx % MM_BN; kb = idx / MM_BN; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      sb[kb][n] = (gn < N && gkb < K) ? (tb ? Bm[(long long)gn * K + gkb] : Bm[(long long)gkb * N + gn]) : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc += sa[ty][k] * sb[k][tx];
+    for (int k = 0; k < MM_BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sa[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sb[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
     __syncthreads();
   }
-  if (row < M && col < N) Cm[(long long)row * N + col] = acc + (bias ? bias[col] : 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col < N) Cm[(long long)row * N + col] = acc[i][j] + (bias ? bias[col] : 0.f);
+    }
+  }
 }
 extern "C" int ttg_matmul_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int transA,
                               int transB, void* stream) {
   TTG_REQUIRE(M > 0 && N > 0 && K > 0, "matmul: empty operand");
-  dim3 grid((N + 15) / 16, (M + 15) / 16);
+  dim3 grid((N + MM_BN - 1) / MM_BN, (M + MM_BM - 1) / MM_BM);
   matmul_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, bias, C, M, N, K, transA, transB);
   TTG_CHECK_LAUNCH("matmul_f32");
   return TTG_OK;

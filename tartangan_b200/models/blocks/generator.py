@@ -9,11 +9,15 @@ upsampling, batch statistics included), the first 3x3 conv reads its input throu
 BatchNorm+LeakyReLU pair is one kernel.
 """
 import functools
+import os
 
 from torch import nn
 
 from ... import ops
 from ..layers import (BatchNorm2d, Conv2d, Interpolate, LeakyReLU, Linear, Tanh, native, run_layers)
+
+
+_FP32_TAIL = os.environ.get('TTG_GTAIL_FP32', '0') == '1'     # A/B: fp32 output conv (round 1 path)
 
 
 class GeneratorBlock(nn.Module):
@@ -118,6 +122,13 @@ class GeneratorOutput(nn.Module):
         layers = list(self.convs)
         x = run_layers(layers[:2], ops.ensure_internal(x))
         conv = layers[2]
+        if (isinstance(conv, Conv2d) and len(layers) == 4 and isinstance(layers[3], Tanh)
+                and ops.state.act_dtype == ops.torch.bfloat16 and not _FP32_TAIL):
+            # bf16 mode: the C -> 3 conv writes bf16 through the 8-channel TMA staging (45 + 17 us instead of the 180 us
+            # fp32 3-channel epilogue), the layout boundary converts to fp32 NCHW and tanh (elementwise, so it commutes
+            # with the layout change) runs on the flat fp32 image
+            img = ops.from_internal(conv(x))
+            return ops.tanh(img.reshape(-1)).view(img.shape)
         x = conv(x, out_dtype=ops.torch.float32) if isinstance(conv, Conv2d) else conv(x)
         x = run_layers(layers[3:], x)
         return ops.from_internal(x)

@@ -24,6 +24,8 @@ SLOPE = 0.2
 import os as _os
 _NO_DIRECT = _os.environ.get('TTG_NO_DIRECT', '0') == '1'
 _NO_ARENA = _os.environ.get('TTG_NO_ARENA', '0') == '1'
+# TTG_SIDE_WGRAD=0: weight-gradient kernels stay on the launching stream (A/B; see side_wgrad below)
+_SIDE_WGRAD = _os.environ.get('TTG_SIDE_WGRAD', '1') == '1'
 
 
 class _State:
@@ -36,6 +38,8 @@ class _State:
     fused_attention = True         # tcgen05 attention kernels when the shape allows (else bmm / softmax / bmm)
     direct_grads = False           # inside direct_param_grads(): parameter gradients are added to p.grad by the kernels
     arena = None                   # ZeroArena of the running trainer (pre-zeroed workspaces), or None
+    wgrad_stream = None            # side stream of the in-place weight-gradient kernels (side_wgrad)
+    wgrad_pending = False          # kernels were launched on it since the last join_side_streams()
 
 
 state = _State()
@@ -105,6 +109,14 @@ def _ws_zero(nbytes, device):
     return _ws(nbytes, device), 0
 
 
+def join_side_streams():
+    """The launching stream waits for the weight-gradient kernels on the side stream (before anything reads `.grad`:
+    the optimiser, a gradient all-reduce, the arena reset of the next half-step)."""
+    if state.wgrad_pending:
+        torch.cuda.current_stream().wait_stream(state.wgrad_stream)
+        state.wgrad_pending = False
+
+
 class direct_param_grads:
     """Context for `loss.backward()`: conv / BatchNorm parameter gradients are ADDED to `p.grad` by the producing
     kernels (ttg_*_acc) and the backward returns None for them, so autograd launches no AccumulateGrad / gradient
@@ -117,6 +129,7 @@ class direct_param_grads:
 
     def __exit__(self, *a):
         state.direct_grads = self.prev
+        join_side_streams()
 
 
 def _direct(p):
@@ -126,6 +139,10 @@ def _direct(p):
             and p.grad.shape == p.shape):
         return p.grad
     return None
+
+
+import contextlib as _contextlib
+_null_ctx = _contextlib.nullcontext()
 
 
 def _wgrad_direct(x, gy, w, bias, up, want_b):
@@ -138,13 +155,28 @@ def _wgrad_direct(x, gy, w, bias, up, want_b):
         return False
     x, gy = nhwc(x), nhwc(gy)
     n, _, h, wd_ = gy.shape
-    ws, z = _ws_zero(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
-    fused_bias = want_b and cout >= 16
-    call('ttg_conv2d_wgrad_tc_acc', ptr(x), ptr(gy), ptr(dw), ptr(db) if fused_bias else None, n, h, wd_, _pad16(cin),
-         _pad16(cout), cin, cout, k, 0, 1 | z, ptr(ws))
-    if want_b and not fused_bias:
-        ws2, z2 = _ws_zero(_lib.lib.ttg_bn_workspace_bytes(cout), x.device)
-        call('ttg_channel_sum_acc', ptr(gy), n * h * wd_, cout, ptr(db), 1 | z2, ptr(ws2), dtype_code(gy.dtype))
+    # The weight gradient only feeds `.grad`: nothing later in backward depends on it, so it runs on a SIDE stream and
+    # the dgrad / BatchNorm-backward chain on the launching stream does not wait for it.  The layers below 32x32 launch
+    # 32-128 CTAs on 148 SMs (section 7b of DESIGN.md); their wgrad kernels now fill the SMs the chain leaves idle.
+    # All in-place weight-gradient kernels share the one side stream (no two of them ever add to a buffer
+    # concurrently); join_side_streams() orders the optimiser / all-reduce / next arena reset after them.
+    side = None
+    if _SIDE_WGRAD and x.is_cuda:
+        side = state.wgrad_stream
+        if side is None:
+            side = state.wgrad_stream = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream())          # x, gy (and the cleared arena) are ready
+        x.record_stream(side)
+        gy.record_stream(side)
+        state.wgrad_pending = True
+    with torch.cuda.stream(side) if side is not None else _null_ctx:
+        ws, z = _ws_zero(_lib.lib.ttg_conv2d_wgrad_tc_workspace_bytes(cin, cout, k), x.device)
+        fused_bias = want_b and cout >= 16
+        call('ttg_conv2d_wgrad_tc_acc', ptr(x), ptr(gy), ptr(dw), ptr(db) if fused_bias else None, n, h, wd_, _pad16(cin),
+             _pad16(cout), cin, cout, k, 0, 1 | z, ptr(ws))
+        if want_b and not fused_bias:
+            ws2, z2 = _ws_zero(_lib.lib.ttg_bn_workspace_bytes(cout), x.device)
+            call('ttg_channel_sum_acc', ptr(gy), n * h * wd_, cout, ptr(db), 1 | z2, ptr(ws2), dtype_code(gy.dtype))
     return True
 
 

@@ -61,8 +61,17 @@ class BucketedAllReduce:
             self.pending[b] -= 1
             if self.pending[b] == 0:
                 lo, hi, _ = self.buckets[b]
+                self._join()
                 self.works.append(dist.all_reduce(self.flat_grad[lo:hi], group=self.group, async_op=True))
         return hook
+
+    @staticmethod
+    def _join():
+        """The in-place weight-gradient kernels run on a side stream (ops._wgrad_direct): the collective, which is
+        ordered after the launching stream only, must wait for them too."""
+        if torch.cuda.is_available():
+            from . import ops
+            ops.join_side_streams()
 
     def begin(self):
         """Arm the hooks for one backward pass."""
@@ -76,6 +85,7 @@ class BucketedAllReduce:
             for b, left in enumerate(self.pending):
                 if left > 0:
                     lo, hi, _ = self.buckets[b]
+                    self._join()
                     self.works.append(dist.all_reduce(self.flat_grad[lo:hi], group=self.group, async_op=True))
                     self.pending[b] = 0
             for w in self.works:

@@ -320,8 +320,20 @@ class GanTrainer(Trainer):
         def seg(fn):
             nonlocal pool
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=pool):
-                fn()
+            # Python's cyclic collector must not run inside a capture: collecting an OLDER trainer (its CUDA graphs and
+            # their private memory pool) calls cudaFree / cudaGraphExecDestroy, which invalidates a capture in progress
+            # ("operation failed due to a previous error during capture"; seen when several trainers are built in one
+            # process, e.g. the test suite).  Collect before, keep the collector off while capturing.
+            import gc
+            gc.collect()
+            was_enabled = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, pool=pool):
+                    fn()
+            finally:
+                if was_enabled:
+                    gc.enable()
             pool = g.pool()
             graphs.append(g)
 
