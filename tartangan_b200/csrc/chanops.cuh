@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256) chan_reduce_c3_kernel(Op op, long long ng
   if (threadIdx.x < Op::NACC * 3) atomicAdd(&out[threadIdx.x], (double)s_acc[threadIdx.x]);
 }
 template <typename T> static inline bool c3_ok(int C, const void* const* ptrs, int nptr, long long n) {
-  if (C != 3 || n % (3 * Vec<T>::N)) return false;
+  static const bool off = getenv("TTG_NO_C3") != nullptr;       // development A/B switch
+  if (off || C != 3 || n % (3 * Vec<T>::N)) return false;
   for (int i = 0; i < nptr; ++i)
     if (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) return false;
   return true;

@@ -125,6 +125,7 @@ template <typename T> struct BnActFwdStatsOp {
     const double t = var + (double)eps;
     double y = (double)rsqrtf((float)t);
     y = y * (1.5 - 0.5 * t * y * y);
+    y = y * (1.5 - 0.5 * t * y * y);      // (second step: the fp32 seed is only good to ~2^-22)
     mf = (float)m; rf = (float)y;
   }
   template <int V> struct P { float a[V], b[V]; };     // y = x*a + b
@@ -209,8 +210,9 @@ template <typename T> struct BnActBwdMapOp {
   float *ggamma, *gbeta; int acc;                      // parameter gradients (block 0), added to the buffers when acc
   __device__ void finalize(int) const {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (gbeta) gbeta[c] = (acc ? gbeta[c] : 0.f) + (float)sums[c];
-      if (ggamma) ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)sums[C + c];
+      // (accumulating: atomic, because the D(real) and D(fake) backward chains may run on two streams at once)
+      if (gbeta) { if (acc) atomicAdd(&gbeta[c], (float)sums[c]); else gbeta[c] = (float)sums[c]; }
+      if (ggamma) { if (acc) atomicAdd(&ggamma[c], (float)sums[C + c]); else ggamma[c] = (float)sums[C + c]; }
     }
   }
   template <int V> struct P { BnChan<V> c; float db[V], cc[V]; };
@@ -230,8 +232,8 @@ template <typename T> struct BnActBwdMapOp {
 __global__ void bn_param_grads_kernel(const double* sums, int C, float* ggamma, float* gbeta, int acc) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    if (gbeta) gbeta[c] = (acc ? gbeta[c] : 0.f) + (float)sums[c];
-    if (ggamma) ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)sums[C + c];
+    if (gbeta) { if (acc) atomicAdd(&gbeta[c], (float)sums[c]); else gbeta[c] = (float)sums[c]; }
+    if (ggamma) { if (acc) atomicAdd(&ggamma[c], (float)sums[C + c]); else ggamma[c] = (float)sums[C + c]; }
   }
 }
 
@@ -300,7 +302,8 @@ template <typename T> struct BnActBwd2MapOp {
       const double iM = 1.0 / (double)M;
       const double db = sums[c] * iM, cc = sums[C + c] * iM, ub = sums[2 * C + c] * iM, e = sums[3 * C + c] * iM;
       const double cov = sums[4 * C + c] * iM - ub * db;
-      ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)((double)invstd[c] * (double)M * (cov - cc * e));
+      const float v = (float)((double)invstd[c] * (double)M * (cov - cc * e));
+      if (acc) atomicAdd(&ggamma[c], v); else ggamma[c] = v;
     }
   }
   template <int V> struct P { BnChan<V> c; float db[V], cc[V], ub[V], e[V], k[V]; };   // k = cc*e - cov
@@ -330,7 +333,8 @@ __global__ void bn_bwd2_gamma_kernel(const double* sums, const float* invstd, lo
     double invM = 1.0 / (double)M;
     double db = sums[c] * invM, cc = sums[C + c] * invM, ub = sums[2 * C + c] * invM, e = sums[3 * C + c] * invM;
     double cov = sums[4 * C + c] * invM - ub * db;
-    ggamma[c] = (acc ? ggamma[c] : 0.f) + (float)((double)invstd[c] * (double)M * (cov - cc * e));
+    const float v = (float)((double)invstd[c] * (double)M * (cov - cc * e));
+    if (acc) atomicAdd(&ggamma[c], v); else ggamma[c] = v;
   }
 }
 

@@ -40,6 +40,7 @@ class _State:
     arena = None                   # ZeroArena of the running trainer (pre-zeroed workspaces), or None
     wgrad_stream = None            # side stream of the in-place weight-gradient kernels (side_wgrad)
     wgrad_pending = False          # kernels were launched on it since the last join_side_streams()
+    pending_streams = set()        # other streams that carry parts of the running step (the trainer's D(fake) stream)
 
 
 state = _State()
@@ -117,6 +118,21 @@ def join_side_streams():
         state.wgrad_pending = False
 
 
+def join_all_streams():
+    """The launching stream waits for EVERY stream that may hold contributions to `.grad` or unfinished parts of the
+    step (the weight-gradient stream, the D(fake) stream).  Called when a backward pass ends and before a gradient
+    all-reduce: the in-place kernels return no tensor to autograd, so the engine inserts no synchronisation for them
+    (and a CUDA-graph capture must not end with unjoined work)."""
+    cur = torch.cuda.current_stream()
+    if state.wgrad_pending:
+        cur.wait_stream(state.wgrad_stream)
+        state.wgrad_pending = False
+    for st in list(state.pending_streams):
+        if st != cur:
+            cur.wait_stream(st)
+    state.pending_streams.clear()
+
+
 class direct_param_grads:
     """Context for `loss.backward()`: conv / BatchNorm parameter gradients are ADDED to `p.grad` by the producing
     kernels (ttg_*_acc) and the backward returns None for them, so autograd launches no AccumulateGrad / gradient
@@ -129,7 +145,7 @@ class direct_param_grads:
 
     def __exit__(self, *a):
         state.direct_grads = self.prev
-        join_side_streams()
+        join_all_streams()
 
 
 def _direct(p):

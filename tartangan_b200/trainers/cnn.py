@@ -11,15 +11,18 @@ class CNNTrainer(GanTrainer):
     discriminator_cls = Discriminator
     d_output_cls = DiscriminatorOutput
 
-    def d_losses(self, real, fake):
-        """BCEWithLogits over cat[p_real, p_fake] vs [1.., 0..] (cnn.py:122-131) = the mean of the
-        two half-batch means; D(real) and D(fake) stay separate forwards (separate BN statistics)."""
+    # BCEWithLogits over cat[p_real, p_fake] vs [1.., 0..] (cnn.py:122-131) = the mean of the two half-batch means;
+    # D(real) and D(fake) stay separate forwards (separate BN statistics)
+    def d_real(self, real):
         p_real = self.d(real)
+        return p_real, ops.BceLogitsFn.apply(p_real, torch.ones_like(p_real))
+
+    def d_fake(self, fake):
         p_fake = self.d(fake.detach())
-        ones = torch.ones_like(p_real)
-        l_real = ops.BceLogitsFn.apply(p_real, ones)
-        l_fake = ops.BceLogitsFn.apply(p_fake, torch.zeros_like(p_fake))
-        return p_real, ops.AxpbyFn.apply(l_real, l_fake, 0.5, 0.5)
+        return ops.BceLogitsFn.apply(p_fake, torch.zeros_like(p_fake))
+
+    def d_combine(self, l_real, l_fake):
+        return ops.AxpbyFn.apply(l_real, l_fake, 0.5, 0.5)
 
     def g_loss(self, fake):
         p = self.d(fake)

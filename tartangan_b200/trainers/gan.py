@@ -19,6 +19,7 @@ from .trainer import Trainer
 from .utils import toggle_grad
 
 _EARLY_GEN = os.environ.get('TTG_EARLY_GEN', '0') == '1'      # development switch, see _stage_inputs
+_FAKE_STREAM = os.environ.get('TTG_FAKE_STREAM', '1') == '1'   # A/B switch, see d_forward_backward
 
 
 class GanTrainer(Trainer):
@@ -92,9 +93,21 @@ class GanTrainer(Trainer):
                 torch.distributed.broadcast(t.data, 0)
 
     # ------------------------------------------------------------------ losses (subclass hooks)
+    def d_real(self, real):
+        """-> (p_real, loss of the real half)"""
+        raise NotImplementedError
+
+    def d_fake(self, fake):
+        """-> loss of the fake half"""
+        raise NotImplementedError
+
+    def d_combine(self, l_real, l_fake):
+        raise NotImplementedError
+
     def d_losses(self, real, fake):
         """-> (p_real, d_loss without penalty)"""
-        raise NotImplementedError
+        p_real, l_real = self.d_real(real)
+        return p_real, self.d_combine(l_real, self.d_fake(fake))
 
     def g_loss(self, fake):
         raise NotImplementedError
@@ -152,10 +165,34 @@ class GanTrainer(Trainer):
         real = imgs
         if self.args.grad_penalty:
             real = imgs.detach().requires_grad_()
-        p_real, d_loss = self.d_losses(real, fake)
         gp = None
-        if self.args.grad_penalty:
+        if _FAKE_STREAM and self.args.grad_penalty and ops.get_precision() == 'bf16':
+            # The fake half of the D step (forward, and through autograd its whole backward chain) runs on a second
+            # stream: D(fake) forward overlaps the R1 inner backward, the fake backward chain overlaps the real one and
+            # the R1 double backward.  D's layers below 32x32 launch 32-128 CTAs on 148 SMs, so two chains fill what one
+            # leaves idle.  Order kept: D(fake) forward starts after D(real) forward (the BatchNorm running statistics
+            # are updated real first, then fake, like the reference); parameter gradients of the two chains meet in the
+            # flat .grad buffer through the single weight-gradient stream and atomic BatchNorm accumulations.  bf16 mode
+            # only: the fp32 parity path stays on one stream (fixed summation order).
+            main = torch.cuda.current_stream()
+            side = getattr(self, '_fake_stream', None)
+            if side is None:
+                side = self._fake_stream = torch.cuda.Stream(device=self.device)
+            p_real, l_real = self.d_real(real)
+            side.wait_stream(main)
+            ops.state.pending_streams.add(side)     # joined again when backward ends / before a gradient all-reduce
+            fake.record_stream(side)
+            with torch.cuda.stream(side):
+                l_fake = self.d_fake(fake)
             gp = gradient_penalty(p_real, real)
+            main.wait_stream(side)
+            l_fake.record_stream(main)
+            d_loss = self.d_combine(l_real, l_fake)
+        else:
+            p_real, d_loss = self.d_losses(real, fake)
+            if self.args.grad_penalty:
+                gp = gradient_penalty(p_real, real)
+        if gp is not None:
             d_loss = ops.AxpbyFn.apply(d_loss, gp, 1.0, float(self.args.grad_penalty))
         self._backward(d_loss, self.optimizer_d, overlap)
         return d_loss.detach(), (gp.detach() if gp is not None else None)

@@ -11,12 +11,15 @@ class IQNTrainer(GanTrainer):
     discriminator_cls = IQNDiscriminator
     d_output_cls = IQNDiscriminatorOutput
 
-    def d_losses(self, real, fake):
-        """D returns (mean-over-quantile prediction, quantile-Huber loss) (iqn.py:118-120)."""
-        n = len(real)
-        p_real, l_real = self.d(real, targets=torch.ones(n, 1, device=self.device))
-        _, l_fake = self.d(fake.detach(), targets=torch.zeros(n, 1, device=self.device))
-        return p_real, ops.add(l_real, l_fake)
+    # D returns (mean-over-quantile prediction, quantile-Huber loss) (iqn.py:118-120); d_loss = l_real + l_fake
+    def d_real(self, real):
+        return self.d(real, targets=torch.ones(len(real), 1, device=self.device))
+
+    def d_fake(self, fake):
+        return self.d(fake.detach(), targets=torch.zeros(len(fake), 1, device=self.device))[1]
+
+    def d_combine(self, l_real, l_fake):
+        return ops.add(l_real, l_fake)
 
     def g_loss(self, fake):
         _, loss = self.d(fake, targets=torch.ones(len(fake), 1, device=self.device))
