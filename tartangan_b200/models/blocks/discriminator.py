@@ -76,13 +76,16 @@ class ResidualDiscriminatorBlock(nn.Module):
         fuse_pool = isinstance(layers[-1], AvgPool2d)
         if self.interpolate is _default_interpolate:
             xh, xs = ops.fork_bilinear_down(x)       # (the gradient fan-in of the two branches is one kernel)
-            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
         else:
             xs, xh = ops.fork(x)
-            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
             xs = self.interpolate(xs)
         if self.project_input is not None:
-            xs = run_layers(self.project_input, xs)
+            with ops.skip_branch(xs) as sb:          # the 1x1 projection runs beside the conv branch
+                xs = run_layers(self.project_input, xs)
+            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
+            xs = sb.join(xs)
+        else:
+            h = run_layers(layers[:-1] if fuse_pool else layers, xh)
         return ops.avg_pool2_add(h, xs) if fuse_pool else ops.add(xs, h)
 
 

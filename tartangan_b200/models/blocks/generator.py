@@ -64,9 +64,13 @@ class ResidualGeneratorBlock(nn.Module):
     def forward(self, x):
         x = ops.ensure_internal(x)
         xs, xh = ops.fork(x)
-        h = run_layers(self.convs, xh, up_first=self.upsample)
         if self.project_input is not None:
-            xs = run_layers(self.project_input, xs)      # 1x1 conv commutes with nearest upsampling: run it low-res
+            with ops.skip_branch(xs) as sb:               # beside the conv branch, on the companion stream
+                xs = run_layers(self.project_input, xs)  # 1x1 conv commutes with nearest upsampling: run it low-res
+            h = run_layers(self.convs, xh, up_first=self.upsample)
+            xs = sb.join(xs)
+        else:
+            h = run_layers(self.convs, xh, up_first=self.upsample)
         return ops.add_up2(h, xs) if self.upsample else ops.add(xs, h)
 
 

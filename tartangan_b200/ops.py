@@ -26,6 +26,8 @@ _NO_DIRECT = _os.environ.get('TTG_NO_DIRECT', '0') == '1'
 _NO_ARENA = _os.environ.get('TTG_NO_ARENA', '0') == '1'
 # TTG_SIDE_WGRAD=0: weight-gradient kernels stay on the launching stream (A/B; see side_wgrad below)
 _SIDE_WGRAD = _os.environ.get('TTG_SIDE_WGRAD', '1') == '1'
+# TTG_SKIP_STREAM=0: the skip branch of a residual block stays on the launching stream (A/B; see skip_branch below)
+_SKIP_STREAM = _os.environ.get('TTG_SKIP_STREAM', '1') == '1'
 
 
 class _State:
@@ -116,6 +118,46 @@ def join_side_streams():
     if state.wgrad_pending:
         torch.cuda.current_stream().wait_stream(state.wgrad_stream)
         state.wgrad_pending = False
+
+
+class skip_branch:
+    """Context for the skip branch of a residual block (1x1 projection of the resampled input, generator.py:59-60,
+    discriminator.py:92-94): it is independent of the conv branch until the residual add, so it runs on a companion
+    stream of the launching stream and its small kernels fill SMs the conv branch leaves idle; autograd runs its
+    backward (the projection's dgrad) on that stream as well.  `join(out)` before the add.  bf16 mode only (the fp32
+    parity path stays on one stream)."""
+    _streams = {}
+
+    def __init__(self, *inputs):
+        self.inputs = [t for t in inputs if torch.is_tensor(t) and t.is_cuda]
+        self.side = None
+        if _SKIP_STREAM and self.inputs and state.act_dtype == torch.bfloat16:
+            self.cur = torch.cuda.current_stream()
+            key = (self.cur.device.index, self.cur.cuda_stream)
+            side = skip_branch._streams.get(key)
+            if side is None:
+                side = skip_branch._streams[key] = torch.cuda.Stream(device=self.cur.device)
+            self.side = side
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.cur)
+            for t in self.inputs:
+                t.record_stream(self.side)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.side is not None:
+            self._ctx.__exit__(*a)
+        return False
+
+    def join(self, out):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+            out.record_stream(self.cur)
+        return out
 
 
 def join_all_streams():

@@ -178,6 +178,11 @@ class GanTrainer(Trainer):
             side = getattr(self, '_fake_stream', None)
             if side is None:
                 side = self._fake_stream = torch.cuda.Stream(device=self.device)
+                # (the head's Linear / embedding gradients reach AccumulateGrad from two streams by design; the engine
+                # synchronises them, the advisory warning about it would be printed every step)
+                warn_off = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+                if warn_off is not None:
+                    warn_off(False)
             p_real, l_real = self.d_real(real)
             side.wait_stream(main)
             ops.state.pending_streams.add(side)     # joined again when backward ends / before a gradient all-reduce
