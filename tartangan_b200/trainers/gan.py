@@ -20,6 +20,7 @@ from .utils import toggle_grad
 
 _EARLY_GEN = os.environ.get('TTG_EARLY_GEN', '0') == '1'      # development switch, see _stage_inputs
 _FAKE_STREAM = os.environ.get('TTG_FAKE_STREAM', '1') == '1'   # A/B switch, see d_forward_backward
+_EARLY_GFWD = os.environ.get('TTG_EARLY_GFWD', '1') == '1'     # A/B switch, see early_g_forward
 
 
 class GanTrainer(Trainer):
@@ -205,12 +206,37 @@ class GanTrainer(Trainer):
     def d_update(self):
         self.optimizer_d.step()
 
-    def g_forward_backward(self, imgs, overlap=True):
+    def early_g_forward(self, n):
+        """Graph mode: the generator forward of the G STEP, issued at the start of the step on its own stream.  It
+        depends on nothing the D step produces (G's parameters change only at the end of the step, z1 is already
+        staged), so it runs beside the D step; only D(fake_g) has to wait for D's update.  Order kept: it starts after
+        the generator sample of the D step (G's BatchNorm running statistics: z0 pass first, then z1, like the
+        reference).  Returns the sample for g_forward_backward(fake=...); None when switched off."""
+        if not _EARLY_GFWD or ops.get_precision() != 'bf16':
+            return None
+        main = torch.cuda.current_stream()
+        g2 = getattr(self, '_g_stream', None)
+        if g2 is None:
+            g2 = self._g_stream = torch.cuda.Stream(device=self.device)
+        toggle_grad(self.g, True)               # the graph of this forward is what the G step differentiates
+        g2.wait_stream(main)
+        ops.state.pending_streams.add(g2)
+        with torch.cuda.stream(g2):
+            fake = self.sample_g(n)
+        return fake
+
+    def g_forward_backward(self, imgs, overlap=True, fake=None):
         toggle_grad(self.g, True)
         toggle_grad(self.d, False)
         self.optimizer_g.zero_grad()
         self._reset_arena()
-        fake = self.sample_g(len(imgs))
+        if fake is None:
+            fake = self.sample_g(len(imgs))
+        else:                                   # produced by early_g_forward on its own stream
+            main = torch.cuda.current_stream()
+            main.wait_stream(self._g_stream)
+            fake.record_stream(main)
+            ops.state.pending_streams.add(self._g_stream)       # its backward chain runs there too
         g_loss = self.g_loss(fake)
         self._backward(g_loss, self.optimizer_g, overlap)
         return g_loss.detach()
@@ -395,9 +421,10 @@ class GanTrainer(Trainer):
             if self.world_size > 1:               # build the reducers (and their hooks) before capturing
                 self._reducer(self.optimizer_d); self._reducer(self.optimizer_g)
             def rest():
+                early = self.early_g_forward(b)
                 out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
                 self.d_update()
-                out['g_loss'] = self.g_forward_backward(st['imgs'], overlap)
+                out['g_loss'] = self.g_forward_backward(st['imgs'], overlap, fake=early)
                 self.g_update()
             seg(rest)
             self._segments = [(graphs[0], 'imgs'), (graphs[1], None)]
