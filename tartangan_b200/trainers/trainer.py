@@ -175,6 +175,10 @@ class Trainer:
                                                  drop_last=True)
         logs = defaultdict(list)
         self._maybe_resume()
+        fid = None
+        if getattr(self.args, 'fid', False):
+            from .fid import FIDEvaluator                 # needs --inception-moments and local Inception weights
+            fid = self.fid_evaluator = FIDEvaluator(self)
         sampler = None
         if getattr(self.args, 'gen_freq', 0) and not getattr(self.args, 'no_samples', False):
             from .sampler import ImageSampler
@@ -193,6 +197,8 @@ class Trainer:
                         self.save_checkpoint()
                     if sampler is not None:
                         sampler.on_batch_end(self.steps)
+                    if fid is not None:
+                        fid.on_batch_end(self.steps, logs)
                     if not self.args.quiet_logs or self.steps % self.args.log_iters == 0:
                         print(f'step {self.steps} ' + ' '.join(f'{k}={v:.4f}' for k, v in metrics.items()), flush=True)
                     self.steps += 1
@@ -371,6 +377,14 @@ class Trainer:
                        help='run the training step as CUDA graphs (static shapes; z/tau staged from the CPU generator)')
         p.add_argument('--device-dataset', action='store_true',
                        help='keep the uint8 .npz image stack in GPU memory; crop + normalise batches with one kernel')
+        # components/metrics/fid.py:51-59 (enabled by --fid)
+        p.add_argument('--inception-moments', type=type_or_none(str), default=None,
+                       help='Path to pre-calculated inception moments (.npz with mu, sigma)')
+        p.add_argument('--n-inception-imgs', default=1000, type=int)
+        p.add_argument('--cleanup-inception-model', action='store_true')
+        p.add_argument('--fid-freq', default=10000, type=int, help='Calculate test metrics every N batches')
+        p.add_argument('--inception-weights', type=type_or_none(str), default=None,
+                       help='local Inception-v3 state dict (no network: nothing is downloaded)')
         p.add_argument('--no-samples', action='store_true', help='do not render progress samples (no z draws for them)')
         p.add_argument('--checkpoint-format', default='reference', choices=('reference', 'state_dict'),
                        help='reference: whole pickled objects readable by the unmodified reference; state_dict: state dicts')

@@ -312,3 +312,76 @@ print('REFERENCE_LOADED_OK')
 """
     r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
     assert 'REFERENCE_LOADED_OK' in r.stdout, r.stderr[-2000:]
+
+
+def test_fid_statistics_match_scipy_and_numpy(tmp_path):
+    """f-4 (inception_utils.py:180-247, components/metrics/fid.py): covariance, Newton-Schulz matrix square root, Frechet
+    distance and Inception score against scipy / numpy; the accumulation loop with a stand-in feature network."""
+    import numpy as np
+    from scipy import linalg
+    from tartangan_b200.trainers import fid as F_
+    rng = np.random.RandomState(0)
+    a, b = rng.randn(400, 24), rng.randn(300, 24) * 1.3 + 0.2
+    ta, tb = torch.tensor(a), torch.tensor(b)
+    assert np.allclose(F_.torch_cov(ta).numpy(), np.cov(a, rowvar=False), atol=1e-10)
+    s1, s2 = np.cov(a, rowvar=False), np.cov(b, rowvar=False)
+    root = F_.sqrt_newton_schulz(torch.tensor(s1 @ s2)).numpy()
+    assert np.allclose(root @ root, s1 @ s2, atol=1e-6)
+    want = ((a.mean(0) - b.mean(0)) ** 2).sum() + np.trace(s1) + np.trace(s2) - 2 * np.trace(linalg.sqrtm(s1 @ s2).real)
+    got = float(F_.frechet_distance(ta.mean(0), F_.torch_cov(ta), tb.mean(0), F_.torch_cov(tb)))
+    assert abs(got - want) <= 1e-5 * abs(want)
+    assert abs(float(F_.frechet_distance(ta.mean(0), F_.torch_cov(ta), ta.mean(0), F_.torch_cov(ta)))) < 1e-6
+    p = torch.softmax(torch.tensor(rng.randn(200, 10) * 2), 1)
+    scores = []
+    for i in range(5):
+        c = p[i * 40:(i + 1) * 40].numpy()
+        scores.append(np.exp(np.mean(np.sum(c * (np.log(c) - np.log(c.mean(0, keepdims=True))), 1))))
+    m, sd = F_.inception_score(p, 5)
+    assert abs(m - np.mean(scores)) < 1e-9 and abs(sd - np.std(scores)) < 1e-9
+    # the loop: a stand-in feature network, moments of one distribution, samples of the same and of a shifted one
+
+    class Net(torch.nn.Module):
+        def forward(self, x):
+            f = x.flatten(1)[:, :16]
+            return f, f[:, :10]
+    torch.manual_seed(0)
+    ref = torch.randn(4000, 3, 4, 4).clamp(-1, 1)
+    pool, _ = F_.accumulate_activations(lambda: ref, Net(), 4000)
+    np.savez(tmp_path / 'moments.npz', mu=pool.mean(0).numpy(), sigma=F_.torch_cov(pool).numpy())
+    metrics = F_.InceptionMetrics(str(tmp_path / 'moments.npz'), 'cpu', net=Net())
+    same = metrics.get(lambda: torch.randn(500, 3, 4, 4).clamp(-1, 1), 4000, num_splits=5)
+    shifted = metrics.get(lambda: (torch.randn(500, 3, 4, 4) + 0.5).clamp(-1, 1), 4000, num_splits=5)
+    assert same[2] < 0.2 and shifted[2] > 10 * max(same[2], 1e-3)
+    with pytest.raises(FileNotFoundError):
+        F_.load_inception_net(str(tmp_path / 'missing.pth'))
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/tartangan'), reason='needs the reference tree (build container only)')
+def test_inception_feature_wrapper_matches_reference():
+    """f-4: InceptionFeatures on a randomly initialised torchvision Inception-v3 gives the same pool features and logits
+    as the reference's WrapInception around the SAME network (inception_utils.py:33-81) - no pretrained weights needed."""
+    import types
+    from torchvision.models import inception_v3
+    from tartangan_b200.trainers.fid import InceptionFeatures
+    sys.path.insert(0, '/root/reference')
+    for name, mod in (('smart_open', dict(open=open)), ('boto3', dict(resource=lambda *a, **k: None, client=lambda *a, **k: None))):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(mod)
+            sys.modules[name] = m
+    before = set(sys.modules)
+    try:
+        import importlib
+        ref = importlib.import_module('tartangan.inception_utils')
+    finally:
+        sys.path.remove('/root/reference')
+        for k in set(sys.modules) - before:                  # leave no real `tartangan` package behind for later tests
+            if k == 'tartangan' or k.startswith('tartangan.'):
+                del sys.modules[k]
+    torch.manual_seed(0)
+    net = inception_v3(weights=None, aux_logits=True, transform_input=False, init_weights=True).eval()
+    x = torch.rand(2, 3, 64, 64) * 2 - 1
+    with torch.no_grad():
+        p_ref, l_ref = ref.WrapInception(net)(x)
+        p, l = InceptionFeatures(net)(x)
+    assert torch.allclose(p, p_ref, atol=1e-5, rtol=1e-4) and torch.allclose(l, l_ref, atol=1e-5, rtol=1e-4)

@@ -137,7 +137,24 @@ def iqn_fused(b, c=128, nq=8):
               f'tanh {b*nq*c/med/1e6:.0f} G/s')
 
 
-if sys.argv[1] == 'iqnf':
+def spectral(rows, cols):
+    """Single-launch spectral-norm power iteration + scaling (ttg_spectral_norm) and its backward at one filter size."""
+    w = torch.randn(rows, cols, device='cuda') * 0.05
+    u = torch.nn.functional.normalize(torch.randn(rows, device='cuda'), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(cols, device='cuda'), dim=0)
+    out = torch.empty_like(w); sigma = torch.empty(1, device='cuda'); g = torch.randn_like(w); gw = torch.empty_like(w)
+    ws = torch.empty(16 + rows + cols, device='cuda')
+    fwd = lambda: call('ttg_spectral_norm', ptr(w), ptr(u), ptr(v), ptr(out), ptr(sigma), rows, cols, 1, 1e-12, ptr(ws))
+    bwd = lambda: call('ttg_spectral_norm_bwd', ptr(g), ptr(out), ptr(u), ptr(v), ptr(sigma), ptr(gw), rows, cols, ptr(ws))
+    for name, fn, passes in (('fwd (W^T u, W v, sigma, W / sigma: 4 passes over W)', fwd, 5), ('bwd (dot + update: 2 passes)', bwd, 5)):
+        med, best = timeit(fn)
+        nb = rows * cols * 4 * passes
+        print(f'spectral_norm {name} {rows}x{cols}: median {med*1e3:.1f} us  ({nb/1e6:.2f} MB of L2-resident traffic, one CTA -> {nb/med/1e6:.0f} GB/s)')
+
+
+if sys.argv[1] == 'sn':
+    spectral(int(sys.argv[2]), int(sys.argv[3]))
+elif sys.argv[1] == 'iqnf':
     iqn_fused(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128, int(sys.argv[4]) if len(sys.argv) > 4 else 8)
 elif sys.argv[1] == 'iqn':
     iqn(int(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 128)
