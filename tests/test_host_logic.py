@@ -369,15 +369,17 @@ def test_inception_feature_wrapper_matches_reference():
             m = types.ModuleType(name)
             m.__dict__.update(mod)
             sys.modules[name] = m
-    before = set(sys.modules)
+    # an earlier test may have aliased `tartangan` to this package (install_as_tartangan): set those entries aside,
+    # import the real reference module, then put everything back
+    aside = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'tartangan' or k.startswith('tartangan.')}
     try:
         import importlib
         ref = importlib.import_module('tartangan.inception_utils')
     finally:
         sys.path.remove('/root/reference')
-        for k in set(sys.modules) - before:                  # leave no real `tartangan` package behind for later tests
-            if k == 'tartangan' or k.startswith('tartangan.'):
-                del sys.modules[k]
+        for k in [k for k in sys.modules if k == 'tartangan' or k.startswith('tartangan.')]:
+            del sys.modules[k]
+        sys.modules.update(aside)
     torch.manual_seed(0)
     net = inception_v3(weights=None, aux_logits=True, transform_input=False, init_weights=True).eval()
     x = torch.rand(2, 3, 64, 64) * 2 - 1
