@@ -245,6 +245,9 @@ def main():
         m = trainer.train_batch(host, as_floats=True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    import math
+    if not all(math.isfinite(float(v)) for v in m.values()):        # a fast step that computes garbage is not a result
+        raise SystemExit(f'bench: non-finite losses after the timed steps: {m}')
     sampler.stop_flag = True
     sampler.join()
     if world > 1:
@@ -277,6 +280,7 @@ def main():
                     (host.numel() * 4 + 2 * args.batch * 256 * 4 + 3 * args.batch * 8 * 4) * world,
                     'd2h_bytes_per_step': 12 * world},
             'gpu_launches': launches, 'host_issue_ms_per_step': host_issue_ms,
+            'last_losses': {k: float(v) for k, v in m.items()},
             'clocks': sampler.result(),
             'roofline': roof,
         }

@@ -21,6 +21,7 @@ from .utils import toggle_grad
 _EARLY_GEN = os.environ.get('TTG_EARLY_GEN', '0') == '1'      # development switch, see _stage_inputs
 _FAKE_STREAM = os.environ.get('TTG_FAKE_STREAM', '1') == '1'   # A/B switch, see d_forward_backward
 _EARLY_GFWD = os.environ.get('TTG_EARLY_GFWD', '1') == '1'     # A/B switch, see early_g_forward
+_GEN_ASYNC = os.environ.get('TTG_GEN_ASYNC', '1') == '1'       # A/B switch, see _capture (generator-sample graph on its own stream)
 
 
 class GanTrainer(Trainer):
@@ -186,6 +187,7 @@ class GanTrainer(Trainer):
                     warn_off(False)
             p_real, l_real = self.d_real(real)
             side.wait_stream(main)
+            self._wait_gen_sample(side)
             ops.state.pending_streams.add(side)     # joined again when backward ends / before a gradient all-reduce
             fake.record_stream(side)
             with torch.cuda.stream(side):
@@ -195,6 +197,7 @@ class GanTrainer(Trainer):
             l_fake.record_stream(main)
             d_loss = self.d_combine(l_real, l_fake)
         else:
+            self._wait_gen_sample(torch.cuda.current_stream())
             p_real, d_loss = self.d_losses(real, fake)
             if self.args.grad_penalty:
                 gp = gradient_penalty(p_real, real)
@@ -205,6 +208,14 @@ class GanTrainer(Trainer):
 
     def d_update(self):
         self.optimizer_d.step()
+
+    def _wait_gen_sample(self, stream):
+        """Graph mode with the generator-sample graph on its own stream: `stream` waits (an external event-wait node
+        inside the step graph) until that graph has produced this step's sample."""
+        ev = getattr(self, '_gen_done', None)
+        st = getattr(self, '_st', None)
+        if ev is not None and st is not None and st.get('active'):
+            stream.wait_event(ev)
 
     def early_g_forward(self, n):
         """Graph mode: the generator forward of the G STEP, issued at the start of the step on its own stream.  It
@@ -220,6 +231,7 @@ class GanTrainer(Trainer):
             g2 = self._g_stream = torch.cuda.Stream(device=self.device)
         toggle_grad(self.g, True)               # the graph of this forward is what the G step differentiates
         g2.wait_stream(main)
+        self._wait_gen_sample(g2)               # (G's BatchNorm running statistics: the z0 pass comes first)
         ops.state.pending_streams.add(g2)
         with torch.cuda.stream(g2):
             fake = self.sample_g(n)
@@ -385,7 +397,9 @@ class GanTrainer(Trainer):
         from .. import _lib
         k_before = _lib.Counters.kernels
 
-        def seg(fn):
+        def seg(fn, own_pool=False):
+            """own_pool: the segment gets a private memory pool of its own.  Segments that share a pool may alias each
+            other's freed intermediates, which is only safe when they never run concurrently."""
             nonlocal pool
             g = torch.cuda.CUDAGraph()
             # Python's cyclic collector must not run inside a capture: collecting an OLDER trainer (its CUDA graphs and
@@ -397,12 +411,13 @@ class GanTrainer(Trainer):
             was_enabled = gc.isenabled()
             gc.disable()
             try:
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=None if own_pool else pool):
                     fn()
             finally:
                 if was_enabled:
                     gc.enable()
-            pool = g.pool()
+            if not own_pool:
+                pool = g.pool()
             graphs.append(g)
 
         # Data parallel: the bucketed NCCL all-reduces are captured INSIDE the graph.  They are launched from the
@@ -416,10 +431,23 @@ class GanTrainer(Trainer):
         def gen():
             with torch.no_grad():
                 out['fake'] = self.sample_g(b)
-        seg(gen)                                  # needs no images: runs while the host batch is still in flight
+        gen_async = _GEN_ASYNC and not blocking and ops.get_precision() == 'bf16'
+        # needs no images: runs while the host batch is still in flight (and, with gen_async, beside the step graph: then
+        # its intermediates must not share memory with the step graph's)
+        seg(gen, own_pool=gen_async)
         if not blocking:
             if self.world_size > 1:               # build the reducers (and their hooks) before capturing
                 self._reducer(self.optimizer_d); self._reducer(self.optimizer_g)
+            self._gen_done = self._gen_stream = None
+            if gen_async:
+                # The generator-sample graph (G forward of the D step, needs neither the images nor anything of this
+                # step) is replayed on its OWN stream; the step graph waits for it through an external event-wait node
+                # placed where the sample is first needed (D(fake) forward, the early G-step forward), so it overlaps
+                # the image copy AND D(real) forward + the R1 inner backward.
+                self._gen_stream = torch.cuda.Stream(device=self.device)
+                self._gen_done = torch.cuda.Event(external=True)
+                self._gen_done.record(torch.cuda.current_stream())
+
             def rest():
                 early = self.early_g_forward(b)
                 out['d_loss'], out['gp'] = self.d_forward_backward(st['imgs'], overlap, fake=out['fake'])
@@ -456,8 +484,16 @@ class GanTrainer(Trainer):
             self._stage_inputs(imgs)
         from .. import _lib
         _lib.Counters.kernels += self._graph_kernels
+        gen_stream = getattr(self, '_gen_stream', None)
         for si, (graph, exchange) in enumerate(self._segments):
-            graph.replay()
+            if si == 0 and gen_stream is not None:
+                main = torch.cuda.current_stream()
+                gen_stream.wait_stream(main)              # the previous step (Adam of G, its BatchNorm buffers) is done
+                with torch.cuda.stream(gen_stream):
+                    graph.replay()
+                    self._gen_done.record(gen_stream)
+            else:
+                graph.replay()
             if early and si == 0:
                 self._stage_inputs(imgs, 'rest')          # CPU draws of tau / z1 while the generator sample runs
             if isinstance(exchange, str):         # 'imgs': the next graph reads the image batch
