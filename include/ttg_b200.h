@@ -292,6 +292,9 @@ int ttg_dot_f32out(const void* a, const void* b, float* out, long long n, void* 
 
 /* ---- spectral norm power iteration (torch.nn.utils.spectral_norm semantics; the seam is the
  * conv_factory kwarg of the blocks: generator.py:34, discriminator.py:28,52) */
+/* one launch each: a cluster of 8 CTAs, phases separated by cluster barriers, fixed-order sums (bitwise repeatable);
+ * workspace: ttg_spectral_norm_workspace_floats(rows, cols) floats (also enough for _sigma and _bwd) */
+size_t ttg_spectral_norm_workspace_floats(int rows, int cols);
 int ttg_spectral_norm(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
                       int n_iter, float eps, void* workspace, void* stream);
 int ttg_spectral_norm_sigma(const float* w, const float* u, const float* v, float* w_out, float* sigma, int rows,

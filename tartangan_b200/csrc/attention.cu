@@ -228,11 +228,18 @@ extern "C" int ttg_dot_f32out(const void* a, const void* b, float* out, long lon
 
 // ---------------------------------------------------------------- spectral norm power iteration
 // W is [rows, cols] fp32 row-major (conv weight viewed (Cout, Cin*k*k), at most 256 x 2304 = 2.4 MB, L2 resident).
-// ONE launch of ONE 1024-thread CTA per call (the matrices are tiny; a launch costs more than the arithmetic):
-//   per iteration  v = normalize(W^T u)   (thread per column, coalesced across the warp)
-//                  u = normalize(W v)     (warp per row, shuffle reduction)
-//   then sigma = u^T W v and w_out = W / sigma.  Fixed summation order: bitwise repeatable from run to run.
-// u / v live in shared memory between the phases; `workspace` is unused (kept in the ABI).
+// ONE launch per call: a thread-block CLUSTER of 8 CTAs (the matrices are tiny, a launch costs more than the
+// arithmetic, but one CTA alone reads 2.4 MB four times at ~50 GB/s: 217 us).  The phases are separated by cluster
+// barriers; partial results travel through a small global workspace:
+//   per iteration  v = normalize(W^T u)   (CTA = a slice of the columns; threads = column x row-group, fixed-order sums)
+//                  u = normalize(W v)     (CTA = a slice of the rows; warp per row, shuffle reduction)
+//   then sigma = u^T W v and w_out = W / sigma (CTA = a slice of the elements).
+// Every sum has a fixed order: bitwise repeatable from run to run.
+// workspace: 2 * SN_CL + rows + cols floats (ttg_spectral_norm_workspace_floats).
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define SN_CL 8
+#define SN_THREADS 512
 __device__ __forceinline__ float sn_block_sum(float x, float* red) {      // all threads get the total
   x = warp_sum(x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -243,96 +250,141 @@ __device__ __forceinline__ float sn_block_sum(float x, float* red) {      // all
   for (int i = 0; i < nw; ++i) t += red[i];
   return t;
 }
+__device__ __forceinline__ void sn_cluster_barrier(cg::cluster_group& cl) { __threadfence(); cl.sync(); }
+__device__ __forceinline__ float sn_sum_partials(const volatile float* p) {
+  float t = 0.f;
+  for (int i = 0; i < SN_CL; ++i) t += p[i];
+  return t;
+}
 // n_iter == 0: eval mode, sigma from the stored u, v without updating them
-__global__ void __launch_bounds__(1024) sn_fused_kernel(const float* __restrict__ w, float* __restrict__ u_g, float* __restrict__ v_g,
-                                                        float* __restrict__ w_out, float* __restrict__ sigma_g, int rows, int cols,
-                                                        int n_iter, float eps) {
-  extern __shared__ float sn_smem[];
-  float* u = sn_smem; float* v = u + rows; float* wv = v + cols; float* red = wv + rows;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-  for (int r = tid; r < rows; r += blockDim.x) u[r] = u_g[r];
-  for (int c = tid; c < cols; c += blockDim.x) v[c] = v_g[c];
-  __syncthreads();
+__global__ void __cluster_dims__(SN_CL, 1, 1) __launch_bounds__(SN_THREADS)
+sn_fused_kernel(const float* __restrict__ w, float* __restrict__ u_g, float* __restrict__ v_g, float* __restrict__ w_out,
+                float* __restrict__ sigma_g, int rows, int cols, int n_iter, float eps, float* __restrict__ ws) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
+  __shared__ float red[32];
+  __shared__ float part[SN_THREADS];
+  volatile float* pv = ws;                  // [SN_CL] partial |v|^2
+  volatile float* pu = ws + SN_CL;          // [SN_CL] partial |u|^2 (or partial sigma)
+  float* vraw = ws + 2 * SN_CL;             // [cols]
+  float* uraw = vraw + cols;                // [rows]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = SN_THREADS / 32;
+  const int c_per = (cols + SN_CL - 1) / SN_CL, c0 = rank * c_per, c1 = min(cols, c0 + c_per);
+  const int r_per = (rows + SN_CL - 1) / SN_CL, r0 = rank * r_per, r1 = min(rows, r0 + r_per);
+  float inv_v = 1.f, inv_u = 1.f;           // scale of vraw / uraw (1: they hold the stored, normalised vectors)
+  if (n_iter == 0) {
+    for (int c = c0 + tid; c < c1; c += SN_THREADS) vraw[c] = v_g[c];
+    for (int r = r0 + tid; r < r1; r += SN_THREADS) uraw[r] = u_g[r];
+    sn_cluster_barrier(cl);
+  }
   for (int it = 0; it < n_iter; ++it) {
+    // ---- v = W^T u over this CTA's columns: thread = (column, row group); the groups are summed in a fixed order
     float sq = 0.f;
-    for (int c = tid; c < cols; c += blockDim.x) {
+    for (int cb = c0; cb < c1; cb += SN_THREADS) {
+      const int ncs = min(SN_THREADS, c1 - cb);            // columns in this pass (all of the slice unless it is huge)
+      const int rg = SN_THREADS / ncs;                      // row groups
+      const int cl_ = tid % ncs, g = tid / ncs;
       float a = 0.f;
-      for (int r = 0; r < rows; ++r) a += w[(long long)r * cols + c] * u[r];
-      v[c] = a; sq += a * a;
+      if (g < rg)
+        for (int r = g; r < rows; r += rg) a += w[(long long)r * cols + cb + cl_] * (it == 0 ? u_g[r] : __ldcg(&uraw[r]) * inv_u);
+      __syncthreads();
+      part[tid] = a;
+      __syncthreads();
+      if (tid < ncs) {
+        float t = 0.f;
+        for (int gg = 0; gg < rg; ++gg) t += part[gg * ncs + tid];
+        vraw[cb + tid] = t; sq += t * t;
+      }
     }
-    const float inv_v = 1.f / fmaxf(sqrtf(sn_block_sum(sq, red)), eps);
-    for (int c = tid; c < cols; c += blockDim.x) v[c] *= inv_v;
-    __syncthreads();
+    const float sqb = sn_block_sum(sq, red);
+    if (tid == 0) pv[rank] = sqb;
+    sn_cluster_barrier(cl);
+    inv_v = 1.f / fmaxf(sqrtf(sn_sum_partials(pv)), eps);
+    // ---- u = W v over this CTA's rows: warp per row
     sq = 0.f;
-    for (int r = warp; r < rows; r += nw) {
+    for (int r = r0 + warp; r < r1; r += nw) {
       const float* wr = w + (long long)r * cols;
       float a = 0.f;
-      for (int c = lane; c < cols; c += 32) a += wr[c] * v[c];
-      a = warp_sum(a);
-      if (lane == 0) { u[r] = a; sq += a * a; }
+      for (int c = lane; c < cols; c += 32) a += wr[c] * __ldcg(&vraw[c]);      // (written by other SMs: bypass L1)
+      a = warp_sum(a) * inv_v;
+      if (lane == 0) { uraw[r] = a; sq += a * a; }
     }
-    const float inv_u = 1.f / fmaxf(sqrtf(sn_block_sum(sq, red)), eps);
-    for (int r = tid; r < rows; r += blockDim.x) u[r] *= inv_u;
-    __syncthreads();
+    const float squ = sn_block_sum(sq, red);
+    if (tid == 0) pu[rank] = squ;
+    sn_cluster_barrier(cl);
+    inv_u = 1.f / fmaxf(sqrtf(sn_sum_partials(pu)), eps);
   }
-  // sigma = u^T (W v)
-  float part = 0.f;
-  for (int r = warp; r < rows; r += nw) {
-    const float* wr = w + (long long)r * cols;
-    float a = 0.f;
-    for (int c = lane; c < cols; c += 32) a += wr[c] * v[c];
-    a = warp_sum(a);
-    if (lane == 0) part += a * u[r];
-  }
-  const float sigma = sn_block_sum(part, red);
-  const float inv = 1.f / sigma;
-  const long long n = (long long)rows * cols;
-  for (long long i = tid; i < n; i += blockDim.x) w_out[i] = w[i] * inv;
+  float sigma;
   if (n_iter > 0) {
-    for (int r = tid; r < rows; r += blockDim.x) u_g[r] = u[r];
-    for (int c = tid; c < cols; c += blockDim.x) v_g[c] = v[c];
+    sigma = sn_sum_partials(pu) * inv_u;                    // u^T W v with u = W v / |W v|
+  } else {
+    float p = 0.f;
+    for (int r = r0 + warp; r < r1; r += nw) {
+      const float* wr = w + (long long)r * cols;
+      float a = 0.f;
+      for (int c = lane; c < cols; c += 32) a += wr[c] * __ldcg(&vraw[c]);
+      a = warp_sum(a);
+      if (lane == 0) p += a * __ldcg(&uraw[r]);
+    }
+    const float pb = sn_block_sum(p, red);
+    if (tid == 0) pu[rank] = pb;
+    sn_cluster_barrier(cl);
+    sigma = sn_sum_partials(pu);
   }
-  if (tid == 0) sigma_g[0] = sigma;
+  const float inv = 1.f / sigma;
+  const long long n = (long long)rows * cols, per = (n + SN_CL - 1) / SN_CL, e0 = rank * per, e1 = min(n, e0 + per);
+  for (long long i = e0 + tid; i < e1; i += SN_THREADS) w_out[i] = w[i] * inv;
+  if (n_iter > 0) {
+    for (int r = r0 + tid; r < r1; r += SN_THREADS) u_g[r] = uraw[r] * inv_u;
+    for (int c = c0 + tid; c < c1; c += SN_THREADS) v_g[c] = vraw[c] * inv_v;
+  }
+  if (rank == 0 && tid == 0) sigma_g[0] = sigma;
 }
+extern "C" size_t ttg_spectral_norm_workspace_floats(int rows, int cols) { return (size_t)(2 * SN_CL + rows + cols + 16); }
 static int sn_launch(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols, int n_iter, float eps,
-                     cudaStream_t st, const char* name) {
-  TTG_REQUIRE(rows > 0 && cols > 0 && rows + cols <= 8192, "spectral_norm: matrix too large for the single-CTA kernel");
-  const size_t smem = sizeof(float) * (size_t)(2 * rows + cols + 32);
-  sn_fused_kernel<<<1, 1024, smem, st>>>(w, u, v, w_out, sigma, rows, cols, n_iter, eps);
+                     float* ws, cudaStream_t st, const char* name) {
+  TTG_REQUIRE(rows > 0 && cols > 0 && ws != nullptr, "spectral_norm: bad arguments");
+  sn_fused_kernel<<<SN_CL, SN_THREADS, 0, st>>>(w, u, v, w_out, sigma, rows, cols, n_iter, eps, ws);
   TTG_CHECK_LAUNCH(name);
   return TTG_OK;
 }
 extern "C" int ttg_spectral_norm(const float* w, float* u, float* v, float* w_out, float* sigma, int rows, int cols,
                                  int n_iter, float eps, void* workspace, void* stream) {
-  (void)workspace;
   TTG_REQUIRE(n_iter >= 1, "spectral_norm: n_iter must be >= 1");
-  return sn_launch(w, u, v, w_out, sigma, rows, cols, n_iter, eps, (cudaStream_t)stream, "spectral_norm");
+  return sn_launch(w, u, v, w_out, sigma, rows, cols, n_iter, eps, (float*)workspace, (cudaStream_t)stream, "spectral_norm");
 }
 // eval mode: sigma = u^T W v with the given (already normalised) u, v; no update
 extern "C" int ttg_spectral_norm_sigma(const float* w, const float* u, const float* v, float* w_out, float* sigma, int rows,
                                        int cols, void* workspace, void* stream) {
-  (void)workspace;
-  return sn_launch(w, (float*)u, (float*)v, w_out, sigma, rows, cols, 0, 0.f, (cudaStream_t)stream, "spectral_norm_sigma");
+  return sn_launch(w, (float*)u, (float*)v, w_out, sigma, rows, cols, 0, 0.f, (float*)workspace, (cudaStream_t)stream,
+                   "spectral_norm_sigma");
 }
 // g_w = (g - dot(g, w_out) * u v^T) / sigma   (u, v constants: torch.nn.utils.spectral_norm detaches them); one launch
-__global__ void __launch_bounds__(1024) sn_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ w_out,
-                                                            const float* __restrict__ u, const float* __restrict__ v,
-                                                            const float* __restrict__ sigma, float* __restrict__ gw, int rows, int cols) {
+__global__ void __cluster_dims__(SN_CL, 1, 1) __launch_bounds__(SN_THREADS)
+sn_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ w_out, const float* __restrict__ u,
+                    const float* __restrict__ v, const float* __restrict__ sigma, float* __restrict__ gw, int rows, int cols,
+                    float* __restrict__ ws) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank();
   __shared__ float red[32];
-  const long long n = (long long)rows * cols;
+  volatile float* pd = ws;
+  const long long n = (long long)rows * cols, per = (n + SN_CL - 1) / SN_CL, e0 = rank * per, e1 = min(n, e0 + per);
   float part = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) part += g[i] * w_out[i];
-  const float d = sn_block_sum(part, red);
+  for (long long i = e0 + threadIdx.x; i < e1; i += SN_THREADS) part += g[i] * w_out[i];
+  const float pb = sn_block_sum(part, red);
+  if (threadIdx.x == 0) pd[rank] = pb;
+  sn_cluster_barrier(cl);
+  const float d = sn_sum_partials(pd);
   const float inv = 1.f / sigma[0];
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+  for (long long i = e0 + threadIdx.x; i < e1; i += SN_THREADS) {
     const int r = (int)(i / cols), c = (int)(i % cols);
     gw[i] = (g[i] - d * u[r] * v[c]) * inv;
   }
 }
 extern "C" int ttg_spectral_norm_bwd(const float* g, const float* w_out, const float* u, const float* v, const float* sigma,
                                      float* gw, int rows, int cols, void* workspace, void* stream) {
-  (void)workspace;
-  sn_bwd_fused_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, w_out, u, v, sigma, gw, rows, cols);
+  TTG_REQUIRE(workspace != nullptr, "spectral_norm_bwd: workspace missing");
+  sn_bwd_fused_kernel<<<SN_CL, SN_THREADS, 0, (cudaStream_t)stream>>>(g, w_out, u, v, sigma, gw, rows, cols, (float*)workspace);
   TTG_CHECK_LAUNCH("spectral_norm_bwd");
   return TTG_OK;
 }

@@ -1712,7 +1712,7 @@ class SpectralNormFn(Function):
         rows, cols = w.shape[0], w[0].numel()
         w_out = torch.empty_like(wd)
         sigma = torch.empty(1, dtype=torch.float32, device=w.device)
-        ws = torch.empty(4 + rows + cols, dtype=torch.float32, device=w.device)
+        ws = torch.empty(_lib.lib.ttg_spectral_norm_workspace_floats(rows, cols), dtype=torch.float32, device=w.device)
         if n_iter > 0:
             call('ttg_spectral_norm', ptr(wd), ptr(u), ptr(v), ptr(w_out), ptr(sigma), rows, cols, n_iter, eps, ptr(ws))
         else:       # eval: sigma = u^T W v with the stored vectors, no update
@@ -1729,5 +1729,5 @@ class SpectralNormFn(Function):
         rows, cols = w_out.shape[0], w_out[0].numel()
         gw = torch.empty_like(w_out)
         call('ttg_spectral_norm_bwd', ptr(g), ptr(w_out), ptr(u), ptr(v), ptr(sigma), ptr(gw), rows, cols,
-             ptr(_ws(8, g.device)))
+             ptr(_ws(4 * _lib.lib.ttg_spectral_norm_workspace_floats(rows, cols), g.device)))
         return gw, None, None, None, None

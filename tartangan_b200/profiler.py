@@ -54,6 +54,8 @@ _STREAM_MODELS = {
     # (x, y, N, Hi, Wi, C, dtype): full-resolution tensor + quarter-resolution tensor
     'ttg_bilinear_down_fwd': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', int(a[2] * a[3] * a[4] * a[5] * _elt(a[6]) * 1.25)),
     'ttg_bilinear_down_bwd': lambda a: (f'N{a[2]} {a[3]}x{a[4]} C{a[5]}', int(a[2] * a[3] * a[4] * a[5] * _elt(a[6]) * 1.25)),
+    # (gy, add, gx, N, Hi, Wi, C, dtype): + the full-resolution addend
+    'ttg_bilinear_down_bwd_add': lambda a: (f'N{a[3]} {a[4]}x{a[5]} C{a[6]}', int(a[3] * a[4] * a[5] * a[6] * _elt(a[7]) * (2.25 if a[1] else 1.25))),
     # (a, b, out, n, alpha, beta, dtype)
     'ttg_axpby': lambda a: (f'n{a[3]}', a[3] * _elt(a[6]) * (2 if a[0] == a[1] else 3)),
     # (x, y8, npix, c_real): bf16

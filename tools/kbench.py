@@ -143,13 +143,13 @@ def spectral(rows, cols):
     u = torch.nn.functional.normalize(torch.randn(rows, device='cuda'), dim=0)
     v = torch.nn.functional.normalize(torch.randn(cols, device='cuda'), dim=0)
     out = torch.empty_like(w); sigma = torch.empty(1, device='cuda'); g = torch.randn_like(w); gw = torch.empty_like(w)
-    ws = torch.empty(16 + rows + cols, device='cuda')
+    ws = torch.empty(_lib.lib.ttg_spectral_norm_workspace_floats(rows, cols), device='cuda')
     fwd = lambda: call('ttg_spectral_norm', ptr(w), ptr(u), ptr(v), ptr(out), ptr(sigma), rows, cols, 1, 1e-12, ptr(ws))
     bwd = lambda: call('ttg_spectral_norm_bwd', ptr(g), ptr(out), ptr(u), ptr(v), ptr(sigma), ptr(gw), rows, cols, ptr(ws))
     for name, fn, passes in (('fwd (W^T u, W v, sigma, W / sigma: 4 passes over W)', fwd, 5), ('bwd (dot + update: 2 passes)', bwd, 5)):
         med, best = timeit(fn)
         nb = rows * cols * 4 * passes
-        print(f'spectral_norm {name} {rows}x{cols}: median {med*1e3:.1f} us  ({nb/1e6:.2f} MB of L2-resident traffic, one CTA -> {nb/med/1e6:.0f} GB/s)')
+        print(f'spectral_norm {name} {rows}x{cols}: median {med*1e3:.1f} us  ({nb/1e6:.2f} MB of L2-resident traffic, -> {nb/med/1e6:.0f} GB/s)')
 
 
 if sys.argv[1] == 'sn':
