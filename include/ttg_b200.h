@@ -212,6 +212,14 @@ int ttg_u8_crop_normalize(const unsigned char* stack, const int* index, const in
                           int H, int W, int C, int size, int dtype_out, int nchw_out, void* stream);
 int ttg_cast(const void* x, int src_dtype, void* y, int dst_dtype, long long n, void* stream);
 /* nn.Tanh at the generator output (generator.py:126) */
+/* generator head (GeneratorOutput, generator.py:115-129): y = tanh(conv1x1(a, w) + bias) for C -> 3, a bf16 NHWC, y fp32
+ * NCHW (the module boundary's layout): one streaming CUDA-core kernel instead of an N = 3 GEMM + tanh + layout pass;
+ * _bwd: input gradient (bf16 NHWC), weight and bias gradients (fp32; added to gw / gb when accumulate) in one pass */
+int ttg_rgb_head_supported(int Cin, int Cout);
+size_t ttg_rgb_head_workspace_bytes(int Cin);
+int ttg_rgb_head_fwd(const void* a, const float* w, const float* bias, float* y, int N, int HW, int Cin, void* stream);
+int ttg_rgb_head_bwd(const void* a, const float* w, const float* y, const float* g, void* ga, float* gw, float* gb, int N,
+                     int HW, int Cin, int accumulate, void* workspace, void* stream);
 int ttg_tanh_fwd(const float* x, float* y, long long n, void* stream);
 int ttg_tanh_bwd(const float* y, const float* g, float* gx, long long n, void* stream);
 

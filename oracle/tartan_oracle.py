@@ -3,9 +3,11 @@
 This file is a functional (state-dict driven) fp32 restatement, on CPU torch,
 of the arithmetic of the reference hot path.  It exists so that the CUDA path
 in ``tartangan_b200`` can be checked on a box where ``/root/reference`` does
-not exist.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.
-The product package never does.
+not exist.  Only ``tests/``, ``__graft_entry__.smoke()``, the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` and the
+measurement tools under ``tools/`` (golden-vector generation; the same-box
+stock-PyTorch bar ``tools/bench_eager_gpu.py``, which runs THIS composition on
+``cuda`` through cuDNN / ATen) may import it.  The product package never does.
 
 Parity status: PINNED against outputs of the reference itself, run in the build
 container (``tools/make_golden.py`` imports ``/root/reference`` read-only and

@@ -109,7 +109,7 @@ def stream():
 
 # kernels launched per entry point (for the bench's gpu_launches counter)
 KERNELS_PER_CALL = {
-    'ttg_bn_stats': 2, 'ttg_conv2d_wgrad_direct_det': 2, 'ttg_bn_act_bwd': 2, 'ttg_bn_act_bwd2': 2, 'ttg_channel_sum': 2, 'ttg_sqsum_f32': 2,
+    'ttg_bn_stats': 2, 'ttg_rgb_head_bwd': 2, 'ttg_conv2d_wgrad_direct_det': 2, 'ttg_bn_act_bwd': 2, 'ttg_bn_act_bwd2': 2, 'ttg_channel_sum': 2, 'ttg_sqsum_f32': 2,
     'ttg_dot_f32out': 2, 'ttg_adam_flat': 2, 
     'ttg_attn_bwd': 3, 'ttg_conv2d_wgrad_tc_acc': 2, 'ttg_bn_act_bwd_acc': 2, 'ttg_bn_act_bwd2_acc': 2, 'ttg_channel_sum_acc': 2, 'ttg_conv2d_wgrad_tc': 2, 'ttg_conv2d_wgrad_tc_ex': 2, 'ttg_conv2d_wgrad_bias_tc_ex': 2,
 }

@@ -203,18 +203,38 @@ __device__ __forceinline__ int bil_candidates(int i, int in, int out, int* oidx,
 // one thread per input pixel: the (<= 3 x 3) contributing outputs and their weights are found once,
 // then every channel vector of the pixel is gathered with them
 // `add` (optional, same shape as gx): gx = add + B^T gy — the gradient fan-in of a D block's input (skip branch + conv
-// branch, discriminator.py:90-95) without a separate add pass
+// branch, discriminator.py:90-95) without a separate add pass.
+// The contributing outputs and weights of a pixel depend on its row and on its column only: every block first builds
+// the two candidate tables ((Hi + Wi) entries) in shared memory, instead of 8 divisions per pixel (109 us for the RGB
+// gradient of a 256 x 128 x 128 batch, where a pixel is only 3 elements).
 template <typename T, int V>
-__global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ add, T* __restrict__ gx, int N, int Hi, int Wi, int C) {
+__global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ add, T* __restrict__ gx, int N, int Hi, int Wi, int C, int pervec) {
+  extern __shared__ __align__(16) unsigned char bil_smem[];
+  int* s_n = reinterpret_cast<int*>(bil_smem);                  // [Hi + Wi] candidate counts (rows first, then columns)
+  int* s_o = s_n + (Hi + Wi);                                   // [Hi + Wi][4] output indices
+  float* s_w = reinterpret_cast<float*>(s_o + 4 * (Hi + Wi));   // [Hi + Wi][4] weights
   const int cv = C / V; const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long total = (long long)N * Hi * Wi;
-  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+  for (int e = threadIdx.x; e < Hi + Wi; e += blockDim.x) {
+    int o[4]; float w[4];
+    const int n = e < Hi ? bil_candidates(e, Hi, Ho, o, w) : bil_candidates(e - Hi, Wi, Wo, o, w);
+    s_n[e] = n;
+    for (int k = 0; k < 4; ++k) { s_o[4 * e + k] = k < n ? o[k] : 0; s_w[4 * e + k] = k < n ? w[k] : 0.f; }
+  }
+  __syncthreads();
+  // pervec: one work item = one channel vector of one pixel, so that the small deep layers (8 x 8 x 128 channels: 16 K
+  // pixels) spread over the whole GPU; otherwise one item = one pixel (few vectors per pixel: the table lookups are
+  // shared; measured faster for C <= 16: 82.6 vs 120 us on the RGB gradient, 32 vs 41 us at 64 x 64 x 16)
+  const int per = pervec ? cv : 1;
+  const long long total = (long long)N * Hi * Wi * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / per;
+    const int v0 = pervec ? (int)(i % per) : 0, v1 = pervec ? v0 + 1 : cv;
     const int ix = (int)(p % Wi); const long long q = p / Wi; const int iy = (int)(q % Hi); const int n = (int)(q / Hi);
-    int oys[4], oxs[4]; float wys[4], wxs[4];
-    const int ny = bil_candidates(iy, Hi, Ho, oys, wys), nx = bil_candidates(ix, Wi, Wo, oxs, wxs);
+    const int ny = s_n[iy], nx = s_n[Hi + ix];
+    const int* oys = s_o + 4 * iy; const int* oxs = s_o + 4 * (Hi + ix);
+    const float* wys = s_w + 4 * iy; const float* wxs = s_w + 4 * (Hi + ix);
     const T* gbase = gy + (long long)n * Ho * Wo * C;
-    T* dst = gx + p * C;
-    for (int v = 0; v < cv; ++v) {
+    for (int v = v0; v < v1; ++v) {
       float acc[V];
       if (add) Ld<T, V>::ld(add + p * C + v * V, acc);
       else {
@@ -229,7 +249,7 @@ __global__ void bilinear_down_bwd_kernel(const T* __restrict__ gy, const T* __re
 #pragma unroll
           for (int j = 0; j < V; ++j) acc[j] += w * g[j];
         }
-      Ld<T, V>::st(dst + v * V, acc);
+      Ld<T, V>::st(gx + p * C + v * V, acc);
     }
   }
 }
@@ -256,6 +276,8 @@ extern "C" int ttg_bilinear_down_bwd_add(const void* gy, const void* add, void* 
   const long long pixels = (long long)N * Hi * Wi;
   // (measured in the step profile: ~200 us per RGB launch against ~98 us for the thread-per-pixel kernel below, whose
   // per-pixel candidate search is shared by the channels; kept for A/B only)
+  const size_t bsm = (size_t)(Hi + Wi) * 9 * sizeof(int);           // candidate tables of the thread-per-pixel kernel
+  TTG_REQUIRE(bsm <= 48 * 1024, "bilinear_down_bwd: image too large for the candidate tables (%d x %d)", Hi, Wi);
   static const bool use_elem = getenv("TTG_BILELEM") != nullptr;
   if (C < 8 && use_elem) {
     TTG_DISPATCH(dtype, {
@@ -264,9 +286,10 @@ extern "C" int ttg_bilinear_down_bwd_add(const void* gy, const void* add, void* 
     TTG_CHECK_LAUNCH("bilinear_down_bwd_elem");
     return TTG_OK;
   }
+  const int pv = C >= 32 ? 1 : 0;
   TTG_DISPATCH(dtype, {
-    if (vec2_ok<T>(C, gy, gx) && (add == nullptr || vec2_ok<T>(C, add, gx))) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, Vec<T>::N>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C); }
-    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, 1>, pixels, 128, 128), 128, 0, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C); }
+    if (vec2_ok<T>(C, gy, gx) && (add == nullptr || vec2_ok<T>(C, add, gx))) { bilinear_down_bwd_kernel<T, Vec<T>::N><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, Vec<T>::N>, pixels * (pv ? C / Vec<T>::N : 1), 128 * 4, 128, bsm), 128, bsm, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C, pv); }
+    else { bilinear_down_bwd_kernel<T, 1><<<ttg_grid_occ(bilinear_down_bwd_kernel<T, 1>, pixels * (C > 16 ? C : 1), 128 * 4, 128, bsm), 128, bsm, st>>>((const T*)gy, (const T*)add, (T*)gx, N, Hi, Wi, C, C > 16 ? 1 : 0); }
   });
   TTG_CHECK_LAUNCH("bilinear_down_bwd");
   return TTG_OK;
@@ -599,6 +622,126 @@ extern "C" int ttg_cast(const void* x, int src_dtype, void* y, int dst_dtype, lo
   else if (src_dtype == TTG_BF16 && dst_dtype == TTG_BF16) cast_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, n);
   else return ttg_set_error(TTG_ERR_ARG, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
   TTG_CHECK_LAUNCH("cast");
+  return TTG_OK;
+}
+
+// ---------------------------------------------------------------- generator head: conv1x1(C -> 3) + tanh + layout boundary
+// GeneratorOutput (generator.py:115-129) ends with conv1x1(C -> data_dims = 3) -> tanh, and the module boundary returns
+// fp32 NCHW.  As a GEMM this layer has N = 3: on the tensor-core path it took 176 us (fp32 3-channel epilogue) + tanh +
+// the NHWC -> NCHW pass.  It is a pure HBM stream (32 B read, 12 B written per pixel), so: one CUDA-core kernel, a thread
+// per pixel, fp32 weights and accumulation, tanh, and the three fp32 planes written directly (coalesced over pixels).
+// Backward in one kernel as well: gpre = g (1 - y^2); ga[p, ci] = sum_co gpre[co] w[co, ci] (bf16 NHWC); the 3 x C
+// weight gradient and the bias gradient are reduced per thread -> warp -> block -> one fp64 atomic per value and block.
+#define RGB_CO 3
+template <int CIN>
+__global__ void __launch_bounds__(256) rgb_head_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y, long long npix, int HW) {
+  __shared__ float sw[RGB_CO * CIN + RGB_CO];
+  for (int i = threadIdx.x; i < RGB_CO * CIN; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < RGB_CO) sw[RGB_CO * CIN + threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    float x[CIN];
+#pragma unroll
+    for (int v = 0; v < CIN / 8; ++v) { Vec<bf16> q; q.load(a + p * CIN + v * 8); q.unpack(x + v * 8); }
+    const long long n = p / HW; const int pp = (int)(p % HW);
+#pragma unroll
+    for (int co = 0; co < RGB_CO; ++co) {
+      float acc = sw[RGB_CO * CIN + co];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) acc += x[ci] * sw[co * CIN + ci];
+      y[(n * RGB_CO + co) * HW + pp] = tanhf(acc);
+    }
+  }
+}
+template <int CIN>
+__global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const bf16* __restrict__ a, const float* __restrict__ w,
+                                                           const float* __restrict__ y, const float* __restrict__ g,
+                                                           bf16* __restrict__ ga, double* __restrict__ sums, long long npix, int HW) {
+  constexpr int NW = RGB_CO * CIN + RGB_CO;          // weight gradient [co][ci] then bias gradient [co]
+  __shared__ float sw[RGB_CO * CIN];
+  __shared__ float s_acc[NW];
+  for (int i = threadIdx.x; i < RGB_CO * CIN; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < NW; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float gw[RGB_CO][CIN], gb[RGB_CO];
+#pragma unroll
+  for (int co = 0; co < RGB_CO; ++co) {
+    gb[co] = 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) gw[co][ci] = 0.f;
+  }
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const long long n = p / HW; const int pp = (int)(p % HW);
+    float gp[RGB_CO];
+#pragma unroll
+    for (int co = 0; co < RGB_CO; ++co) {
+      const long long o = (n * RGB_CO + co) * HW + pp;
+      const float t = y[o];
+      gp[co] = g[o] * (1.f - t * t);
+      gb[co] += gp[co];
+    }
+    float x[CIN], o[CIN];
+#pragma unroll
+    for (int v = 0; v < CIN / 8; ++v) { Vec<bf16> q; q.load(a + p * CIN + v * 8); q.unpack(x + v * 8); }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float acc = 0.f;
+#pragma unroll
+      for (int co = 0; co < RGB_CO; ++co) { acc += gp[co] * sw[co * CIN + ci]; gw[co][ci] += gp[co] * x[ci]; }
+      o[ci] = acc;
+    }
+#pragma unroll
+    for (int v = 0; v < CIN / 8; ++v) { Vec<bf16> q; q.pack(o + v * 8); q.store(ga + p * CIN + v * 8); }
+  }
+#pragma unroll
+  for (int co = 0; co < RGB_CO; ++co) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float t = gw[co][ci];
+      for (int s = 16; s >= 1; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[co * CIN + ci], t);
+    }
+    float t = gb[co];
+    for (int s = 16; s >= 1; s >>= 1) t += __shfl_xor_sync(0xffffffffu, t, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[RGB_CO * CIN + co], t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NW; i += blockDim.x) atomicAdd(&sums[i], (double)s_acc[i]);
+}
+__global__ void rgb_head_finalize_kernel(const double* __restrict__ sums, float* __restrict__ gw, float* __restrict__ gb, int nw, int acc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nw) { if (acc) atomicAdd(&gw[i], (float)sums[i]); else gw[i] = (float)sums[i]; }
+  else if (i < nw + RGB_CO && gb) { if (acc) atomicAdd(&gb[i - nw], (float)sums[i]); else gb[i - nw] = (float)sums[i]; }
+}
+extern "C" int ttg_rgb_head_supported(int Cin, int Cout) { return Cout == RGB_CO && (Cin == 8 || Cin == 16 || Cin == 32) ? 1 : 0; }
+extern "C" size_t ttg_rgb_head_workspace_bytes(int Cin) { return sizeof(double) * (size_t)(RGB_CO * Cin + RGB_CO); }
+// a: bf16 NHWC [N, HW, Cin]; w: fp32 [3][Cin]; y: fp32 NCHW [N, 3, HW] = tanh(conv1x1(a) + bias)
+extern "C" int ttg_rgb_head_fwd(const void* a, const float* w, const float* bias, float* y, int N, int HW, int Cin, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(ttg_rgb_head_supported(Cin, RGB_CO), "rgb_head_fwd: Cin = %d unsupported", Cin);
+  const long long npix = (long long)N * HW;
+#define TTG_RGB_F(C) rgb_head_fwd_kernel<C><<<ttg_grid_occ(rgb_head_fwd_kernel<C>, npix, 256 * 2), 256, 0, st>>>((const bf16*)a, w, bias, y, npix, HW)
+  if (Cin == 8) TTG_RGB_F(8); else if (Cin == 16) TTG_RGB_F(16); else TTG_RGB_F(32);
+#undef TTG_RGB_F
+  TTG_CHECK_LAUNCH("rgb_head_fwd");
+  return TTG_OK;
+}
+// g: fp32 NCHW cotangent of y; ga: bf16 NHWC [N, HW, Cin]; gw [3][Cin] / gb [3] overwritten (accumulate = 0) or added to
+extern "C" int ttg_rgb_head_bwd(const void* a, const float* w, const float* y, const float* g, void* ga, float* gw, float* gb,
+                                int N, int HW, int Cin, int accumulate, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TTG_REQUIRE(ttg_rgb_head_supported(Cin, RGB_CO) && workspace != nullptr, "rgb_head_bwd: bad arguments (Cin = %d)", Cin);
+  const long long npix = (long long)N * HW;
+  double* sums = (double*)workspace;
+  const int nw = RGB_CO * Cin;
+  cudaMemsetAsync(sums, 0, sizeof(double) * (nw + RGB_CO), st);
+#define TTG_RGB_B(C) rgb_head_bwd_kernel<C><<<ttg_grid_occ(rgb_head_bwd_kernel<C>, npix, 256 * 8), 256, 0, st>>>((const bf16*)a, w, y, g, (bf16*)ga, sums, npix, HW)
+  if (Cin == 8) TTG_RGB_B(8); else if (Cin == 16) TTG_RGB_B(16); else TTG_RGB_B(32);
+#undef TTG_RGB_B
+  TTG_CHECK_LAUNCH("rgb_head_bwd");
+  rgb_head_finalize_kernel<<<1, 128, 0, st>>>(sums, gw, gb, nw, accumulate);
+  TTG_CHECK_LAUNCH("rgb_head_finalize");
   return TTG_OK;
 }
 

@@ -21,6 +21,7 @@ from ..layers import (BatchNorm2d, Conv2d, Interpolate, LeakyReLU, Linear, Tanh,
 # default: rounding the pre-activation to bf16 before tanh lowered the gradient cosine of one mid-generator BatchNorm
 # beta from ~0.975 to ~0.968 in 2 of 5 runs of tests/test_gpu_parity_configs.py (bar 0.97); parity comes first.
 _FP32_TAIL = os.environ.get('TTG_GTAIL_BF16', '0') != '1'
+_RGB_HEAD = os.environ.get('TTG_RGB_HEAD', '1') == '1'       # A/B switch: the fused generator head (ops.RgbHeadFn)
 
 
 class GeneratorBlock(nn.Module):
@@ -129,6 +130,11 @@ class GeneratorOutput(nn.Module):
         layers = list(self.convs)
         x = run_layers(layers[:2], ops.ensure_internal(x))
         conv = layers[2]
+        if (type(conv) is Conv2d and len(layers) == 4 and isinstance(layers[3], Tanh) and _RGB_HEAD
+                and ops.rgb_head_ok(conv, x)):
+            # bf16 mode, C -> 3: conv1x1 + tanh + the fp32 NCHW boundary as ONE streaming kernel (fp32 weights and
+            # accumulation: no precision is given up, unlike the bf16 tail below)
+            return ops.RgbHeadFn.apply(x, conv.weight, conv.bias)
         if (isinstance(conv, Conv2d) and len(layers) == 4 and isinstance(layers[3], Tanh)
                 and ops.state.act_dtype == ops.torch.bfloat16 and not _FP32_TAIL):
             # opt-in (see _FP32_TAIL): the C -> 3 conv writes bf16 through the 8-channel TMA staging (45 + 17 us instead of

@@ -165,6 +165,8 @@ def join_all_streams():
     step (the weight-gradient stream, the D(fake) stream).  Called when a backward pass ends and before a gradient
     all-reduce: the in-place kernels return no tensor to autograd, so the engine inserts no synchronisation for them
     (and a CUDA-graph capture must not end with unjoined work)."""
+    if not state.wgrad_pending and not state.pending_streams:
+        return                                    # (nothing forked: also the CPU-only host-logic tests)
     cur = torch.cuda.current_stream()
     if state.wgrad_pending:
         cur.wait_stream(state.wgrad_stream)
@@ -1140,6 +1142,47 @@ class TanhFn(Function):
 
 def tanh(x):
     return TanhFn.apply(x)
+
+
+class RgbHeadFn(Function):
+    """tanh(conv1x1(a, w) + bias) -> fp32 NCHW image: the generator's output layer (generator.py:120-129) as one
+    streaming kernel forward and one backward (ttg_rgb_head_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, a, w, bias):
+        a = nhwc(a)
+        n, cin, h, wd_ = a.shape
+        y = torch.empty((n, w.shape[0], h, wd_), dtype=torch.float32, device=a.device)
+        wf = _flat(w.detach()).view(w.shape[0], cin)
+        call('ttg_rgb_head_fwd', ptr(a), ptr(wf), ptr(bias), ptr(y), n, h * wd_, cin)
+        ctx.save_for_backward(a, w, y)
+        ctx.bias = bias
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        a, w, y = ctx.saved_tensors
+        n, cin, h, wd_ = a.shape
+        g = g.contiguous()
+        ga = _empty_like(a)
+        bias = ctx.bias
+        dw, db = _direct(w), (_direct(bias) if bias is not None else None)
+        direct = dw is not None and (bias is None or db is not None) and not state.inputs_only
+        gw = dw if direct else torch.empty_like(w, dtype=torch.float32)
+        gb = (db if direct else torch.empty(w.shape[0], dtype=torch.float32, device=a.device)) if bias is not None else None
+        ws = _ws(_lib.lib.ttg_rgb_head_workspace_bytes(cin), a.device)
+        call('ttg_rgb_head_bwd', ptr(a), ptr(_flat(w.detach())), ptr(y), ptr(g), ptr(ga), ptr(gw), ptr(gb), n, h * wd_, cin,
+             1 if direct else 0, ptr(ws))
+        if direct:
+            return ga, None, None
+        return ga, gw, gb
+
+
+def rgb_head_ok(conv, x):
+    w = conv.weight if hasattr(conv, 'weight') and isinstance(conv.weight, torch.nn.Parameter) else None
+    return (w is not None and x.dtype == torch.bfloat16 and x.dim() == 4 and w.shape[2] == 1 and w.shape[3] == 1
+            and bool(_lib.lib.ttg_rgb_head_supported(w.shape[1], w.shape[0])))
 
 
 # --------------------------------------------------------------------------- fp32 matmul / Linear

@@ -66,6 +66,9 @@ _STREAM_MODELS = {
     'ttg_nhwc_to_nchw': lambda a: (f'N{a[2]} C{a[3]} HW{a[4]}', a[2] * a[3] * a[4] * (4 + _elt(a[5]))),
     # (p, g, m, v, ema, n, ...): p, m, v read + written, g read, ema read + written when present
     'ttg_adam_flat': lambda a: (f'n{a[5]}', a[5] * 4 * (7 + (2 if a[4] else 0))),
+    # (a, w, bias, y, N, HW, Cin) / (a, w, y, g, ga, gw, gb, N, HW, Cin, ...): bf16 NHWC activations, fp32 NCHW image
+    'ttg_rgb_head_fwd': lambda a: (f'N{a[4]} HW{a[5]} C{a[6]}', a[4] * a[5] * (a[6] * 2 + 12)),
+    'ttg_rgb_head_bwd': lambda a: (f'N{a[7]} HW{a[8]} C{a[9]}', a[7] * a[8] * (a[9] * 4 + 24)),
     # (x, src_dtype, y, dst_dtype, n)
     'ttg_cast': lambda a: (f'n{a[4]}', a[4] * (_elt(a[1]) + _elt(a[3]))),
 }

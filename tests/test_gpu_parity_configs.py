@@ -100,8 +100,11 @@ def test_forward_activations_bf16(config, batch):
             out = run_cuda()
         for h in handles:
             h.remove()
-        assert set(ref_acts) <= set(acts), (net, sorted(set(ref_acts) - set(acts)))
-        errs = {k: _rel_l2(acts[k], v) for k, v in ref_acts.items()}
+        # the generator's C -> 3 output conv is fused with tanh and the layout boundary (ops.RgbHeadFn): its
+        # pre-activation is never stored, the IMAGE below is what is compared for that layer
+        head = {f'blocks.{len(t.g.blocks) - 1}.convs.2'} if net == 'g' else set()
+        assert set(ref_acts) - set(acts) <= head, (net, sorted(set(ref_acts) - set(acts)))
+        errs = {k: _rel_l2(acts[k], v) for k, v in ref_acts.items() if k in acts}
         med = sorted(errs.values())[len(errs) // 2]
         k_worst = max(errs, key=errs.get)
         worst[net] = (k_worst, errs[k_worst], med)

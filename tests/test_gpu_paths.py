@@ -256,3 +256,28 @@ def test_device_image_stack_matches_host_pipeline(tmp_path):
     assert torch.allclose(g[0], g[0]) and g.shape == (25, t.gan_config.latent_dims)
     n = g.norm(dim=1)                           # slerp between (almost) equal-norm gaussians keeps the norm in their range
     assert float(n.min()) > 0.5 * float(n.max())
+
+
+def test_generator_head_fused_kernel():
+    """ops.RgbHeadFn (ttg_rgb_head_fwd / _bwd): tanh(conv1x1(a) + b) -> fp32 NCHW and its three gradients against torch
+    on the bf16-rounded input, at the three supported widths; the trainer-level path is covered by the parity tests."""
+    from tartangan_b200 import ops
+    import tartangan_b200 as tb
+    tb.set_precision('bf16')
+    torch.manual_seed(11)
+    for cin, n, hw in ((16, 3, 24), (8, 2, 16), (32, 2, 12)):
+        a = (torch.randn(n, cin, hw, hw) * 0.7).bfloat16().float()
+        w = (torch.randn(3, cin, 1, 1) / math.sqrt(cin)).requires_grad_()
+        b = (torch.randn(3) * 0.1).requires_grad_()
+        ar = a.clone().requires_grad_()
+        y = torch.tanh(F.conv2d(ar, w, b))
+        g = torch.randn_like(y)
+        ga, gw, gb = torch.autograd.grad(y, (ar, w, b), g)
+        ad = ops.to_internal(a.cuda()).requires_grad_()
+        wd, bd = w.detach().cuda().requires_grad_(), b.detach().cuda().requires_grad_()
+        yd = ops.RgbHeadFn.apply(ad, wd, bd)
+        assert yd.dtype == torch.float32 and yd.is_contiguous() and yd.shape == y.shape
+        assert float((yd.cpu() - y).abs().max()) < 2e-5
+        gad, gwd, gbd = torch.autograd.grad(yd, (ad, wd, bd), g.cuda())
+        assert rel_l2(gad.float().cpu(), ga) < 1e-2           # bf16 output
+        assert rel_l2(gwd.cpu(), gw) < 2e-4 and rel_l2(gbd.cpu(), gb) < 2e-4
