@@ -21,8 +21,11 @@ template <class Op> struct ChanV<bf16, Op> { static constexpr int value = OpBf16
 //   template <int V> __device__ void acc(const float* v /*NIN*/, int j, const P<V>&, float* a /*NACC*/) const;
 template <typename T, int V, class Op>
 __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, int C, double* __restrict__ out) {
-  extern __shared__ float s_acc[];   // [NACC][C]
-  for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) s_acc[i] = 0.f;
+  // block-level accumulators in DOUBLE: the warps add their partial sums with shared-memory atomics in arrival order; in
+  // fp32 that order changed the statistics in the 7th digit from run to run, enough to flip a LeakyReLU mask now and then
+  // (a rare, box-dependent 1 % deviation of a small gradient tensor in the fp32 parity tests); in fp64 it cannot
+  extern __shared__ double s_acc[];   // [NACC][C]
+  for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) s_acc[i] = 0.0;
   __syncthreads();
   const int groups = C / V;
   const int rpi = blockDim.x / groups;           // rows per block iteration
@@ -101,10 +104,10 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, long long M, in
 #pragma unroll
     for (int k = 0; k < Op::NACC; ++k)
 #pragma unroll
-      for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + g * V + j], a[k][j]);
+      for (int j = 0; j < V; ++j) atomicAdd(&s_acc[k * C + g * V + j], (double)a[k][j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], (double)s_acc[i]);
+  for (int i = threadIdx.x; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], s_acc[i]);
 }
 
 
@@ -208,9 +211,9 @@ __global__ void __launch_bounds__(CB_THREADS) chan_reduce_bulk_kernel(Op op, lon
   uint8_t* ring = cb_smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16);
   uint64_t* empty = full + CB_STAGES;
-  float* s_acc = reinterpret_cast<float*>(empty + CB_STAGES);          // [NACC][C]
+  double* s_acc = reinterpret_cast<double*>(empty + CB_STAGES);        // [NACC][C] (double: see chan_reduce_kernel)
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < Op::NACC * C; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = tid; i < Op::NACC * C; i += blockDim.x) s_acc[i] = 0.0;
   if (tid == 0) {
     for (int i = 0; i < CB_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 8); }
     mbar_fence_init();
@@ -273,11 +276,11 @@ __global__ void __launch_bounds__(CB_THREADS) chan_reduce_bulk_kernel(Op op, lon
 #pragma unroll
       for (int k = 0; k < Op::NACC; ++k)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[k * C + g * 8 + j], a[k][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[k * C + g * 8 + j], (double)a[k][j]);
     }
   }
   __syncthreads();
-  for (int i = tid; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], (double)s_acc[i]);
+  for (int i = tid; i < Op::NACC * C; i += blockDim.x) atomicAdd(&out[i], s_acc[i]);
 }
 
 static int g_chan_bulk = 1;      // development switch (ttg_set_chan_bulk)
@@ -351,8 +354,8 @@ __global__ void __launch_bounds__(256) chan_map_c3_kernel(Op op, long long ngrou
 template <typename T, class Op>
 __global__ void __launch_bounds__(256) chan_reduce_c3_kernel(Op op, long long ngroups, double* __restrict__ out) {
   constexpr int VN = Vec<T>::N, G = 3 * VN;
-  __shared__ float s_acc[Op::NACC * 3];
-  if (threadIdx.x < Op::NACC * 3) s_acc[threadIdx.x] = 0.f;
+  __shared__ double s_acc[Op::NACC * 3];
+  if (threadIdx.x < Op::NACC * 3) s_acc[threadIdx.x] = 0.0;
   __syncthreads();
   typename Op::template P<1> prm[3];
 #pragma unroll
@@ -383,10 +386,10 @@ __global__ void __launch_bounds__(256) chan_reduce_c3_kernel(Op op, long long ng
     for (int k = 0; k < Op::NACC; ++k) {
       float t = a[c][k];
       for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[k * 3 + c], t);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[k * 3 + c], (double)t);
     }
   __syncthreads();
-  if (threadIdx.x < Op::NACC * 3) atomicAdd(&out[threadIdx.x], (double)s_acc[threadIdx.x]);
+  if (threadIdx.x < Op::NACC * 3) atomicAdd(&out[threadIdx.x], s_acc[threadIdx.x]);
 }
 template <typename T> static inline bool c3_ok(int C, const void* const* ptrs, int nptr, long long n) {
   static const bool off = getenv("TTG_NO_C3") != nullptr;       // development A/B switch
@@ -411,7 +414,7 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
   if constexpr (std::is_same<T, bf16>::value) {
     if (cb_ok<T, Op>(C, ptrs, Op::NIN, M * C)) {
       const long long nvec = M * C / 8, nchunks = (nvec + CB_UNITS - 1) / CB_UNITS;
-      const size_t bsmem = (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16 + 2 * CB_STAGES * 8 + sizeof(float) * Op::NACC * C;
+      const size_t bsmem = (size_t)CB_STAGES * Op::NIN * CB_UNITS * 16 + 2 * CB_STAGES * 8 + sizeof(double) * Op::NACC * C;
       int err = 0;
       const int grid = cb_grid(chan_reduce_bulk_kernel<Op>, nchunks, bsmem, &err);
       if (err) return ttg_set_error(TTG_ERR_CUDA, "%s: shared memory attribute", name);
@@ -420,7 +423,7 @@ static int launch_chan_reduce(const char* name, Op op, long long M, int C, doubl
       return TTG_OK;
     }
   }
-  size_t smem = sizeof(float) * Op::NACC * C;
+  size_t smem = sizeof(double) * Op::NACC * C;
   constexpr int VV = ChanV<T, Op>::value;
   if (ttg_vec_ok<T>(C, ptrs, Op::NIN, VV) && C / VV <= 256) {
     constexpr int V = VV;
