@@ -142,6 +142,9 @@ class skip_branch:
     def __enter__(self):
         if self.side is not None:
             self.side.wait_stream(self.cur)
+            if torch.is_grad_enabled():            # its backward (and that of the branch point) runs there too
+                state.pending_streams.add(self.side)
+                state.pending_streams.add(self.cur)
             for t in self.inputs:
                 t.record_stream(self.side)
             self._ctx = torch.cuda.stream(self.side)
@@ -160,21 +163,25 @@ class skip_branch:
         return out
 
 
-def join_all_streams():
+def join_all_streams(clear=True):
     """The launching stream waits for EVERY stream that may hold contributions to `.grad` or unfinished parts of the
-    step (the weight-gradient stream, the D(fake) stream).  Called when a backward pass ends and before a gradient
-    all-reduce: the in-place kernels return no tensor to autograd, so the engine inserts no synchronisation for them
-    (and a CUDA-graph capture must not end with unjoined work)."""
+    step: the weight-gradient stream, the D(fake) stream, the early-G stream, the skip-branch companions and the stream
+    that called backward (`state.pending_streams`).  Called when a backward pass ends (clear=True) and, by the
+    data-parallel hooks, before every gradient all-reduce (clear=False: later buckets must wait for the same streams).
+    The in-place kernels return no tensor to autograd, so the engine inserts no synchronisation for them; and a hook
+    runs on whichever chain's stream finished last on the HOST, which says nothing about the other chains' kernels."""
     if not state.wgrad_pending and not state.pending_streams:
         return                                    # (nothing forked: also the CPU-only host-logic tests)
     cur = torch.cuda.current_stream()
     if state.wgrad_pending:
         cur.wait_stream(state.wgrad_stream)
-        state.wgrad_pending = False
+        if clear:
+            state.wgrad_pending = False
     for st in list(state.pending_streams):
         if st != cur:
             cur.wait_stream(st)
-    state.pending_streams.clear()
+    if clear:
+        state.pending_streams.clear()
 
 
 class direct_param_grads:

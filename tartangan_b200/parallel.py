@@ -71,7 +71,7 @@ class BucketedAllReduce:
         ordered after the launching stream only, must wait for them too."""
         if torch.cuda.is_available():
             from . import ops
-            ops.join_all_streams()
+            ops.join_all_streams(clear=False)
 
     def begin(self):
         """Arm the hooks for one backward pass."""

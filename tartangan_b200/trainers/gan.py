@@ -140,6 +140,8 @@ class GanTrainer(Trainer):
     def _backward(self, loss, optimizer, overlap=True):
         """loss.backward(); in data parallel the loss is scaled by 1/world so the SUMMED gradients are the
         global-batch average, and (eager mode) the exchange is overlapped with the rest of backward."""
+        if loss.is_cuda and ops.state.pending_streams:
+            ops.state.pending_streams.add(torch.cuda.current_stream())     # (a bucket hook may run on another chain's stream)
         if self.world_size == 1:
             with ops.direct_param_grads():      # conv / BatchNorm parameter gradients land in the flat .grad buffer
                 loss.backward()
@@ -408,6 +410,8 @@ class GanTrainer(Trainer):
             # process, e.g. the test suite).  Collect before, keep the collector off while capturing.
             import gc
             gc.collect()
+            ops.state.pending_streams.clear()      # (streams forked outside this capture must not be waited on inside it)
+            ops.state.wgrad_pending = False
             was_enabled = gc.isenabled()
             gc.disable()
             try:
