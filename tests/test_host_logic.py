@@ -27,6 +27,34 @@ def test_header_and_library_agree():
     assert set(protos) <= exported, set(protos) - exported
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: include/ttg_b200.h compiles as strict C99 (no C++ / torch types in the signatures), a
+    C program that takes the address of EVERY declared entry point links against the library, and the calls that need
+    no device (version, error string) work from C."""
+    from tartangan_b200 import _lib
+    names = sorted(_lib.parse_header())
+    src = tmp_path / 'abi.c'
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "ttg_b200.h"\n'
+                   'typedef void (*fn)(void);\n'
+                   'static fn table[] = {' + ', '.join(f'(fn){n}' for n in names) + '};\n'
+                   'int main(void) {\n'
+                   '  size_t i, n = sizeof table / sizeof table[0];\n'
+                   '  for (i = 0; i < n; ++i) if (!table[i]) return 2;\n'
+                   '  if (ttg_version() < 100) return 3;\n'
+                   '  if (!ttg_last_error()) return 4;\n'
+                   '  printf("%d symbols\\n", (int)n);\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / 'abi'
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror',
+                        '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe), '-L', lib_dir, '-lttg_b200',
+                        f'-Wl,-rpath,{lib_dir}'], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.strip() == f'{len(names)} symbols'
+
+
 def _build(kind, g):
     from tartangan_b200.models import pluggan
     from tartangan_b200.models.blocks import (DiscriminatorOutput, GeneratorInputMLP, GeneratorOutput,
