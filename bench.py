@@ -19,6 +19,13 @@ import sys
 import threading
 import time
 
+if '--impl=reference' in sys.argv or ('--impl' in sys.argv and 'reference' in sys.argv):
+    # The CPU arm is to use every host core.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers when the
+    # variable is unset (the driver launches both arms through it for N > 1); torch.set_num_threads() after the OpenMP
+    # runtime has started does not undo that for the autograd worker threads (measured here: 4.6 instead of 20-27
+    # images/s on 8 cores).  Only rank 0 computes on this arm, so it takes all cores; set before torch is imported.
+    os.environ['OMP_NUM_THREADS'] = os.environ['MKL_NUM_THREADS'] = str(os.cpu_count() or 1)
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
