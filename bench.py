@@ -176,6 +176,7 @@ def run_reference(args):
                            f'--warmup {args.warmup} clamped to {steps} / {warmup} and the batch to {batch} images so the '
                            'run stays within minutes; images/sec is per image, so the batch size does not scale it'},
         'cpu_baseline': {'value': val, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
+                         'omp_num_threads': os.environ.get('OMP_NUM_THREADS'),
                          'sample': f'{steps} train steps of batch {batch} (of the 256/GPU workload), torch CPU fp32'},
         'e2e': {'value': val, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }

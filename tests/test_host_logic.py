@@ -225,10 +225,14 @@ def test_data_parallel_with_in_place_parameter_gradients(tmp_path):
 
 
 def test_bench_reference_arm_prints_contract_line():
+    # launched the way torch.distributed.run launches a worker of an N > 1 job: OMP_NUM_THREADS=1 in the environment,
+    # which the CPU arm must override (it is to use every host core; rank 0 alone computes)
+    env = dict(os.environ, OMP_NUM_THREADS='1', RANK='0', WORLD_SIZE='2', LOCAL_RANK='0')
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
-                        '--warmup', '1'], capture_output=True, text=True, timeout=600)
+                        '--warmup', '1'], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['cpu_baseline']['omp_num_threads'] == str(os.cpu_count()) == str(line['cpu_baseline']['cores'])
     assert line['impl'] == 'reference' and line['unit'] == 'images/sec' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0
 
