@@ -310,7 +310,11 @@ class GanTrainer(Trainer):
         z, tau, tau, z, tau) into pinned buffers and copy them, with the images, into the static device
         buffers the graphs read.  part: None = everything; 'first' = z0 and the image copy only, 'rest' = the
         remaining draws (TTG_EARLY_GEN=1: the generator-sample graph, which reads only z0, is launched between
-        the two parts so that the other CPU draws overlap it; same draw order, off by default until measured)."""
+        the two parts so that the other CPU draws overlap it, and the image copy is issued before any draw; same
+        draw order.  Measured at the end of round 2, `profiles/r2_bench_1gpu_split_staging.log`: 12.59 ms / step,
+        end to end 18 573 images/s against 18 700 without it - no gain, the ~1.1 ms between the device-timed and
+        the end-to-end step is the 50.9 MB pinned H2D copy in front of D(real), not the ~1 ms of CPU draws; off by
+        default)."""
         st = self._st
         b, nq = self.args.batch_size, (self.d.to_output.iqn.num_quantiles if st['tau'] else 0)
         order = ['z0'] + (['t0', 't1'] if st['tau'] else []) + ['z1'] + (['t2'] if st['tau'] else [])
@@ -327,6 +331,15 @@ class GanTrainer(Trainer):
             if ev is not None:
                 ev.synchronize()
         slot = st['slot']
+        if part == 'first' and getattr(self, '_copy_stream', None) is not None:
+            # split staging: the image batch starts travelling BEFORE the CPU draws (~1 ms per step at the headline
+            # size), which then overlap the copy instead of preceding it
+            cs = self._copy_stream
+            cs.wait_stream(torch.cuda.current_stream())   # the previous step may still be reading the static buffer
+            with torch.cuda.stream(cs):
+                st['imgs'].copy_(imgs, non_blocking=True)
+                self._imgs_ready.record(cs)
+            imgs = None
         for key in order:
             i = int(key[1])
             if key[0] == 'z':
@@ -339,7 +352,7 @@ class GanTrainer(Trainer):
             ev = st['pin_done'][slot] or torch.cuda.Event()
             ev.record()
             st['pin_done'][slot] = ev
-        if part == 'rest':
+        if part == 'rest' or imgs is None:
             return                                        # the images went with the first part
         cs = getattr(self, '_copy_stream', None)
         if cs is None:
