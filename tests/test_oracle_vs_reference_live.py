@@ -1,0 +1,129 @@
+"""Pins the CPU oracle to the LIVE reference at the NAMED configurations (build container only: needs /root/reference).
+
+tests/golden/*.pt pin the oracle at tiny custom widths; the GPU parity tests use it as the checker at the reference's
+own configs ('32', '64', '128', attention configs).  Here the unmodified reference trainers
+(/root/reference/tartangan/trainers/{cnn,iqn}.py: build_models + train_batch) and the oracle start from the same
+state dicts, see the same images and the same CPU random stream, and must agree on every loss of two steps and on
+every parameter / buffer afterwards (torch CPU fp32 on both sides; measured in the build container: bit-identical
+losses and parameters at config '128').  Also pins the oracle's
+table of configurations to models/pluggan.py GAN_CONFIGS.  CPU only; skipped where the reference tree is absent.
+"""
+import argparse
+import contextlib
+import importlib
+import io
+import os
+import sys
+import types
+import warnings
+
+import pytest
+import torch
+
+from oracle import tartan_oracle as O
+
+pytestmark = pytest.mark.skipif(not os.path.isdir('/root/reference/tartangan'),
+                                reason='needs the reference tree (build container only)')
+
+
+@contextlib.contextmanager
+def _reference():
+    """The real `tartangan` package, imported with the three shims of SURVEY.md Appendix C, isolated from the
+    install_as_tartangan aliases other tests may have left in sys.modules."""
+    sys.path.insert(0, '/root/reference')
+    added = []
+    for name, attrs in (('smart_open', dict(open=open)),
+                        ('boto3', dict(resource=lambda *a, **k: None, client=lambda *a, **k: None))):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            added.append(name)
+    import tqdm._utils
+    if not hasattr(tqdm._utils, '_unicode'):
+        tqdm._utils._unicode = str
+    aside = {k: sys.modules.pop(k) for k in list(sys.modules) if k == 'tartangan' or k.startswith('tartangan.')}
+    try:
+        yield (importlib.import_module('tartangan.models.pluggan'), importlib.import_module('tartangan.trainers.cnn'),
+               importlib.import_module('tartangan.trainers.iqn'))
+    finally:
+        sys.path.remove('/root/reference')
+        for k in [k for k in sys.modules if k == 'tartangan' or k.startswith('tartangan.')]:
+            del sys.modules[k]
+        sys.modules.update(aside)
+        for name in added:
+            sys.modules.pop(name, None)
+
+
+def _reference_trainer(kind, cnn, iqn, config, batch, extra=()):
+    mod = cnn if kind == 'cnn' else iqn
+    cls = mod.CNNTrainer if kind == 'cnn' else mod.IQNTrainer
+    p = argparse.ArgumentParser()
+    cls.add_args_to_parser(p)
+    for cc in cls.get_component_classes(p.parse_known_args(['/unused'])[0]):
+        cc.add_args_to_parser(p)
+    args = p.parse_args(['/unused', '--batch-size', str(batch), '--config', config] + list(extra))
+    args.device = 'cpu'
+    t = cls.__new__(cls)
+    t.args, t.steps, t.epoch = args, 0, 1
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        t.build_models()
+    return t
+
+
+def _sd(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def test_config_table_matches_reference():
+    with _reference() as (pluggan, _, _):
+        ref = dict(pluggan.GAN_CONFIGS)
+    for key, spec in O.SPECS.items():
+        assert key in ref, key
+        c = ref[key]
+        assert (c.base_size, c.latent_dims, c.data_dims, tuple(c.blocks), tuple(c.attention)) == tuple(spec), key
+        assert c.num_blocks_per_scale == 1, key          # what the oracle's builders assume
+    # every configuration BASELINE.json / SURVEY 8d names is in the oracle's table
+    for key in ('64', '128', '256', '512', '512thin'):
+        assert key in O.SPECS
+
+
+@pytest.mark.parametrize('kind,config,batch,extra', [
+    ('cnn', '64', 2, ()),                       # C1 (cnn '64')
+    ('iqn', '64', 2, ()),                       # C2
+    ('iqn', '128', 2, ()),                      # C3, the benchmarked configuration
+    ('iqn', '32', 3, ('--norm', 'id')),         # the multi-GPU parity worker's configuration, identity norm
+    ('cnn', '32', 2, ('--activation', 'elu')),
+    ('iqn', '32', 2, ('--g-base', 'tiledz')),
+])
+def test_oracle_tracks_live_reference(kind, config, batch, extra):
+    opts = dict(zip(extra[::2], extra[1::2]))
+    with _reference() as (pluggan, cnn, iqn):
+        t = _reference_trainer(kind, cnn, iqn, config, batch, extra)
+        size = t.g.max_size
+        orc = O.OracleTrainer(kind, O.SPECS[config], _sd(t.g), _sd(t.target_g), _sd(t.d), batch,
+                              norm=opts.get('--norm', 'bn'), g_base=opts.get('--g-base', 'mlp'),
+                              activation=opts.get('--activation', 'relu'))
+        for step in range(2):
+            imgs = O.tartan_batch(4321 + step, batch, size)
+            torch.manual_seed(900 + step)
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                ref = t.train_batch(imgs)
+            torch.manual_seed(900 + step)
+            got = orc.train_batch(imgs)
+            for k in ref:
+                assert abs(float(got[k]) - float(ref[k])) <= 1e-6 * max(1.0, abs(float(ref[k]))), (step, k, got[k], ref[k])
+        for name, mod, state in (('g', t.g, orc.g), ('target_g', t.target_g, orc.target_g), ('d', t.d, orc.d)):
+            for k, v in mod.state_dict().items():
+                o = state[k].detach()
+                if v.dtype.is_floating_point:
+                    # Adam(beta1 = 0) moves every element by ~lr * sign(g): rounding-level differences of a gradient
+                    # near zero can flip one element by 2 lr; everything else agrees to rounding
+                    diff = (o - v).abs()
+                    lr = 4e-4 if name == 'd' else 1e-4
+                    loose = diff > 1e-5 + 1e-4 * v.abs()
+                    assert float(loose.float().mean()) <= 2e-3 and float(diff.max()) <= 4.1 * lr, (name, k, float(diff.max()))
+                else:
+                    assert torch.equal(o, v), (name, k)
