@@ -96,16 +96,32 @@ def test_config_table_matches_reference():
     ('iqn', '32', 3, ('--norm', 'id')),         # the multi-GPU parity worker's configuration, identity norm
     ('cnn', '32', 2, ('--activation', 'elu')),
     ('iqn', '32', 2, ('--g-base', 'tiledz')),
+    ('cnn', '256+attention', 2, ()),            # C4: cnn '256' with attention=(3,), gamma set to 0.5
+    ('iqn', '512thin+nq64', 2, ()),             # C5: iqn '512thin' (native attention=(3,)), 64 quantiles, gamma 0.5
 ])
 def test_oracle_tracks_live_reference(kind, config, batch, extra):
     opts = dict(zip(extra[::2], extra[1::2]))
+    config, _, variant = config.partition('+')
     with _reference() as (pluggan, cnn, iqn):
+        spec, nq, steps = O.SPECS[config], O.NUM_QUANTILES, 2
+        if variant == 'attention':
+            spec = spec._replace(attention=(3,))
+            pluggan.GAN_CONFIGS[config + 'sa'] = pluggan.GAN_CONFIGS[config]._replace(attention=(3,))
+            config = config + 'sa'
         t = _reference_trainer(kind, cnn, iqn, config, batch, extra)
+        if variant:
+            steps = 1                           # (256 / 512 pixel images on host cores)
+            with torch.no_grad():               # gamma initialises to 0 (attention.py:19): make the attention matter
+                for m in list(t.g.modules()) + list(t.target_g.modules()) + list(t.d.modules()):
+                    if hasattr(m, 'gamma'):
+                        m.gamma.fill_(0.5)
+        if variant == 'nq64':
+            nq = t.d.to_output.iqn.num_quantiles = 64
         size = t.g.max_size
-        orc = O.OracleTrainer(kind, O.SPECS[config], _sd(t.g), _sd(t.target_g), _sd(t.d), batch,
+        orc = O.OracleTrainer(kind, spec, _sd(t.g), _sd(t.target_g), _sd(t.d), batch,
                               norm=opts.get('--norm', 'bn'), g_base=opts.get('--g-base', 'mlp'),
-                              activation=opts.get('--activation', 'relu'))
-        for step in range(2):
+                              activation=opts.get('--activation', 'relu'), num_quantiles=nq)
+        for step in range(steps):
             imgs = O.tartan_batch(4321 + step, batch, size)
             torch.manual_seed(900 + step)
             with warnings.catch_warnings():
