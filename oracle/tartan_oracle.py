@@ -12,8 +12,12 @@ stock-PyTorch bar ``tools/bench_eager_gpu.py``, which runs THIS composition on
 Parity status: PINNED against outputs of the reference itself, run in the build
 container (``tools/make_golden.py`` imports ``/root/reference`` read-only and
 writes ``tests/golden/*.pt``; ``tests/test_oracle_golden.py`` replays them).
+At the reference's NAMED configurations (cnn '64', iqn '64', iqn '128', the
+attention configs) ``tests/test_oracle_vs_reference_live.py`` runs the
+unmodified reference trainers beside this file in the build container: same
+state, images and random stream -> bit-identical losses and parameters.
 The reference's own test-suite pins nothing on this path, so
-those generated vectors are the only pin there is.
+those two are the only pins there are.
 
 Reference locations restated here (all under /root/reference/tartangan):
   models/pluggan.py:18-28     GANConfig / scale_model        -> Spec, scaled()
