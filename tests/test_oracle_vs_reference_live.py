@@ -98,13 +98,14 @@ def test_config_table_matches_reference():
     ('iqn', '32', 2, ('--g-base', 'tiledz')),
     ('cnn', '256+attention', 2, ()),            # C4: cnn '256' with attention=(3,), gamma set to 0.5
     ('iqn', '512thin+nq64', 2, ()),             # C5: iqn '512thin' (native attention=(3,)), 64 quantiles, gamma 0.5
+    ('iqn', '512+attention+nq64', 1, ()),       # C5: iqn '512' with attention=(3,), 64 quantiles
 ])
 def test_oracle_tracks_live_reference(kind, config, batch, extra):
     opts = dict(zip(extra[::2], extra[1::2]))
-    config, _, variant = config.partition('+')
+    config, *variant = config.split('+')
     with _reference() as (pluggan, cnn, iqn):
         spec, nq, steps = O.SPECS[config], O.NUM_QUANTILES, 2
-        if variant == 'attention':
+        if 'attention' in variant:
             spec = spec._replace(attention=(3,))
             pluggan.GAN_CONFIGS[config + 'sa'] = pluggan.GAN_CONFIGS[config]._replace(attention=(3,))
             config = config + 'sa'
@@ -115,7 +116,7 @@ def test_oracle_tracks_live_reference(kind, config, batch, extra):
                 for m in list(t.g.modules()) + list(t.target_g.modules()) + list(t.d.modules()):
                     if hasattr(m, 'gamma'):
                         m.gamma.fill_(0.5)
-        if variant == 'nq64':
+        if 'nq64' in variant:
             nq = t.d.to_output.iqn.num_quantiles = 64
         size = t.g.max_size
         orc = O.OracleTrainer(kind, spec, _sd(t.g), _sd(t.target_g), _sd(t.d), batch,
