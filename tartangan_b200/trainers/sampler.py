@@ -27,7 +27,7 @@ def slerp_grid(top_left, top_right, bottom_left, bottom_right, nrows, ncols):
     for a in np.linspace(0, 1, nrows):
         left, right = slerp(a, tl, bl), slerp(a, tr, br)
         rows.append(np.vstack([slerp(b, left, right) for b in np.linspace(0, 1, ncols)]))
-    return torch.from_numpy(np.concatenate(rows, axis=0))
+    return torch.from_numpy(np.concatenate(rows, axis=0).astype(np.float32))      # (float32 like the reference's grid)
 
 
 class ImageSampler:

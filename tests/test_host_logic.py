@@ -7,6 +7,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -419,3 +420,24 @@ def test_inception_feature_wrapper_matches_reference():
         p_ref, l_ref = ref.WrapInception(net)(x)
         p, l = InceptionFeatures(net)(x)
     assert torch.allclose(p, p_ref, atol=1e-5, rtol=1e-4) and torch.allclose(l, l_ref, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/tartangan'), reason='needs the reference tree (build container only)')
+def test_slerp_grid_matches_reference():
+    """f-2: the 5x5 interpolation grid of the progress sampler against the reference's utils/slerp.py (loaded from its
+    file: numpy + torch only), incl. the parallel-corner (linear) branch; same dtype, values to float32 rounding."""
+    import importlib.util
+    from tartangan_b200.trainers.sampler import slerp, slerp_grid
+    spec = importlib.util.spec_from_file_location('_ref_slerp', '/root/reference/tartangan/utils/slerp.py')
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(3)
+    for latent, (nr, nc) in ((64, (5, 5)), (256, (5, 5)), (16, (3, 7))):
+        z = torch.randn(4, latent)
+        want = ref.slerp_grid(*[t for t in z], nr, nc)              # the reference passes CPU tensors (image_sampler.py:47-53)
+        got = slerp_grid(*[t.numpy() for t in z], nr, nc)
+        assert got.dtype == want.dtype == torch.float32 and got.shape == want.shape == (nr * nc, latent)
+        assert torch.allclose(got, want, atol=2e-6, rtol=1e-5)
+        assert torch.equal(got[0], z[0]) and torch.allclose(got[-1], z[3], atol=1e-6)
+    v = np.arange(1, 9, dtype=np.float32)
+    assert np.allclose(slerp(0.25, v, 2 * v), ref.slerp(0.25, v, 2 * v))         # omega = 0: LERP branch
