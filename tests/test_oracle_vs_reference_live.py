@@ -1,4 +1,5 @@
-"""Pins the CPU oracle to the LIVE reference at the NAMED configurations (build container only: needs /root/reference).
+"""Pins the CPU oracle - and the command-line surface of the mirror trainers - to the LIVE reference at the NAMED
+configurations (build container only: needs /root/reference).
 
 tests/golden/*.pt pin the oracle at tiny custom widths; the GPU parity tests use it as the checker at the reference's
 own configs ('32', '64', '128', attention configs).  Here the unmodified reference trainers
@@ -144,3 +145,38 @@ def test_oracle_tracks_live_reference(kind, config, batch, extra):
                     assert float(loose.float().mean()) <= 2e-3 and float(diff.max()) <= 4.1 * lr, (name, k, float(diff.max()))
                 else:
                     assert torch.equal(o, v), (name, k)
+
+
+@pytest.mark.parametrize('kind', ['cnn', 'iqn'])
+def test_cli_surface_matches_reference(kind):
+    """every command-line flag of the reference trainers (trainer.py:271-313 plus the component flags,
+    e.g. model_checkpoint.py:110-117 and metrics/fid.py:51-59) exists here with the same default, and a reference
+    command line parses to the same values; flags added here are additive (not required)."""
+    from tartangan_b200.trainers.cnn import CNNTrainer
+    from tartangan_b200.trainers.iqn import IQNTrainer
+    ours_cls = CNNTrainer if kind == 'cnn' else IQNTrainer
+    ours = argparse.ArgumentParser()
+    ours_cls.add_args_to_parser(ours)
+    with _reference() as (_, cnn, iqn):
+        ref_cls = cnn.CNNTrainer if kind == 'cnn' else iqn.IQNTrainer
+        ref = argparse.ArgumentParser()
+        ref_cls.add_args_to_parser(ref)
+        for cc in ref_cls.get_component_classes(ref.parse_known_args(['/unused', '--fid'])[0]):
+            cc.add_args_to_parser(ref)
+        ref_actions = [a for a in ref._actions if a.dest != 'help']
+        line = ['/data/x.npz', '--batch-size', '32', '--config', '128', '--grad-penalty', '2.5', '--lr-g', '2e-4',
+                '--norm', 'id', '--activation', 'selu', '--g-base', 'tiledz', '--checkpoint-freq', '500',
+                '--resume-training-step', '1500', '--run-id', 'abc', '--quiet-logs', '--gen-freq', '50']
+        ref_ns = vars(ref.parse_args(line))
+    ours_by_dest = {a.dest: a for a in ours._actions}
+    for a in ref_actions:
+        assert a.dest in ours_by_dest, f'missing flag {a.option_strings or a.dest}'
+        b = ours_by_dest[a.dest]
+        assert set(a.option_strings) <= set(b.option_strings), (a.option_strings, b.option_strings)
+        assert a.default == b.default, (a.dest, a.default, b.default)
+        assert a.nargs == b.nargs and type(a).__name__ == type(b).__name__, a.dest
+    ours_ns = vars(ours.parse_args(line))
+    for k, v in ref_ns.items():
+        assert ours_ns[k] == v, (k, ours_ns[k], v)
+    extra = [a for a in ours._actions if a.dest not in {r.dest for r in ref_actions} and a.dest != 'help']
+    assert all(not a.required and a.option_strings for a in extra)        # additive, optional flags only
