@@ -78,7 +78,7 @@ class ResidualGeneratorBlock(nn.Module):
 class GeneratorInputMLP(nn.Module):
     """generator.py:65-80: Linear(latent -> size^2*C) -> act -> view(B, C, size, size)."""
 
-    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None,
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=nn.BatchNorm1d,
                  activation_factory=functools.partial(LeakyReLU, 0.2)):
         super().__init__()
         self.base_img = nn.Sequential(Linear(latent_dims, size ** 2 * output_dims), native(activation_factory)())
@@ -92,7 +92,7 @@ class GeneratorInputMLP(nn.Module):
 class GeneratorInputMLP1d(nn.Module):
     """generator.py:83-98 (text trainer only): constructor kept for surface parity."""
 
-    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None,
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=nn.BatchNorm1d,
                  activation_factory=functools.partial(LeakyReLU, 0.2)):
         super().__init__()
         self.base = nn.Sequential(Linear(latent_dims, size * output_dims), native(activation_factory)())
@@ -105,7 +105,7 @@ class GeneratorInputMLP1d(nn.Module):
 class TiledZGeneratorInput(nn.Module):
     """generator.py:101-112: z tiled over a size x size grid (requires latent_dims == output_dims)."""
 
-    def __init__(self, latent_dims, output_dims, size=4, norm_factory=None, **_):
+    def __init__(self, latent_dims, output_dims, size=4, norm_factory=nn.BatchNorm2d, **_):
         super().__init__()
         self.size = size
         assert latent_dims == output_dims

@@ -15,7 +15,7 @@ from .layers import Linear
 class CosineQuantileEmbedding(nn.Module):
     """iqn.py:27-46.  `activation` must be tanh (the fused kernel's embedding activation)."""
 
-    def __init__(self, state_dims, embedding_dims=64, activation=nn.Tanh, norm_factory=None):
+    def __init__(self, state_dims, embedding_dims=64, activation=nn.Tanh, norm_factory=nn.BatchNorm1d):
         super().__init__()
         if activation not in (nn.Tanh,) and getattr(activation, '__name__', '') != 'Tanh':
             raise NotImplementedError('CosineQuantileEmbedding: only the tanh activation has a kernel')
@@ -38,7 +38,7 @@ class IQN(nn.Module):
     """iqn.py:76-108.  num_quantiles=8, quantile_dims=20, mix='mult'."""
 
     def __init__(self, feature_dims, quantile_dims=20, num_quantiles=8, mix='mult',
-                 quantile_embedding_factory=CosineQuantileEmbedding, norm_factory=None):
+                 quantile_embedding_factory=CosineQuantileEmbedding, norm_factory=nn.BatchNorm1d):
         super().__init__()
         if not mix.startswith('mult'):
             raise NotImplementedError("IQN: only mix='mult' (the reference default) has a kernel")

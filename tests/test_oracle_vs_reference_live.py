@@ -180,3 +180,52 @@ def test_cli_surface_matches_reference(kind):
         assert ours_ns[k] == v, (k, ours_ns[k], v)
     extra = [a for a in ours._actions if a.dest not in {r.dest for r in ref_actions} and a.dest != 'help']
     assert all(not a.required and a.option_strings for a in extra)        # additive, optional flags only
+
+
+def _signature(f):
+    import functools
+    import inspect
+
+    def default(d):
+        if d is inspect.Parameter.empty:
+            return '<required>'
+        if isinstance(d, functools.partial):
+            return ('partial', d.func.__name__, d.args, tuple(sorted(d.keywords.items())))
+        return getattr(d, '__name__', None) or repr(d)          # classes / functions compare by name
+    return [(n, p.kind.name, default(p.default)) for n, p in inspect.signature(f).parameters.items()]
+
+
+def test_module_constructor_signatures_match_reference():
+    """SURVEY 8b, "same constructor signatures and defaults": every class / function of the Python-level contract
+    (models.pluggan, models.blocks, models.iqn, models.losses) takes the reference's parameters, in its order, with
+    its defaults (factory defaults compared by class name: the mirror's BatchNorm2d / Conv2d are kernel-backed
+    subclasses of the torch.nn classes the reference names), and GAN_CONFIGS is the same table."""
+    import tartangan_b200.models.blocks as ob
+    import tartangan_b200.models.iqn as oi
+    import tartangan_b200.models.losses as ol
+    import tartangan_b200.models.pluggan as op
+    names = {
+        'pluggan': ['GANConfig', 'BlockModel', 'Generator', 'Discriminator', 'IQNDiscriminator'],
+        'blocks': ['ResidualGeneratorBlock', 'ResidualDiscriminatorBlock', 'GeneratorBlock', 'DiscriminatorBlock',
+                   'GeneratorInputMLP', 'TiledZGeneratorInput', 'GeneratorOutput', 'DiscriminatorInput',
+                   'DiscriminatorOutput', 'IQNDiscriminatorOutput', 'SelfAttention2d'],
+        'iqn': ['IQN', 'CosineQuantileEmbedding', 'iqn_loss'],
+        'losses': ['gradient_penalty'],
+    }
+    ours = dict(pluggan=op, blocks=ob, iqn=oi, losses=ol)
+    with _reference() as (rp, _, _):
+        ref = dict(pluggan=rp, blocks=importlib.import_module('tartangan.models.blocks'),
+                   iqn=importlib.import_module('tartangan.models.iqn'),
+                   losses=importlib.import_module('tartangan.models.losses'))
+        checked = 0
+        for mod, members in names.items():
+            for n in members:
+                r, o = getattr(ref[mod], n), getattr(ours[mod], n)
+                assert _signature(r) == _signature(o), (mod, n, _signature(r), _signature(o))
+                if isinstance(r, type) and 'forward' in vars(r):
+                    assert _signature(r.forward) == _signature(o.forward), (mod, n, 'forward')
+                checked += 1
+        assert checked == 20
+        assert set(rp.GAN_CONFIGS) <= set(op.GAN_CONFIGS)
+        for k, c in rp.GAN_CONFIGS.items():
+            assert tuple(c) == tuple(op.GAN_CONFIGS[k]), k
