@@ -229,3 +229,22 @@ def test_module_constructor_signatures_match_reference():
         assert set(rp.GAN_CONFIGS) <= set(op.GAN_CONFIGS)
         for k, c in rp.GAN_CONFIGS.items():
             assert tuple(c) == tuple(op.GAN_CONFIGS[k]), k
+
+
+@pytest.mark.parametrize('kind', ['cnn', 'iqn'])
+def test_trainer_method_surface_matches_reference(kind):
+    """the trainer methods a caller of the reference uses exist here and accept the reference's arguments
+    (parameters added here are optional and come last)."""
+    from tartangan_b200.trainers import cnn as oc, iqn as oi
+    ours = oc.CNNTrainer if kind == 'cnn' else oi.IQNTrainer
+    contract = ['create_from_cli', 'add_args_to_parser', 'get_component_classes', 'train', 'build_models', 'train_batch',
+                'prepare_dataset', 'sample_z', 'sample_g', 'make_adversarial_batch', 'make_generator_batch',
+                'update_target_generator', 'init_params_selu', 'get_state', 'set_state']
+    with _reference() as (_, cnn, iqn):
+        ref = cnn.CNNTrainer if kind == 'cnn' else iqn.IQNTrainer
+        ref_mod = cnn if kind == 'cnn' else iqn
+        assert callable(ref_mod.main) and callable((oc if kind == 'cnn' else oi).main)
+        for n in contract:
+            a, b = _signature(getattr(ref, n)), _signature(getattr(ours, n))
+            assert b[:len(a)] == a, (n, a, b)
+            assert all(d != '<required>' for _, _, d in b[len(a):]), (n, b)
