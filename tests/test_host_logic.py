@@ -441,3 +441,27 @@ def test_slerp_grid_matches_reference():
         assert torch.equal(got[0], z[0]) and torch.allclose(got[-1], z[3], atol=1e-6)
     v = np.arange(1, 9, dtype=np.float32)
     assert np.allclose(slerp(0.25, v, 2 * v), ref.slerp(0.25, v, 2 * v))         # omega = 0: LERP branch
+
+
+def test_npz_dataset_matches_the_reference_transform_pipeline(tmp_path):
+    """f-3 (host side): NpzImageDataset against the transform stack the reference builds for .npz data
+    (trainers/trainer.py:68-74: ToPILImage -> RandomCrop -> ToTensor -> Normalize(0.5, 0.5)) with torchvision itself:
+    bit-identical pixels for every byte value (crop size = image size: no draw), and a cropped item is one of the
+    windows of the image."""
+    from torchvision import transforms
+    from tartangan_b200.trainers.trainer import NpzImageDataset
+    rng = np.random.RandomState(0)
+    imgs = rng.randint(0, 256, size=(6, 16, 16, 3), dtype=np.uint8)
+    imgs[0] = np.arange(768, dtype=np.uint32).reshape(16, 16, 3) % 256          # every byte value occurs
+    np.savez(tmp_path / 'd.npz', images=imgs)
+    ds = NpzImageDataset(str(tmp_path / 'd.npz'), 16)
+    ref = transforms.Compose([transforms.ToPILImage(), transforms.RandomCrop(16), transforms.ToTensor(),
+                              transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+    assert len(ds) == 6
+    for i in range(6):
+        assert torch.equal(ds[i], ref(imgs[i])), i
+    small = NpzImageDataset(str(tmp_path / 'd.npz'), 8)
+    full = ref(imgs[2])
+    item = small[2]
+    assert item.shape == (3, 8, 8)
+    assert any(torch.equal(item, full[:, y:y + 8, x:x + 8]) for y in range(9) for x in range(9))
