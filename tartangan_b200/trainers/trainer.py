@@ -58,7 +58,9 @@ def tartan_batch(seed, batch, size):
 
 class NpzImageDataset(torch.utils.data.Dataset):
     """uint8 image stack stored in an .npz (key 'images' or first array), random-cropped to the
-    generator's output size and mapped to [-1, 1] (contract of image_bytes_dataset.py:44-49)."""
+    generator's output size and mapped to [-1, 1] (contract of image_bytes_dataset.py:44-49).  The crop origin comes
+    from Python's `random` module, row offset first: what RandomCrop does in torchvision 0.5.0, the version the
+    reference pins (requirements.txt:7); torchvision >= 0.8 draws it from torch's global generator instead."""
 
     def __init__(self, path, size):
         data = np.load(path)
