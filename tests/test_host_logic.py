@@ -434,7 +434,10 @@ def test_slerp_grid_matches_reference():
     torch.manual_seed(3)
     for latent, (nr, nc) in ((64, (5, 5)), (256, (5, 5)), (16, (3, 7))):
         z = torch.randn(4, latent)
-        want = ref.slerp_grid(*[t for t in z], nr, nc)              # the reference passes CPU tensors (image_sampler.py:47-53)
+        import warnings
+        with warnings.catch_warnings():         # (numpy 2 deprecation noise from np.dot on torch tensors)
+            warnings.simplefilter('ignore')
+            want = ref.slerp_grid(*[t for t in z], nr, nc)          # the reference passes CPU tensors (image_sampler.py:47-53)
         got = slerp_grid(*[t.numpy() for t in z], nr, nc)
         assert got.dtype == want.dtype == torch.float32 and got.shape == want.shape == (nr * nc, latent)
         assert torch.allclose(got, want, atol=2e-6, rtol=1e-5)
